@@ -1,0 +1,760 @@
+// Sampling engine: plan builder, U-Net executor, samplers and the C ABI (include/cfm_b200.h).
+//
+// The U-Net of AD/image_diffusion/unet.py:490-728 is lowered once, at cfm_engine_create, into
+// a flat list of ops over NHWC activation tensors that live in one arena (offsets assigned by
+// a liveness-based first-fit allocator).  An NFE is then a fixed sequence of kernel launches
+// with no host synchronisation, which is what makes whole-loop CUDA-graph capture possible.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include "engine.h"
+#include "kernels_generic.cuh"
+#include "steps.cuh"
+
+namespace cfm {
+
+static thread_local std::string g_create_error = "";
+
+#define CU_CHECK(e, call)                                                                     \
+  do {                                                                                        \
+    cudaError_t _st = (call);                                                                 \
+    if (_st != cudaSuccess) {                                                                 \
+      (e).err = std::string(#call) + ": " + cudaGetErrorString(_st);                          \
+      return CFM_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+static int fail(Engine& e, int code, const std::string& msg) { e.err = msg; return code; }
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+static int fetch(Engine& e, const std::string& name, int64_t numel, const float** out) {
+  auto it = e.sd.find(name);
+  if (it == e.sd.end()) return fail(e, CFM_ERR_MISSING, "state_dict is missing '" + name + "'");
+  if (it->second.numel != numel)
+    return fail(e, CFM_ERR_MISSING, "state_dict tensor '" + name + "' has " + std::to_string(it->second.numel) +
+                                        " elements, expected " + std::to_string(numel));
+  *out = it->second.data;
+  e.param_count += numel;
+  return 0;
+}
+
+static int upload(Engine& e, const float* host, size_t n, float** dev) {
+  void* p = nullptr;
+  CU_CHECK(e, cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(float)));
+  e.owned.push_back(p);
+  CU_CHECK(e, cudaMemcpy(p, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  *dev = (float*)p;
+  return 0;
+}
+
+template <typename T>
+static int dev_alloc(Engine& e, size_t n, T** dev) {
+  void* p = nullptr;
+  CU_CHECK(e, cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  e.owned.push_back(p);
+  *dev = (T*)p;
+  return 0;
+}
+
+// OIHW [Cout][Cin][ks][ks] -> [(ky*ks+kx)*Cin + ci][Cout]
+static std::vector<float> to_kn(const float* w, int Cout, int Cin, int ks) {
+  std::vector<float> r((size_t)ks * ks * Cin * Cout);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < ks * ks; ++t)
+        r[((size_t)t * Cin + c) * Cout + o] = w[((size_t)o * Cin + c) * ks * ks + t];
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------
+struct Cur { int id; int C, H, W; };
+
+static int new_tensor(Engine& e, int C, int H, int W) {
+  TensorDesc t; t.C = C; t.H = H; t.W = W;
+  e.tensors.push_back(t);
+  return (int)e.tensors.size() - 1;
+}
+
+static int heads_for(const cfm_unet_config& c, int channels, bool upsample_side) {
+  if (c.num_head_channels != -1) return channels / c.num_head_channels;
+  if (upsample_side && c.num_heads_upsample != -1) return c.num_heads_upsample;
+  return c.num_heads;
+}
+
+// Adds a conv op; w given as state_dict names.  skip_name empty => no 1x1 skip operand.
+static int add_conv(Engine& e, const std::string& name, const std::string& wname, int ks, int stride, int ups,
+                    int src0, int src1, bool src_is_input, int Cin, int Hin, int Win, int Cout,
+                    const std::string& skip_wname, int skip0, int skip1, int Cskip,
+                    int res0, int res1, int emb_off, int out, bool out_is_output) {
+  Op op; op.kind = OP_CONV; op.name = name;
+  op.ks = ks; op.stride = stride; op.ups = ups; op.src0 = src0; op.src1 = src1; op.src_is_input = src_is_input;
+  op.Cin = Cin; op.Hin = Hin; op.Win = Win; op.Cout = Cout;
+  const int Hv = ups ? Hin * 2 : Hin, Wv = ups ? Win * 2 : Win;
+  op.Hout = (Hv + 2 * (ks / 2) - ks) / stride + 1; op.Wout = (Wv + 2 * (ks / 2) - ks) / stride + 1;
+  op.skip0 = skip0; op.skip1 = skip1; op.Cskip = Cskip; op.res0 = res0; op.res1 = res1;
+  op.emb_off = emb_off; op.out = out; op.out_is_output = out_is_output;
+  const float *w = nullptr, *b = nullptr, *ws = nullptr, *bs = nullptr;
+  int rc;
+  if ((rc = fetch(e, wname + ".weight", (int64_t)Cout * Cin * ks * ks, &w))) return rc;
+  if ((rc = fetch(e, wname + ".bias", Cout, &b))) return rc;
+  std::vector<float> bias(b, b + Cout);
+  std::vector<float> wkn = to_kn(w, Cout, Cin, ks);
+  if ((rc = upload(e, wkn.data(), wkn.size(), &op.w_main))) return rc;
+  std::vector<float> w_oihw(w, w + (size_t)Cout * Cin * ks * ks), ws_oi;
+  if (!skip_wname.empty()) {
+    if ((rc = fetch(e, skip_wname + ".weight", (int64_t)Cout * Cskip, &ws))) return rc;
+    if ((rc = fetch(e, skip_wname + ".bias", Cout, &bs))) return rc;
+    for (int i = 0; i < Cout; ++i) bias[i] += bs[i];
+    std::vector<float> wskn = to_kn(ws, Cout, Cskip, 1);
+    if ((rc = upload(e, wskn.data(), wskn.size(), &op.w_skip))) return rc;
+    ws_oi.assign(ws, ws + (size_t)Cout * Cskip);
+  }
+  if ((rc = upload(e, bias.data(), bias.size(), &op.bias))) return rc;
+  op.flops = 2.0 * op.Hout * op.Wout * Cout * ((double)ks * ks * Cin + Cskip);
+  if (e.bf16 && tc_conv_supported(e, op)) {
+    if ((rc = tc_conv_prepare(e, op, w_oihw, ws_oi))) return rc;
+    e.n_tc_convs++;
+  }
+  e.ops.push_back(op);
+  return 0;
+}
+
+static int add_gn(Engine& e, const std::string& name, const std::string& pname, int src0, int src1, int C,
+                  int silu, bool film, int emb_off, int out) {
+  Op op; op.kind = OP_GN; op.name = name; op.src0 = src0; op.src1 = src1; op.out = out;
+  op.Cin = C; op.silu = silu; op.film = film; op.emb_off = emb_off;
+  op.Hin = e.tensors[out].H; op.Win = e.tensors[out].W;
+  if (C % 32) return fail(e, CFM_ERR_INVALID, "GroupNorm32 needs channels divisible by 32 at " + name);
+  const float *g = nullptr, *b = nullptr; int rc;
+  if ((rc = fetch(e, pname + ".weight", C, &g))) return rc;
+  if ((rc = fetch(e, pname + ".bias", C, &b))) return rc;
+  if ((rc = upload(e, g, C, &op.gamma))) return rc;
+  if ((rc = upload(e, b, C, &op.beta))) return rc;
+  e.ops.push_back(op);
+  return 0;
+}
+
+static void add_resample(Engine& e, const std::string& name, int src, int out, int up) {
+  Op op; op.kind = OP_RESAMPLE; op.name = name; op.src0 = src; op.out = out; op.up = up;
+  op.Cin = e.tensors[src].C; op.Hin = e.tensors[src].H; op.Win = e.tensors[src].W;
+  e.ops.push_back(op);
+}
+
+struct EmbPiece { std::string prefix; int width; };
+
+// ResBlock (unet.py:243-351).  x may be a concat (xa, xb); returns output tensor in *out.
+static int add_resblock(Engine& e, const std::string& p, Cur xa, Cur xb, int cout, bool up, bool down,
+                        std::vector<EmbPiece>& emb_pieces, Cur* outc) {
+  const bool film = e.cfg.use_scale_shift_norm != 0;
+  const int cin = xa.C + (xb.id >= 0 ? xb.C : 0);
+  int H = xa.H, W = xa.W, rc;
+  const int a1 = new_tensor(e, cin, H, W);
+  if ((rc = add_gn(e, p + ".in_layers.0", p + ".in_layers.0", xa.id, xb.id, cin, 1, false, -1, a1))) return rc;
+  int conv_src = a1, xs0 = xa.id, xs1 = xb.id;
+  if (up || down) {
+    if (xb.id >= 0) return fail(e, CFM_ERR_INVALID, "up/down ResBlock with a concatenated input is not supported");
+    const int Hn = up ? H * 2 : H / 2, Wn = up ? W * 2 : W / 2;
+    const int a1r = new_tensor(e, cin, Hn, Wn), xr = new_tensor(e, cin, Hn, Wn);
+    add_resample(e, p + ".h_upd", a1, a1r, up ? 1 : 0);
+    add_resample(e, p + ".x_upd", xa.id, xr, up ? 1 : 0);
+    conv_src = a1r; xs0 = xr; xs1 = -1; H = Hn; W = Wn;
+  }
+  const int emb_off = e.emb_total;
+  const int ew = film ? 2 * cout : cout;
+  emb_pieces.push_back({p + ".emb_layers.1", ew});
+  e.emb_total += ew;
+  const int h1 = new_tensor(e, cout, H, W);
+  if ((rc = add_conv(e, p + ".in_layers.2", p + ".in_layers.2", 3, 1, 0, conv_src, -1, false, cin, H, W, cout,
+                     "", -1, -1, 0, -1, -1, film ? -1 : emb_off, h1, false))) return rc;
+  const int a2 = new_tensor(e, cout, H, W);
+  if ((rc = add_gn(e, p + ".out_layers.0", p + ".out_layers.0", h1, -1, cout, 1, film, film ? emb_off : -1, a2))) return rc;
+  const int o = new_tensor(e, cout, H, W);
+  if (cin != cout) {
+    if ((rc = add_conv(e, p + ".out_layers.3", p + ".out_layers.3", 3, 1, 0, a2, -1, false, cout, H, W, cout,
+                       p + ".skip_connection", xs0, xs1, cin, -1, -1, -1, o, false))) return rc;
+  } else {
+    if ((rc = add_conv(e, p + ".out_layers.3", p + ".out_layers.3", 3, 1, 0, a2, -1, false, cout, H, W, cout,
+                       "", -1, -1, 0, xs0, xs1, -1, o, false))) return rc;
+  }
+  *outc = {o, cout, H, W};
+  return 0;
+}
+
+// AttentionBlock (unet.py:354-401)
+static int add_attention(Engine& e, const std::string& p, Cur x, int heads, Cur* outc) {
+  int rc;
+  const int C = x.C;
+  if (heads <= 0 || C % heads) return fail(e, CFM_ERR_INVALID, "bad head count at " + p);
+  const int a = new_tensor(e, C, x.H, x.W);
+  if ((rc = add_gn(e, p + ".norm", p + ".norm", x.id, -1, C, 0, false, -1, a))) return rc;
+  const int qkv = new_tensor(e, 3 * C, x.H, x.W);
+  if ((rc = add_conv(e, p + ".qkv", p + ".qkv", 1, 1, 0, a, -1, false, C, x.H, x.W, 3 * C, "", -1, -1, 0, -1, -1, -1, qkv, false))) return rc;
+  const int att = new_tensor(e, C, x.H, x.W);
+  Op op; op.kind = OP_ATTN; op.name = p + ".attention"; op.src0 = qkv; op.out = att;
+  op.heads = heads; op.ch = C / heads; op.Cin = C; op.Hin = x.H; op.Win = x.W;
+  op.flops = 2.0 * 2.0 * (double)(x.H * x.W) * (x.H * x.W) * C;
+  e.ops.push_back(op);
+  const int o = new_tensor(e, C, x.H, x.W);
+  if ((rc = add_conv(e, p + ".proj_out", p + ".proj_out", 1, 1, 0, att, -1, false, C, x.H, x.W, C, "", -1, -1, 0, x.id, -1, -1, o, false))) return rc;
+  *outc = {o, C, x.H, x.W};
+  return 0;
+}
+
+static int build_plan(Engine& e) {
+  const cfm_unet_config& c = e.cfg;
+  const int mc = c.model_channels;
+  e.ted = 4 * mc;
+  int rc;
+  auto is_attn = [&](int ds) { for (int i = 0; i < c.n_attention_ds; ++i) if (c.attention_ds[i] == ds) return true; return false; };
+  std::vector<EmbPiece> emb_pieces;
+  std::vector<Cur> hs;
+  int ch = (int)(c.channel_mult[0] * mc);
+  const int S = c.image_size;
+  Cur h;
+  {
+    const int t = new_tensor(e, ch, S, S);
+    if ((rc = add_conv(e, "input_blocks.0.0", "input_blocks.0.0", 3, 1, 0, -1, -1, true, c.in_channels, S, S, ch,
+                       "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
+    h = {t, ch, S, S};
+    hs.push_back(h);
+  }
+  int ds = 1, idx = 1;
+  for (int level = 0; level < c.n_levels; ++level) {
+    const int outc = (int)(c.channel_mult[level] * mc);
+    for (int r = 0; r < c.num_res_blocks; ++r, ++idx) {
+      const std::string p = "input_blocks." + std::to_string(idx);
+      if ((rc = add_resblock(e, p + ".0", h, Cur{-1, 0, 0, 0}, outc, false, false, emb_pieces, &h))) return rc;
+      if (is_attn(ds)) if ((rc = add_attention(e, p + ".1", h, heads_for(c, h.C, false), &h))) return rc;
+      hs.push_back(h);
+    }
+    if (level != c.n_levels - 1) {
+      const std::string p = "input_blocks." + std::to_string(idx) + ".0";
+      if (c.resblock_updown) {
+        if ((rc = add_resblock(e, p, h, Cur{-1, 0, 0, 0}, h.C, false, true, emb_pieces, &h))) return rc;
+      } else if (c.conv_resample) {
+        const int t = new_tensor(e, h.C, h.H / 2, h.W / 2);   // k3 s2 p1: floor((H-1)/2)+1
+        e.tensors[t].H = (h.H - 1) / 2 + 1; e.tensors[t].W = (h.W - 1) / 2 + 1;
+        if ((rc = add_conv(e, p + ".op", p + ".op", 3, 2, 0, h.id, -1, false, h.C, h.H, h.W, h.C, "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
+        h = {t, h.C, e.tensors[t].H, e.tensors[t].W};
+      } else {
+        const int t = new_tensor(e, h.C, h.H / 2, h.W / 2);
+        add_resample(e, p + ".op", h.id, t, 0);
+        h = {t, h.C, h.H / 2, h.W / 2};
+      }
+      hs.push_back(h);
+      ds *= 2; ++idx;
+    }
+  }
+  if ((rc = add_resblock(e, "middle_block.0", h, Cur{-1, 0, 0, 0}, h.C, false, false, emb_pieces, &h))) return rc;
+  if ((rc = add_attention(e, "middle_block.1", h, heads_for(c, h.C, false), &h))) return rc;
+  if ((rc = add_resblock(e, "middle_block.2", h, Cur{-1, 0, 0, 0}, h.C, false, false, emb_pieces, &h))) return rc;
+  idx = 0;
+  for (int level = c.n_levels - 1; level >= 0; --level) {
+    const int outc = (int)(mc * c.channel_mult[level]);
+    for (int i = 0; i <= c.num_res_blocks; ++i, ++idx) {
+      const std::string p = "output_blocks." + std::to_string(idx);
+      const Cur skip = hs.back(); hs.pop_back();
+      if (skip.H != h.H || skip.W != h.W) return fail(e, CFM_ERR_INVALID, "skip/feature size mismatch (image_size not divisible by 2^levels)");
+      int sub = 0;
+      if ((rc = add_resblock(e, p + "." + std::to_string(sub++), h, skip, outc, false, false, emb_pieces, &h))) return rc;
+      if (is_attn(ds)) if ((rc = add_attention(e, p + "." + std::to_string(sub++), h, heads_for(c, h.C, true), &h))) return rc;
+      if (level && i == c.num_res_blocks) {
+        const std::string pu = p + "." + std::to_string(sub++);
+        if (c.resblock_updown) {
+          if ((rc = add_resblock(e, pu, h, Cur{-1, 0, 0, 0}, h.C, true, false, emb_pieces, &h))) return rc;
+        } else if (c.conv_resample) {
+          const int t = new_tensor(e, h.C, h.H * 2, h.W * 2);
+          if ((rc = add_conv(e, pu + ".conv", pu + ".conv", 3, 1, 1, h.id, -1, false, h.C, h.H, h.W, h.C, "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
+          h = {t, h.C, h.H * 2, h.W * 2};
+        } else {
+          const int t = new_tensor(e, h.C, h.H * 2, h.W * 2);
+          add_resample(e, pu, h.id, t, 1);
+          h = {t, h.C, h.H * 2, h.W * 2};
+        }
+        ds /= 2;
+      }
+    }
+  }
+  {
+    const int a = new_tensor(e, h.C, h.H, h.W);
+    if ((rc = add_gn(e, "out.0", "out.0", h.id, -1, h.C, 1, false, -1, a))) return rc;
+    if ((rc = add_conv(e, "out.2", "out.2", 3, 1, 0, a, -1, false, h.C, h.H, h.W, c.out_channels, "", -1, -1, 0, -1, -1, -1, -1, true))) return rc;
+  }
+
+  // ---- embedding path weights ----
+  const float* p = nullptr;
+  if ((rc = fetch(e, "time_embed.0.weight", (int64_t)e.ted * mc, &p))) return rc; if ((rc = upload(e, p, (size_t)e.ted * mc, &e.w_t1))) return rc;
+  if ((rc = fetch(e, "time_embed.0.bias", e.ted, &p))) return rc;                 if ((rc = upload(e, p, e.ted, &e.b_t1))) return rc;
+  if ((rc = fetch(e, "time_embed.2.weight", (int64_t)e.ted * e.ted, &p))) return rc; if ((rc = upload(e, p, (size_t)e.ted * e.ted, &e.w_t2))) return rc;
+  if ((rc = fetch(e, "time_embed.2.bias", e.ted, &p))) return rc;                 if ((rc = upload(e, p, e.ted, &e.b_t2))) return rc;
+  if (c.num_classes > 0) {
+    if ((rc = fetch(e, "label_emb.weight", (int64_t)c.num_classes * e.ted, &p))) return rc;
+    if ((rc = upload(e, p, (size_t)c.num_classes * e.ted, &e.label_emb))) return rc;
+  }
+  std::vector<float> wcat((size_t)e.emb_total * e.ted), bcat(e.emb_total);
+  size_t row = 0;
+  for (auto& pc : emb_pieces) {
+    const float *w = nullptr, *b = nullptr;
+    if ((rc = fetch(e, pc.prefix + ".weight", (int64_t)pc.width * e.ted, &w))) return rc;
+    if ((rc = fetch(e, pc.prefix + ".bias", pc.width, &b))) return rc;
+    std::memcpy(&wcat[row * e.ted], w, sizeof(float) * pc.width * e.ted);
+    std::memcpy(&bcat[row], b, sizeof(float) * pc.width);
+    row += pc.width;
+  }
+  if ((rc = upload(e, wcat.data(), wcat.size(), &e.w_emb_cat))) return rc;
+  if ((rc = upload(e, bcat.data(), bcat.size(), &e.b_emb_cat))) return rc;
+  e.flops_per_sample = 2.0 * ((double)mc * e.ted + (double)e.ted * e.ted + (double)e.emb_total * e.ted);
+  for (auto& op : e.ops) e.flops_per_sample += op.flops;
+
+  // ---- liveness + first-fit arena assignment (per-sample element offsets, 64-element aligned) ----
+  for (int i = 0; i < (int)e.ops.size(); ++i) {
+    const Op& op = e.ops[i];
+    for (int id : {op.src0, op.src1, op.skip0, op.skip1, op.res0, op.res1})
+      if (id >= 0) e.tensors[id].last_use = i;
+    if (op.out >= 0) { if (e.tensors[op.out].first_use < 0) e.tensors[op.out].first_use = i; e.tensors[op.out].last_use = std::max(e.tensors[op.out].last_use, i); }
+  }
+  struct Blk { long long off, len; };
+  std::vector<Blk> free_list;
+  long long top = 0;
+  auto align = [](long long v) { return (v + 63) / 64 * 64; };
+  for (int i = 0; i < (int)e.ops.size(); ++i) {
+    const int o = e.ops[i].out;
+    if (o >= 0 && e.tensors[o].first_use == i) {
+      const long long need = align(e.tensors[o].elems());
+      int best = -1;
+      for (int k = 0; k < (int)free_list.size(); ++k)
+        if (free_list[k].len >= need && (best < 0 || free_list[k].len < free_list[best].len)) best = k;
+      if (best >= 0) {
+        e.tensors[o].off = free_list[best].off;
+        free_list[best].off += need; free_list[best].len -= need;
+        if (free_list[best].len == 0) free_list.erase(free_list.begin() + best);
+      } else { e.tensors[o].off = top; top += need; }
+    }
+    for (int t = 0; t < (int)e.tensors.size(); ++t) {
+      if (e.tensors[t].last_use == i && e.tensors[t].off >= 0) {
+        Blk b{e.tensors[t].off, align(e.tensors[t].elems())};
+        free_list.push_back(b);
+        std::sort(free_list.begin(), free_list.end(), [](const Blk& a, const Blk& c2) { return a.off < c2.off; });
+        for (int k = 0; k + 1 < (int)free_list.size();)   // coalesce
+          if (free_list[k].off + free_list[k].len == free_list[k + 1].off) { free_list[k].len += free_list[k + 1].len; free_list.erase(free_list.begin() + k + 1); }
+          else ++k;
+      }
+    }
+  }
+  e.arena_elems_per_sample = top;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// execution
+// ---------------------------------------------------------------------------------------------
+static size_t esize(const Engine& e) { return e.bf16 ? 2 : 4; }
+
+static int ensure_batch(Engine& e, int B) {
+  if (B > e.arena_batch) {
+    if (e.arena) { cudaFree(e.arena); e.arena = nullptr; }
+    tc_conv_release(e);   // tensor maps hold arena addresses
+    const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
+    CU_CHECK(e, cudaMalloc(&e.arena, bytes));
+    e.arena_batch = B;
+  }
+  const int rows_needed = std::max(B, std::max(1, e.cfg.num_classes));
+  if (rows_needed > e.rows_cap) {
+    for (void* p : {(void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample})
+      if (p) cudaFree(p);
+    CU_CHECK(e, cudaMalloc(&e.t_rows, sizeof(float) * rows_needed));
+    CU_CHECK(e, cudaMalloc(&e.hidden, sizeof(float) * (size_t)rows_needed * e.ted));
+    CU_CHECK(e, cudaMalloc(&e.semb, sizeof(float) * (size_t)rows_needed * e.ted));
+    CU_CHECK(e, cudaMalloc(&e.emb_out, sizeof(float) * (size_t)rows_needed * std::max(e.emb_total, 1)));
+    CU_CHECK(e, cudaMalloc(&e.label_idx, sizeof(long long) * rows_needed));
+    CU_CHECK(e, cudaMalloc(&e.row_of_sample, sizeof(int) * rows_needed));
+    e.rows_cap = rows_needed;
+  }
+  return 0;
+}
+
+void* tensor_ptr(const Engine& e, int id, int B) {
+  if (id < 0) return nullptr;
+  return (char*)e.arena + (size_t)e.tensors[id].off * B * esize(e);
+}
+
+// rows of the embedding table: uniform t -> one row (or one per class); per-sample t -> one per sample
+__global__ void setup_rows_kernel(int B, int rows, int uniform, float t_scalar, const float* t_dev,
+                                  const long long* y, float* t_rows, long long* label_idx, int* row_of_sample) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    t_rows[i] = uniform ? t_scalar : t_dev[i];
+    label_idx[i] = uniform ? (long long)i : (y ? y[i] : 0);
+  }
+  if (i < B) row_of_sample[i] = uniform ? (y ? (int)y[i] : 0) : i;
+}
+
+template <typename T>
+static int run_ops(Engine& e, int B, const float* x, const float* cond, float* out, cudaStream_t st) {
+  const int Cx = cond ? e.cfg.in_channels - (e.cfg.in_channels - e.x_channels()) : e.cfg.in_channels;
+  (void)Cx;
+  for (const Op& op : e.ops) {
+    switch (op.kind) {
+      case OP_CONV: {
+        if (op.tc) {
+          int rc = tc_conv_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
+        ConvArgs<T> a{};
+        if (op.src_is_input) {
+          const int cx = cond ? e.x_channels() : e.cfg.in_channels;
+          a.src_nchw0 = x; a.C0 = cx; a.src_nchw1 = cond; a.C1 = e.cfg.in_channels - cx;
+        } else {
+          a.src0 = (const T*)tensor_ptr(e, op.src0, B); a.C0 = e.tensors[op.src0].C;
+          a.src1 = (const T*)tensor_ptr(e, op.src1, B); a.C1 = op.src1 >= 0 ? e.tensors[op.src1].C : 0;
+        }
+        a.Hin = op.Hin; a.Win = op.Win; a.ups = op.ups; a.stride = op.stride; a.ks = op.ks; a.w_main = op.w_main;
+        a.skip0 = (const T*)tensor_ptr(e, op.skip0, B); a.S0 = op.skip0 >= 0 ? e.tensors[op.skip0].C : 0;
+        a.skip1 = (const T*)tensor_ptr(e, op.skip1, B); a.S1 = op.skip1 >= 0 ? e.tensors[op.skip1].C : 0;
+        a.w_skip = op.w_skip; a.bias = op.bias;
+        if (op.emb_off >= 0) { a.emb = e.emb_out + op.emb_off; a.emb_stride = e.emb_total; a.emb_row = e.row_of_sample; }
+        a.res0 = (const T*)tensor_ptr(e, op.res0, B); a.R0 = op.res0 >= 0 ? e.tensors[op.res0].C : 0;
+        a.res1 = (const T*)tensor_ptr(e, op.res1, B); a.R1 = op.res1 >= 0 ? e.tensors[op.res1].C : 0;
+        if (op.out_is_output) a.out_nchw = out; else a.out = (T*)tensor_ptr(e, op.out, B);
+        a.B = B; a.Hout = op.Hout; a.Wout = op.Wout; a.Cout = op.Cout;
+        const long long M = (long long)B * op.Hout * op.Wout;
+        dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (unsigned)((op.Cout + CG_BN - 1) / CG_BN));
+        conv_generic_kernel<T><<<grid, 256, 0, st>>>(a);
+        e.launches++;
+        break;
+      }
+      case OP_GN: {
+        if (e.bf16 && gn_bf16_supported(e, op)) {
+          int rc = gn_bf16_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
+        GnArgs<T> a{};
+        a.src0 = (const T*)tensor_ptr(e, op.src0, B); a.C0 = e.tensors[op.src0].C;
+        a.src1 = (const T*)tensor_ptr(e, op.src1, B); a.C1 = op.src1 >= 0 ? e.tensors[op.src1].C : 0;
+        a.HW = op.Hin * op.Win; a.gamma = op.gamma; a.beta = op.beta; a.eps = 1e-5f; a.silu = op.silu;
+        if (op.film) { a.film = e.emb_out + op.emb_off; a.film_stride = e.emb_total; a.film_row = e.row_of_sample; }
+        a.out = (T*)tensor_ptr(e, op.out, B);
+        a.exact = e.bf16 ? 0 : 1;
+        const int n = (op.Cin / 32) * a.HW;
+        const int cap = 48 * 1024 / 4;   // stay within the default dynamic smem limit
+        a.smem_elems = n <= cap ? n : 0;
+        groupnorm_kernel<T><<<B * 32, 256, (size_t)a.smem_elems * 4, st>>>(a);
+        e.launches++;
+        break;
+      }
+      case OP_RESAMPLE: {
+        const long long total = (long long)B * e.tensors[op.out].elems();
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.sm_count * 16);
+        resample_kernel<T><<<blocks, 256, 0, st>>>((const T*)tensor_ptr(e, op.src0, B), (T*)tensor_ptr(e, op.out, B), B, op.Hin, op.Win, op.Cin, op.up);
+        e.launches++;
+        break;
+      }
+      case OP_ATTN: {
+        AttnArgs<T> a{(const T*)tensor_ptr(e, op.src0, B), (T*)tensor_ptr(e, op.out, B), B, op.Hin * op.Win, op.heads, op.ch, e.cfg.use_new_attention_order};
+        const int nw = 8;
+        dim3 grid((a.T_len + nw - 1) / nw, B * op.heads);
+        const size_t smem = sizeof(float) * (32 * (op.ch + 1) + 32 * op.ch);
+        const int cpl = (op.ch + 31) / 32;
+        if (smem > 48 * 1024 || cpl > 16) return fail(e, CFM_ERR_INVALID, "attention head width too large for the generic kernel");
+        if (cpl <= 1) attention_generic_kernel<T, 1><<<grid, nw * 32, smem, st>>>(a);
+        else if (cpl <= 2) attention_generic_kernel<T, 2><<<grid, nw * 32, smem, st>>>(a);
+        else if (cpl <= 4) attention_generic_kernel<T, 4><<<grid, nw * 32, smem, st>>>(a);
+        else if (cpl <= 8) attention_generic_kernel<T, 8><<<grid, nw * 32, smem, st>>>(a);
+        else attention_generic_kernel<T, 16><<<grid, nw * 32, smem, st>>>(a);
+        e.launches++;
+        break;
+      }
+    }
+  }
+  return 0;
+}
+
+static int forward_impl(Engine& e, int B, const float* x, const float* cond, const float* t_dev, float t_scalar,
+                        const int64_t* y, float* out, cudaStream_t st) {
+  if (B <= 0) return fail(e, CFM_ERR_INVALID, "batch must be positive");
+  if (!x || !out) return fail(e, CFM_ERR_INVALID, "x_dev and out_dev must be non-NULL");
+  if ((y != nullptr) != (e.cfg.num_classes > 0))
+    return fail(e, CFM_ERR_INVALID, "must specify y if and only if the model is class-conditional");
+  if (!cond && e.cfg.in_channels != e.x_channels() && false) return fail(e, CFM_ERR_INVALID, "cond required");
+  int rc = ensure_batch(e, B);
+  if (rc) return rc;
+  const int uniform = t_dev == nullptr;
+  const int rows = uniform ? std::max(1, e.cfg.num_classes) : B;
+  const int n = std::max(rows, B);
+  setup_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, rows, uniform, t_scalar, t_dev, (const long long*)y, e.t_rows, e.label_idx, e.row_of_sample);
+  time_hidden_kernel<<<rows, 256, sizeof(float) * e.cfg.model_channels, st>>>(e.t_rows, e.cfg.model_channels, e.ted, e.w_t1, e.b_t1, e.hidden);
+  linear_rows_kernel<<<dim3((e.ted + 7) / 8, rows), 256, 0, st>>>(e.hidden, e.ted, e.w_t2, e.b_t2, e.ted, e.label_emb, e.label_idx, 1, e.semb);
+  linear_rows_kernel<<<dim3((e.emb_total + 7) / 8, rows), 256, 0, st>>>(e.semb, e.ted, e.w_emb_cat, e.b_emb_cat, e.emb_total, nullptr, nullptr, 0, e.emb_out);
+  e.launches += 4;
+  rc = e.bf16 ? run_ops<bf16>(e, B, x, cond, out, st) : run_ops<float>(e, B, x, cond, out, st);
+  if (rc) return rc;
+  CU_CHECK(e, cudaGetLastError());
+  return 0;
+}
+
+static int ensure_v(Engine& e, long long n) {
+  if (n > e.v_cap) {
+    if (e.v_buf) cudaFree(e.v_buf);
+    CU_CHECK(e, cudaMalloc(&e.v_buf, sizeof(float) * n));
+    e.v_cap = n;
+  }
+  return 0;
+}
+
+static int ew_blocks(const Engine& e, long long n) {
+  return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)e.sm_count * 8));
+}
+
+}  // namespace cfm
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace cfm;
+
+struct cfm_engine { Engine impl; };
+
+extern "C" {
+
+int cfm_abi_version(void) { return CFM_ABI_VERSION; }
+
+const char* cfm_last_error(const cfm_engine* e) { return e ? e->impl.err.c_str() : g_create_error.c_str(); }
+
+int cfm_engine_create(const cfm_unet_config* cfg, int32_t n_tensors, const char* const* names,
+                      const float* const* host_data, const int64_t* numel, int32_t device, cfm_engine** out) {
+  if (!cfg || !out || (n_tensors > 0 && (!names || !host_data || !numel))) { g_create_error = "NULL argument"; return CFM_ERR_INVALID; }
+  *out = nullptr;
+  std::unique_ptr<cfm_engine> h(new cfm_engine());
+  Engine& e = h->impl;
+  e.cfg = *cfg; e.device = device; e.bf16 = cfg->precision == CFM_PRECISION_BF16;
+  auto bad = [&](int code, const std::string& m) { g_create_error = m; return code; };
+  if (cfg->n_levels < 1 || cfg->n_levels > CFM_MAX_LEVELS || cfg->n_attention_ds < 0 || cfg->n_attention_ds > CFM_MAX_LEVELS)
+    return bad(CFM_ERR_INVALID, "n_levels / n_attention_ds out of range");
+  if (cfg->model_channels <= 0 || cfg->model_channels % 32 || cfg->image_size <= 0 || cfg->in_channels <= 0 || cfg->out_channels <= 0 || cfg->num_res_blocks < 1)
+    return bad(CFM_ERR_INVALID, "invalid U-Net configuration (model_channels must be a positive multiple of 32)");
+  if (cfg->precision != CFM_PRECISION_FP32 && cfg->precision != CFM_PRECISION_BF16) return bad(CFM_ERR_INVALID, "unknown precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return bad(CFM_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return bad(CFM_ERR_INVALID, "device index out of range");
+  if (cudaSetDevice(device) != cudaSuccess) return bad(CFM_ERR_CUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bad(CFM_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return bad(CFM_ERR_CUDA, std::string("this library is built for sm_100a (B200); found ") + prop.name);
+  e.sm_count = prop.multiProcessorCount;
+  for (int i = 0; i < n_tensors; ++i) e.sd[names[i]] = HostTensor{host_data[i], numel[i]};
+  int rc = build_plan(e);
+  if (rc) { g_create_error = e.err; for (void* p : e.owned) cudaFree(p); return rc; }
+  e.sd.clear();
+  *out = h.release();
+  return CFM_OK;
+}
+
+void cfm_engine_destroy(cfm_engine* h) {
+  if (!h) return;
+  Engine& e = h->impl;
+  cudaSetDevice(e.device);
+  tc_conv_release(e);
+  for (void* p : e.owned) cudaFree(p);
+  for (void* p : {(void*)e.arena, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf})
+    if (p) cudaFree(p);
+  delete h;
+}
+
+int64_t cfm_engine_param_count(const cfm_engine* e) { return e ? e->impl.param_count : 0; }
+double cfm_engine_flops_per_sample(const cfm_engine* e) { return e ? e->impl.flops_per_sample : 0; }
+int64_t cfm_engine_workspace_bytes(const cfm_engine* e, int32_t batch) {
+  return e ? (int64_t)e->impl.arena_elems_per_sample * batch * (e->impl.bf16 ? 2 : 4) : 0;
+}
+int32_t cfm_engine_kernel_launches(const cfm_engine* e) { return e ? e->impl.launches : 0; }
+int32_t cfm_engine_tensor_core_convs(const cfm_engine* e) { return e ? e->impl.n_tc_convs : 0; }
+
+int cfm_engine_forward(cfm_engine* h, int32_t batch, const float* x_dev, const float* cond_dev, const float* t_dev,
+                       float t_scalar, const int64_t* y_dev, float* out_dev, void* stream) {
+  if (!h) return CFM_ERR_INVALID;
+  Engine& e = h->impl;
+  cudaSetDevice(e.device);
+  e.launches = 0;
+  return forward_impl(e, batch, x_dev, cond_dev, t_dev, t_scalar, y_dev, out_dev, (cudaStream_t)stream);
+}
+
+int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev, const int64_t* y_dev,
+                     const float* t_host, const float* dt_host, int32_t n_steps, uint32_t flags,
+                     float* traj_dev, uint8_t* img_u8_dev, void* stream) {
+  if (!h) return CFM_ERR_INVALID;
+  Engine& e = h->impl;
+  if (!x_dev || !t_host || !dt_host || n_steps < 0 || batch <= 0) return fail(e, CFM_ERR_INVALID, "bad argument to cfm_sample_euler");
+  cudaSetDevice(e.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = e.cfg.image_size;
+  const long long n = (long long)batch * e.x_channels() * S * S;
+  const long long n_cond = cond_dev ? (long long)batch * (e.cfg.in_channels - e.x_channels()) * S * S : 0;
+  int rc = ensure_batch(e, batch); if (rc) return rc;
+  if ((rc = ensure_v(e, n))) return rc;
+  e.launches = 0;
+  if (traj_dev) CU_CHECK(e, cudaMemcpyAsync(traj_dev, x_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (n_steps == 0 && img_u8_dev) { quantize_u8_kernel<<<ew_blocks(e, n), 256, 0, st>>>(img_u8_dev, x_dev, n); e.launches++; }
+
+  const bool use_graph = (flags & CFM_EULER_USE_GRAPH) && n_steps > 0;
+  cudaStream_t work = st;
+  cudaStream_t cap_stream = nullptr;
+  if (use_graph) {
+    // capture on a private stream so a legacy default stream can be the launch stream
+    CU_CHECK(e, cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    CU_CHECK(e, cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+    work = cap_stream;
+  }
+  for (int k = 0; k < n_steps && rc == 0; ++k) {
+    rc = forward_impl(e, batch, x_dev, cond_dev, nullptr, t_host[k], y_dev, e.v_buf, work);
+    if (rc) break;
+    const bool last = k == n_steps - 1;
+    euler_step_kernel<<<ew_blocks(e, n), 256, 0, work>>>(
+        x_dev, e.v_buf, dt_host[k], n, (flags & CFM_EULER_COND_DRIFT) ? cond_dev : nullptr, n_cond,
+        traj_dev ? traj_dev + (long long)(k + 1) * n : nullptr, (last && img_u8_dev) ? img_u8_dev : nullptr);
+    e.launches++;
+  }
+  if (use_graph) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+    if (rc == 0 && ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    if (rc == 0) {
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      if (ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+    }
+    if (rc == 0) {
+      ce = cudaGraphLaunch(exec, st);
+      if (ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(ce));
+      cudaStreamSynchronize(st);
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap_stream);
+  }
+  if (rc) return rc;
+  CU_CHECK(e, cudaGetLastError());
+  return 0;
+}
+
+int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* condition_dev,
+                    const cfm_ddpm_tables* tb, const cfm_ddpm_options* opt, const float* noise_dev,
+                    uint64_t seed, void* stream) {
+  if (!h) return CFM_ERR_INVALID;
+  Engine& e = h->impl;
+  if (!x_dev || !tb || !opt || batch <= 0 || tb->Ns <= 0) return fail(e, CFM_ERR_INVALID, "bad argument to cfm_sample_ddpm");
+  if (opt->mode != CFM_DDPM_PRIOR && !condition_dev) return fail(e, CFM_ERR_INVALID, "condition_dev required for conditional sampling");
+  cudaSetDevice(e.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = e.cfg.image_size, Ns = tb->Ns;
+  const long long n = (long long)batch * e.x_channels() * S * S;
+  int rc = ensure_batch(e, batch); if (rc) return rc;
+  if ((rc = ensure_v(e, n))) return rc;
+  e.launches = 0;
+  const bool repl = opt->mode == CFM_DDPM_REPLACEMENT;
+  const float* amort_cond = opt->mode == CFM_DDPM_AMORTIZED ? condition_dev : nullptr;
+  auto blend_at = [&](int i) { return repl && i >= 0 && i < opt->replace_below_step; };
+  auto zslot = [&](int i, int which) -> const float* { return noise_dev ? noise_dev + ((long long)i * 2 + which) * n : nullptr; };
+
+  const bool use_graph = opt->use_graph != 0;
+  cudaStream_t work = st, cap_stream = nullptr;
+  if (use_graph) {
+    CU_CHECK(e, cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    CU_CHECK(e, cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+    work = cap_stream;
+  }
+  if (blend_at(Ns - 1)) {
+    ddpm_blend_kernel<<<ew_blocks(e, n), 256, 0, work>>>(x_dev, condition_dev, tb->sqrt_alphas_cumprod[Ns - 1],
+        tb->sqrt_one_minus_alphas_cumprod[Ns - 1], opt->pad_value, opt->noise_condition, zslot(Ns - 1, 0), seed, 2u * (Ns - 1), n);
+    e.launches++;
+  }
+  for (int i = Ns - 1; i >= 0 && rc == 0; --i) {
+    rc = forward_impl(e, batch, x_dev, amort_cond, nullptr, tb->model_time[i], nullptr, e.v_buf, work);
+    if (rc) break;
+    DdpmStepScalars s{};
+    s.a = tb->sqrt_recip_alphas_cumprod[i]; s.b = tb->sqrt_recipm1_alphas_cumprod[i];
+    s.c1 = tb->posterior_mean_coef1[i]; s.c2 = tb->posterior_mean_coef2[i];
+    s.sigma = expf(0.5f * tb->posterior_log_variance_clipped[i]);
+    s.add_noise = i > 0;
+    s.blend_next = blend_at(i - 1);
+    s.noise_condition = opt->noise_condition; s.pad_value = opt->pad_value;
+    if (s.blend_next) { s.sa = tb->sqrt_alphas_cumprod[i - 1]; s.sb = tb->sqrt_one_minus_alphas_cumprod[i - 1]; }
+    s.final_clip = i == 0;
+    ddpm_step_kernel<<<ew_blocks(e, n), 256, 0, work>>>(x_dev, e.v_buf, s, condition_dev, zslot(i, 1),
+        s.blend_next ? zslot(i - 1, 0) : nullptr, seed, 2u * i + 1u, s.blend_next ? 2u * (i - 1) : 0u, n);
+    e.launches++;
+  }
+  if (use_graph) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+    if (rc == 0 && ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    if (rc == 0 && (ce = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+    if (rc == 0) {
+      if ((ce = cudaGraphLaunch(exec, st)) != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(ce));
+      cudaStreamSynchronize(st);
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap_stream);
+  }
+  if (rc) return rc;
+  CU_CHECK(e, cudaGetLastError());
+  return 0;
+}
+
+static int rk_pack(RkPtrs* p, const float* const* k_dev, const float* coef_host, int n_k) {
+  if (!k_dev || !coef_host || n_k < 1 || n_k > 8) return CFM_ERR_INVALID;
+  p->n_k = n_k;
+  for (int j = 0; j < 8; ++j) { p->k[j] = j < n_k ? k_dev[j] : nullptr; p->coef[j] = j < n_k ? coef_host[j] : 0.f; }
+  return 0;
+}
+
+int cfm_rk_combine(float* out_dev, const float* y_dev, const float* const* k_dev, const float* coef_host,
+                   int32_t n_k, float dt, int64_t n, void* stream) {
+  RkPtrs p; if (rk_pack(&p, k_dev, coef_host, n_k) || !out_dev || !y_dev || n < 0) return CFM_ERR_INVALID;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  rk_combine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, y_dev, p, dt, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+int cfm_rk_error_sumsq(double* sumsq_dev, const float* y0_dev, const float* y1_dev, const float* const* k_dev,
+                       const float* coef_host, int32_t n_k, float dt, float rtol, float atol, int64_t n, void* stream) {
+  RkPtrs p; if (rk_pack(&p, k_dev, coef_host, n_k) || !sumsq_dev || !y0_dev || !y1_dev || n < 0) return CFM_ERR_INVALID;
+  if (cudaMemsetAsync(sumsq_dev, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return CFM_ERR_CUDA;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  rk_error_sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sumsq_dev, y0_dev, y1_dev, p, dt, rtol, atol, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+int cfm_make_box_condition(float* cond_dev, const float* images_dev, const int32_t* boxes_dev, int32_t batch,
+                           int32_t channels, int32_t height, int32_t width, int32_t patch, float pad_value,
+                           int32_t mode, void* stream) {
+  if (!cond_dev || !images_dev || !boxes_dev || batch < 0 || channels <= 0 || height <= 0 || width <= 0 || patch < 0 || (mode != 0 && mode != 1)) return CFM_ERR_INVALID;
+  const long long n = (long long)batch * channels * height * width;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  box_condition_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cond_dev, images_dev, boxes_dev, batch, channels, height, width, patch, pad_value, mode);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+int cfm_quantize_u8(uint8_t* out_dev, const float* x_dev, int64_t n, void* stream) {
+  if (!out_dev || !x_dev || n < 0) return CFM_ERR_INVALID;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  quantize_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, x_dev, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// Internal engine structures (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/cfm_b200.h"
+
+namespace cfm {
+
+struct HostTensor { const float* data; int64_t numel; };
+
+// An activation tensor of the plan: NHWC [B, H, W, C]; `off` is a per-sample element offset
+// into the arena (multiplied by the batch size at run time).
+struct TensorDesc {
+  int C = 0, H = 0, W = 0;
+  long long off = -1;
+  int first_use = -1, last_use = -1;
+  long long elems() const { return (long long)C * H * W; }
+};
+
+enum OpKind { OP_CONV = 0, OP_GN = 1, OP_RESAMPLE = 2, OP_ATTN = 3 };
+
+struct TcConvPlan;   // tcgen05 implicit-GEMM lowering of a conv op (conv_tc.cu)
+
+struct Op {
+  OpKind kind;
+  std::string name;
+  // tensor ids (-1 = none). For convs: src = main operand, skip = 1x1 operand, res = identity residual.
+  int src0 = -1, src1 = -1, skip0 = -1, skip1 = -1, res0 = -1, res1 = -1, out = -1;
+  bool src_is_input = false, out_is_output = false;
+  // conv
+  int ks = 3, stride = 1, ups = 0, Cin = 0, Cskip = 0, Cout = 0, Hin = 0, Win = 0, Hout = 0, Wout = 0;
+  float* w_main = nullptr; float* w_skip = nullptr; float* bias = nullptr;   // fp32 device
+  int emb_off = -1;        // offset of this block's vector in the embedding table (conv add / FiLM)
+  // groupnorm
+  float* gamma = nullptr; float* beta = nullptr; int silu = 0; bool film = false;
+  // resample
+  int up = 0;
+  // attention
+  int heads = 0, ch = 0;
+  // tensor-core lowering (bf16 mode), null when the generic kernel runs this op
+  TcConvPlan* tc = nullptr;
+  double flops = 0;        // 2*MAC per sample
+};
+
+struct Engine {
+  cfm_unet_config cfg{};
+  int device = 0;
+  bool bf16 = false;
+  std::string err;
+  std::map<std::string, HostTensor> sd;
+  std::vector<void*> owned;            // device allocations freed at destroy
+  std::vector<TensorDesc> tensors;
+  std::vector<Op> ops;
+  long long arena_elems_per_sample = 0;
+  void* arena = nullptr; int arena_batch = 0;
+  // embedding path
+  int ted = 0, emb_total = 0;
+  float *w_t1 = nullptr, *b_t1 = nullptr, *w_t2 = nullptr, *b_t2 = nullptr, *label_emb = nullptr;
+  float *w_emb_cat = nullptr, *b_emb_cat = nullptr;
+  float *t_rows = nullptr, *hidden = nullptr, *semb = nullptr, *emb_out = nullptr;
+  long long* label_idx = nullptr; int* row_of_sample = nullptr; int rows_cap = 0;
+  // scratch for samplers
+  float* v_buf = nullptr; long long v_cap = 0;
+  int64_t param_count = 0;
+  double flops_per_sample = 0;
+  int launches = 0;
+  int n_tc_convs = 0;
+  int sm_count = 148;
+  int x_channels() const { return cfg.out_channels; }
+};
+
+// conv_tc.cu
+bool tc_conv_supported(const Engine& e, const Op& op);
+int  tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w_main_oihw, const std::vector<float>& w_skip_oi);
+int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+void tc_conv_release(Engine& e);
+// bf16 fast kernels (kernels_bf16.cu)
+int  gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+bool gn_bf16_supported(const Engine& e, const Op& op);
+
+}  // namespace cfm

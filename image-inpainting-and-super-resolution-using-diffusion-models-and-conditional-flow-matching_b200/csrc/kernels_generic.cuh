@@ -1,0 +1,378 @@
+// Generic (CUDA-core) kernels of the U-Net evaluation.
+//
+// These are the exact-mode (fp32) path and the fallback for layers the tcgen05
+// implicit-GEMM kernel does not take (3-channel edge convs, odd shapes).  They are
+// templated on the activation storage type T (float | bf16); all math is fp32.
+// Activations are NHWC: [B, H, W, C] with C contiguous.
+#pragma once
+#include "common.cuh"
+
+namespace cfm {
+
+// ---------------------------------------------------------------------------------------
+// Convolution as an implicit GEMM on CUDA cores.
+//   out[b, oy, ox, n] = bias[n] + emb[row[b]][n] + residual[b, oy, ox, n]
+//                     + sum_{tap, c} w_main[(tap*Cin + c)][n] * src[b, iy, ix, c]      (KSxKS, pad KS/2)
+//                     + sum_{c}      w_skip[c][n]             * skip[b, oy, ox, c]      (1x1, optional)
+// `src` and `skip` may each be a channel concatenation of two tensors.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct ConvArgs {
+  // main operand
+  const T* src0; const T* src1; int C0, C1;      // NHWC sources, concat on channels
+  const float* src_nchw0; const float* src_nchw1; // if non-null: fp32 NCHW sources instead (network input)
+  int Hin, Win;                                  // stored source size
+  int ups;                                       // 1: source is nearest-upsampled x2 on the fly
+  int stride, ks;                                // ks = 1 or 3 (pad = ks/2)
+  const float* w_main;                           // [ks*ks*(C0+C1)][Cout]
+  // 1x1 skip operand (same resolution as the output)
+  const T* skip0; const T* skip1; int S0, S1;
+  const float* w_skip;                           // [(S0+S1)][Cout]
+  // epilogue
+  const float* bias;                             // [Cout] (already includes skip bias)
+  const float* emb; int emb_stride; const int* emb_row;  // optional per-sample vector add
+  const T* res0; const T* res1; int R0, R1;      // optional identity residual (concat)
+  T* out;                                        // NHWC [B,Hout,Wout,Cout] (or null)
+  float* out_nchw;                               // fp32 NCHW output instead (network output)
+  int B, Hout, Wout, Cout;
+};
+
+constexpr int CG_BM = 64, CG_BN = 64, CG_BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_generic_kernel(ConvArgs<T> a) {
+  __shared__ float As[CG_BK][CG_BM + 4];
+  __shared__ float Bs[CG_BK][CG_BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int Cin = a.C0 + a.C1;
+  const int Kmain = a.ks * a.ks * Cin;
+  const int Kskip = a.S0 + a.S1;
+  const int Ktot = Kmain + Kskip;
+  const long long M = (long long)a.B * a.Hout * a.Wout;
+  const long long m0 = (long long)blockIdx.x * CG_BM;
+  const int n0 = blockIdx.y * CG_BN;
+  const int pad = a.ks >> 1;
+  const int Hv = a.ups ? a.Hin * 2 : a.Hin, Wv = a.ups ? a.Win * 2 : a.Win;
+
+  // this thread always loads pixel (tid % 64) of the tile
+  const int lm = tid & 63;
+  const long long pm = m0 + lm;
+  const bool pvalid = pm < M;
+  int pb = 0, poy = 0, pox = 0;
+  if (pvalid) {
+    pb = (int)(pm / (a.Hout * a.Wout));
+    int r = (int)(pm - (long long)pb * a.Hout * a.Wout);
+    poy = r / a.Wout; pox = r - poy * a.Wout;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += CG_BK) {
+    // A tile: 64 px x 16 k ; thread loads k = tid/64 + 4*i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kl = (tid >> 6) + 4 * i;
+      const int k = k0 + kl;
+      float v = 0.f;
+      if (pvalid && k < Ktot) {
+        if (k < Kmain) {
+          const int tap = k / Cin, c = k - tap * Cin;
+          const int ky = tap / a.ks, kx = tap - ky * a.ks;
+          int iy = poy * a.stride + ky - pad, ix = pox * a.stride + kx - pad;
+          if (iy >= 0 && iy < Hv && ix >= 0 && ix < Wv) {
+            if (a.ups) { iy >>= 1; ix >>= 1; }
+            if (a.src_nchw0) {
+              v = (c < a.C0)
+                ? a.src_nchw0[(((long long)pb * a.C0 + c) * a.Hin + iy) * a.Win + ix]
+                : a.src_nchw1[(((long long)pb * a.C1 + (c - a.C0)) * a.Hin + iy) * a.Win + ix];
+            } else {
+              const long long pix = ((long long)pb * a.Hin + iy) * a.Win + ix;
+              v = (c < a.C0) ? to_f(a.src0[pix * a.C0 + c]) : to_f(a.src1[pix * a.C1 + (c - a.C0)]);
+            }
+          }
+        } else {
+          const int c = k - Kmain;
+          const long long pix = ((long long)pb * a.Hout + poy) * a.Wout + pox;
+          v = (c < a.S0) ? to_f(a.skip0[pix * a.S0 + c]) : to_f(a.skip1[pix * a.S1 + (c - a.S0)]);
+        }
+      }
+      As[kl][lm] = v;
+    }
+    // B tile: 16 k x 64 n ; thread loads n = tid%64, k = tid/64 + 4*i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kl = (tid >> 6) + 4 * i;
+      const int k = k0 + kl;
+      const int n = n0 + (tid & 63);
+      float v = 0.f;
+      if (k < Ktot && n < a.Cout)
+        v = (k < Kmain) ? a.w_main[(long long)k * a.Cout + n] : a.w_skip[(long long)(k - Kmain) * a.Cout + n];
+      Bs[kl][tid & 63] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CG_BK; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int b = (int)(m / (a.Hout * a.Wout));
+    const int r = (int)(m - (long long)b * a.Hout * a.Wout);
+    const float* embp = a.emb ? a.emb + (long long)a.emb_row[b] * a.emb_stride : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.Cout) continue;
+      float v = acc[i][j] + a.bias[n];
+      if (embp) v += embp[n];
+      if (a.res0) v += (n < a.R0) ? to_f(a.res0[m * a.R0 + n]) : to_f(a.res1[m * a.R1 + (n - a.R0)]);
+      if (a.out_nchw) a.out_nchw[((long long)b * a.Cout + n) * (a.Hout * a.Wout) + r] = v;
+      else a.out[m * a.Cout + n] = from_f<T>(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm(32 groups, eps) [+ FiLM] [+ SiLU] over an NHWC tensor (optionally a concat of two).
+// One CTA per (sample, group).  Group data is staged in shared memory when it fits so
+// the mean / centred variance / normalise passes read global memory once.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct GnArgs {
+  const T* src0; const T* src1; int C0, C1;
+  int HW;
+  const float* gamma; const float* beta;     // [C0+C1]
+  float eps;
+  int silu;
+  // FiLM: h = gn * (1 + scale) + shift, scale = emb[row][film_off + c], shift = emb[row][film_off + C + c]
+  const float* film; int film_stride; const int* film_row;
+  T* out;                                    // NHWC with C0+C1 channels
+  int smem_elems;                            // capacity of the staging buffer (0 = do not stage)
+  int exact;                                 // 1: expf SiLU
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) groupnorm_kernel(GnArgs<T> a) {
+  extern __shared__ float stage[];
+  __shared__ float red[32];
+  const int C = a.C0 + a.C1;
+  const int cpg = C / 32;
+  const int b = blockIdx.x / 32, g = blockIdx.x % 32;
+  const int n = cpg * a.HW;
+  const bool staged = n <= a.smem_elems;
+  auto load = [&](int e) -> float {
+    const int p = e / cpg, c = g * cpg + (e - p * cpg);
+    const long long pix = (long long)b * a.HW + p;
+    return (c < a.C0) ? to_f(a.src0[pix * a.C0 + c]) : to_f(a.src1[pix * a.C1 + (c - a.C0)]);
+  };
+  float s = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const float v = load(e);
+    if (staged) stage[e] = v;
+    s += v;
+  }
+  const float mean = block_sum(s, red) / (float)n;
+  float q = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const float d = (staged ? stage[e] : load(e)) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = block_sum(q, red) / (float)n;
+  const float rstd = rsqrtf(var + a.eps);
+  const float* film = a.film ? a.film + (long long)a.film_row[b] * a.film_stride : nullptr;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int p = e / cpg, c = g * cpg + (e - p * cpg);
+    float v = ((staged ? stage[e] : load(e)) - mean) * rstd * a.gamma[c] + a.beta[c];
+    if (film) v = v * (1.0f + film[c]) + film[C + c];
+    if (a.silu) v = a.exact ? silu_exact(v) : silu_f(v);
+    a.out[((long long)b * a.HW + p) * C + c] = from_f<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 2x2 average pool / nearest x2 upsample on NHWC (ResBlock h_upd / x_upd, Upsample, Downsample(use_conv=False)).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void resample_kernel(const T* __restrict__ src, T* __restrict__ out, int B, int Hin, int Win, int C, int up) {
+  const int Ho = up ? Hin * 2 : Hin / 2, Wo = up ? Win * 2 : Win / 2;
+  const long long total = (long long)B * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float v;
+    if (up) {
+      v = to_f(src[(((long long)b * Hin + (oy >> 1)) * Win + (ox >> 1)) * C + c]);
+    } else {
+      const long long base = (((long long)b * Hin + oy * 2) * Win + ox * 2) * C + c;
+      v = 0.25f * (to_f(src[base]) + to_f(src[base + C]) + to_f(src[base + (long long)Win * C]) + to_f(src[base + (long long)Win * C + C]));
+    }
+    out[i] = from_f<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Attention core, generic: softmax((q s)^T (k s)) v per (sample, head), s = ch^-1/4.
+// qkv: NHWC [B, T, 3C]; channel of (head h, part p in {q,k,v}, c):
+//   legacy order: h*3*ch + p*ch + c          new order: p*C + h*ch + c
+// One warp per query; keys streamed through shared memory in tiles of 32.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct AttnArgs {
+  const T* qkv; T* out; int B, T_len, heads, ch, new_order;
+};
+
+template <typename T, int CH_PER_LANE>
+__global__ void __launch_bounds__(256) attention_generic_kernel(AttnArgs<T> a) {
+  // smem: K tile [32][ch+1], V tile [32][ch]
+  extern __shared__ float sm[];
+  const int ch = a.ch, C = a.heads * ch;
+  float* Ks = sm;
+  float* Vs = sm + 32 * (ch + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int bh = blockIdx.y, b = bh / a.heads, h = bh % a.heads;
+  const int q_idx = blockIdx.x * nwarp + warp;
+  const int qoff = a.new_order ? h * ch : h * 3 * ch;
+  const int koff = a.new_order ? C + h * ch : h * 3 * ch + ch;
+  const int voff = a.new_order ? 2 * C + h * ch : h * 3 * ch + 2 * ch;
+  const float scale = rsqrtf(sqrtf((float)ch));
+  const long long row0 = (long long)b * a.T_len;
+  const bool qvalid = q_idx < a.T_len;
+  // q in registers, distributed: lane holds channels lane + 32*j
+  float qreg[CH_PER_LANE];
+#pragma unroll
+  for (int j = 0; j < CH_PER_LANE; ++j) {
+    const int c = lane + 32 * j;
+    qreg[j] = (qvalid && c < ch) ? to_f(a.qkv[(row0 + q_idx) * 3 * C + qoff + c]) * scale : 0.f;
+  }
+  float m_run = -INFINITY, l_run = 0.f;
+  float acc[CH_PER_LANE];
+#pragma unroll
+  for (int j = 0; j < CH_PER_LANE; ++j) acc[j] = 0.f;
+
+  for (int s0 = 0; s0 < a.T_len; s0 += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * ch; e += blockDim.x) {
+      const int s = e / ch, c = e - s * ch;
+      float kv = 0.f, vv = 0.f;
+      if (s0 + s < a.T_len) {
+        const long long base = (row0 + s0 + s) * 3 * C;
+        kv = to_f(a.qkv[base + koff + c]) * scale;
+        vv = to_f(a.qkv[base + voff + c]);
+      }
+      Ks[s * (ch + 1) + c] = kv;
+      Vs[s * ch + c] = vv;
+    }
+    __syncthreads();
+    // score for key (s0 + lane): needs the full q -> gather q via shuffles
+    float sc = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH_PER_LANE; ++j) {
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        const float qv = __shfl_sync(0xffffffffu, qreg[j], l);
+        const int c = l + 32 * j;
+        if (c < ch) sc = fmaf(qv, Ks[lane * (ch + 1) + c], sc);
+      }
+    }
+    if (s0 + lane >= a.T_len) sc = -INFINITY;
+    const float m_new = fmaxf(m_run, warp_max(sc));
+    const float p = __expf(sc - m_new);
+    const float corr = __expf(m_run - m_new);
+    l_run = l_run * corr + warp_sum(p);
+#pragma unroll
+    for (int j = 0; j < CH_PER_LANE; ++j) acc[j] *= corr;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) {
+      const float pl = __shfl_sync(0xffffffffu, p, l);
+#pragma unroll
+      for (int j = 0; j < CH_PER_LANE; ++j) {
+        const int c = lane + 32 * j;
+        if (c < ch) acc[j] = fmaf(pl, Vs[l * ch + c], acc[j]);
+      }
+    }
+    m_run = m_new;
+  }
+  if (qvalid) {
+    const float inv = 1.0f / l_run;
+#pragma unroll
+    for (int j = 0; j < CH_PER_LANE; ++j) {
+      const int c = lane + 32 * j;
+      if (c < ch) a.out[(row0 + q_idx) * C + h * ch + c] = from_f<T>(acc[j] * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Timestep / class embedding path (fp32 always; rows = distinct (t, y) combinations).
+// ---------------------------------------------------------------------------------------
+// semb[row] = SiLU( W2 * SiLU(W1 * sinus(t_row) + b1) + b2 + label_emb[y_row] )
+// Kernel 1: hidden[row][j] = SiLU(W1 sinus + b1)       (one CTA per row)
+__global__ void time_hidden_kernel(const float* __restrict__ t_rows, int mc, int ted,
+                                   const float* __restrict__ w1, const float* __restrict__ b1,
+                                   float* __restrict__ hidden) {
+  extern __shared__ float sin_emb[];   // [mc]
+  const int row = blockIdx.x;
+  const float t = t_rows[row];
+  const int half = mc / 2;
+  for (int i = threadIdx.x; i < mc; i += blockDim.x) {
+    float v = 0.f;
+    if (i < 2 * half) {
+      const int k = (i < half) ? i : i - half;
+      const float f = expf(-logf(10000.0f) * (float)k / (float)half);
+      const float ang = t * f;
+      v = (i < half) ? cosf(ang) : sinf(ang);
+    }
+    sin_emb[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < ted; j += nw) {
+    float s = 0.f;
+    for (int i = lane; i < mc; i += 32) s = fmaf(w1[(long long)j * mc + i], sin_emb[i], s);
+    s = warp_sum(s);
+    if (lane == 0) hidden[(long long)row * ted + j] = silu_exact(s + b1[j]);
+  }
+}
+
+// Generic row-times-matrix: out[row][j] = act( b[j] + sum_i W[j][i] * in[row][i] + add[idx[row]][j] )
+__global__ void linear_rows_kernel(const float* __restrict__ in, int in_dim, const float* __restrict__ W,
+                                   const float* __restrict__ bvec, int out_dim,
+                                   const float* __restrict__ add_table, const long long* __restrict__ add_idx,
+                                   int act_silu, float* __restrict__ out) {
+  const int row = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int j = blockIdx.x * nw + warp;
+  if (j >= out_dim) return;
+  const float* x = in + (long long)row * in_dim;
+  float s = 0.f;
+  for (int i = lane; i < in_dim; i += 32) s = fmaf(W[(long long)j * in_dim + i], x[i], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += bvec[j];
+    if (add_table) s += add_table[add_idx[row] * out_dim + j];
+    out[(long long)row * out_dim + j] = act_silu ? silu_exact(s) : s;
+  }
+}
+
+}  // namespace cfm

@@ -1,0 +1,206 @@
+"""GPU parity of the sampling loops (Euler / dopri5 / DDPM reverse chains) against the CPU oracle,
+with identical seeded weights, noise tensors and masks."""
+import numpy as np
+import pytest
+import torch
+
+from golden_configs import GOLDEN_CONFIGS
+from oracle import ddpm as D
+from oracle import integrators as I
+from oracle import unet as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def small_cfm(pkg, cuda, precision, **kw):
+    cfg = O.config_from_wrapper((3, 16, 16), 32, 1, channel_mult=(1, 2), attention_resolutions="8", num_heads=2, **kw)
+    params = O.seeded_params(cfg, 31)
+    m = pkg.UNetModelWrapper(dim=(3, 16, 16), num_channels=32, num_res_blocks=1, channel_mult=(1, 2),
+                             attention_resolutions="8", num_heads=2, precision=precision, **kw)
+    m.load_state_dict(params)
+    return cfg, params, m.to(cuda).eval()
+
+
+def test_step_kernels_bit_exact(pkg, cuda):
+    """Euler update, uint8 conversion and RK stage combination are bit-identical to the torch CPU expressions."""
+    x = torch.randn(5, 3, 16, 16); v = torch.randn(5, 3, 16, 16)
+    got = pkg.rk_combine(x.to(cuda), [v.to(cuda)], [1.0], 0.01).cpu()
+    assert torch.equal(got, x + torch.tensor(0.01) * v)
+    ks = [torch.randn(1000) for _ in range(7)]
+    coefs = I._C_MID
+    want = torch.zeros(1000)
+    first = True
+    for c, k in zip(coefs, ks):
+        if c != 0:
+            want = torch.tensor(c, dtype=torch.float32) * k if first else want + torch.tensor(c, dtype=torch.float32) * k
+            first = False
+    y = torch.randn(1000)
+    got = pkg.rk_combine(y.to(cuda), [k.to(cuda) for k in ks], coefs, 0.3).cpu()
+    assert torch.equal(got, y + torch.tensor(0.3) * want)
+    lib = pkg._lib.load()
+    import ctypes as C
+    z = (torch.randn(4097, device=cuda) * 2)
+    out = torch.empty(4097, dtype=torch.uint8, device=cuda)
+    assert lib.cfm_quantize_u8(C.c_void_p(out.data_ptr()), C.c_void_p(z.data_ptr()), 4097, None) == 0
+    assert torch.equal(out.cpu(), D.to_uint8(z.cpu()))          # compute_fid.py:87
+
+
+def test_box_condition_bit_exact(pkg, cuda):
+    img = torch.rand(9, 3, 64, 64) * 2 - 1
+    for cls, fn, patch in ((pkg.InPainting, D.inpainting_condition, 20), (pkg.OutPainting, D.outpainting_condition, 24)):
+        lk = cls(patch_size=patch, pad_value=-2)
+        torch.manual_seed(11)
+        want = fn(img, patch, -2.0)
+        torch.manual_seed(11)
+        got = lk.sample(img.to(cuda)).cpu()
+        assert torch.equal(got, want)
+        assert torch.equal(got == -2.0, want == -2.0)
+    with pytest.raises(RuntimeError):
+        pkg.InPainting(patch_size=20, pad_value=-2).sample(torch.zeros(1, 1, 28, 28, device=cuda))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_euler_trajectory_matches_oracle(pkg, cuda, precision, tol):
+    cfg, params, m = small_cfm(pkg, cuda, precision)
+    x0 = torch.randn(6, 3, 16, 16)
+    t_span = torch.linspace(0, 1, 11)
+    want = I.euler_trajectory(lambda t, x: O.wrapper_forward(cfg, params, t, x), x0, t_span)
+    node = pkg.NeuralODE(m, solver="euler", sensitivity="adjoint")
+    got = node.trajectory(x0.to(cuda), t_span.to(cuda)).cpu()
+    assert got.shape == want.shape == (11, 6, 3, 16, 16)
+    assert torch.equal(got[0], x0)
+    drift = rel_l2(got[-1], want[-1])
+    print(f"euler[{precision}] final-sample drift rel-L2 = {drift:.3e}")
+    assert drift < tol
+    # final-state-only entry point, with CUDA graph, agrees bit-for-bit with the trajectory's last state
+    xf, img = pkg.sample_euler(m, x0.to(cuda), t_span, return_uint8=True, use_graph=True)
+    assert torch.equal(xf.cpu(), got[-1])
+    assert torch.equal(img.cpu(), D.to_uint8(got[-1]))
+    xf2 = pkg.sample_euler(m, x0.to(cuda), t_span, use_graph=False)
+    assert torch.equal(xf2.cpu(), got[-1])
+
+
+def test_euler_conditional_state_drift(pkg, cuda):
+    """utils_mnist2.py:118-134: state = cat(x, con), d(con)/dt = con  (SURVEY F8)."""
+    cfg = O.config_from_wrapper((1, 28, 28), 32, 1, extra_in_channels=1)
+    params = O.seeded_params(cfg, 32)
+    m = pkg.InPaintModelWrapper(dim=(1, 28, 28), num_channels=32, num_res_blocks=1, precision="fp32")
+    m.load_state_dict(params)
+    m = m.to(cuda).eval()
+    x0 = torch.randn(4, 1, 28, 28)
+    torch.manual_seed(5)
+    con = D.inpainting_condition(torch.rand(4, 1, 28, 28) * 2 - 1, 14)
+    t_span = torch.linspace(0, 1, 6)
+
+    def ode(t, s):
+        v = O.inpaint_forward(cfg, params, s[:, :1], t, s[:, 1:])
+        return torch.cat([v, s[:, 1:]], dim=1)
+    want = I.euler_trajectory(ode, torch.cat([x0, con], 1), t_span)[-1]
+    ts, dts = pkg.euler_time_grid(t_span)
+    xf, _, _ = m.engine().sample_euler(x0.to(cuda), ts, dts, cond=con.to(cuda), cond_drift=True)
+    assert rel_l2(xf.cpu(), want[:, :1]) < 2e-4
+    # generic-callable path through NeuralODE (python vector field around the engine)
+    node = pkg.NeuralODE(lambda t, s, args=None: torch.cat([m.forward(s[:, :1], t, con=s[:, 1:]), s[:, 1:]], 1), solver="euler")
+    got = node.trajectory(torch.cat([x0, con], 1).to(cuda), t_span.to(cuda))[-1].cpu()
+    assert rel_l2(got, want) < 2e-4
+
+
+def test_dopri5_matches_oracle_controller(pkg, cuda):
+    cfg, params, m = small_cfm(pkg, cuda, "fp32")
+    x0 = torch.randn(4, 3, 16, 16)
+    so, sg = {}, {}
+    want = I.dopri5(lambda t, x: O.wrapper_forward(cfg, params, t, x), x0, [0.0, 1.0], 1e-4, 1e-4, stats=so)
+    got = pkg.odeint(m, x0.to(cuda), torch.linspace(0, 1, 2), rtol=1e-4, atol=1e-4, method="dopri5", stats=sg)
+    assert got.shape == (2, 4, 3, 16, 16)
+    assert sg == so, (sg, so)                       # same accepted/rejected step sequence
+    assert rel_l2(got[-1].cpu(), want[-1]) < 5e-4
+    # tuple state (x, con) as in utils_mnist.py:96-108
+    ca, cb = pkg.odeint(lambda t, s: (m(t, s[0]), s[1]), (x0.to(cuda), torch.ones(4, 2, device=cuda)),
+                        torch.linspace(0, 1, 2), rtol=1e-4, atol=1e-4, method="dopri5")
+    assert ca.shape == (2, 4, 3, 16, 16) and abs(float(cb[-1, 0, 0]) - np.e) < 1e-3
+
+
+def ddpm_setup(pkg, cuda, precision, in_ch, Ns):
+    cfg = O.config_from_create_model(image_size=16, in_channels=in_ch, out_channels=1, num_channels=32, num_res_blocks=1,
+                                     channel_mult="1,2", attention_resolutions="8", resblock_updown=True)
+    params = O.seeded_params(cfg, 41)
+    net = pkg.create_model(image_size=16, in_channels=in_ch, out_channels=1, num_channels=32, num_res_blocks=1,
+                           channel_mult="1,2", attention_resolutions="8", resblock_updown=True, precision=precision)
+    net.load_state_dict(params)
+    net = net.to(cuda).eval()
+    ddpm = pkg.DDPM(Ns)
+    eps_oracle = lambda xi, t: O.unet_forward(cfg, params, xi, t)
+    return net, ddpm, eps_oracle
+
+
+class NoiseTape:
+    """Replays one [Ns, 2, n] tensor in the oracle's call order (q_sample draw, then posterior draw)."""
+
+    def __init__(self, Ns, shape, mode):
+        self.t = torch.randn(Ns, 2, int(np.prod(shape)))
+        self.i, self.slot, self.Ns, self.mode = Ns - 1, 0 if mode == "replacement" else 1, Ns, mode
+
+    def __call__(self, shape):
+        z = self.t[self.i, self.slot].reshape(shape)
+        if self.mode == "replacement" and self.slot == 0:
+            self.slot = 1
+        else:
+            self.i -= 1
+            self.slot = 0 if self.mode == "replacement" else 1
+        return z
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 6e-2)])
+def test_ddpm_replacement_inpainting(pkg, cuda, precision, tol):
+    Ns = 40
+    net, ddpm, eps_oracle = ddpm_setup(pkg, cuda, precision, 1, Ns)
+    torch.manual_seed(2)
+    img = torch.rand(3, 1, 16, 16) * 2 - 1
+    cond = img.clone(); cond[:, :, 5:11, 4:10] = -2.0
+    xT = torch.randn(3, 1, 16, 16)
+    tape = NoiseTape(Ns, xT.shape, "replacement")
+    want = D.sample_replacement(eps_oracle, Ns, xT, cond, tape)
+    fn = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Replacement(start_fraction=1.0, noise=True),
+                                       pkg.InPainting(6, -2.0), noise=tape.t)
+    got = fn(xT.to(cuda), cond.to(cuda)).cpu()
+    assert got.abs().max() <= 1.0
+    d = rel_l2(got, want)
+    print(f"ddpm replacement[{precision}] final-sample drift = {d:.3e}")
+    assert d < tol
+    # start_fraction < 1 and un-noised condition variants take the same code path as the oracle
+    tape2 = NoiseTape(Ns, xT.shape, "replacement")
+    want2 = D.sample_replacement(eps_oracle, Ns, xT, cond, lambda s: torch.zeros(s), start_fraction=0.5, noise_condition=False)
+    fn2 = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Replacement(start_fraction=0.5, noise=False),
+                                        pkg.InPainting(6, -2.0), noise=torch.zeros_like(tape2.t), use_graph=True)
+    assert rel_l2(fn2(xT.to(cuda), cond.to(cuda)).cpu(), want2) < tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 6e-2)])
+def test_ddpm_amortized_and_prior(pkg, cuda, precision, tol):
+    Ns = 30
+    net, ddpm, eps_oracle = ddpm_setup(pkg, cuda, precision, 2, Ns)
+    cond = torch.rand(2, 1, 16, 16) * 2 - 1; cond[:, :, 3:9, 3:9] = -2.0
+    xT = torch.randn(2, 1, 16, 16)
+    tape = NoiseTape(Ns, xT.shape, "amortized")
+    want = D.sample_amortized(eps_oracle, Ns, xT, cond, tape)
+    fn = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(0.9, 0, 0.1), pkg.InPainting(6, -2.0),
+                                       noise=tape.t)
+    assert rel_l2(fn(xT.to(cuda), cond.to(cuda)).cpu(), want) < tol
+    # prior sampling with an amortised network substitutes none_like(x) = pad_value for the condition
+    tape = NoiseTape(Ns, xT.shape, "amortized")
+    want = D.sample_amortized(eps_oracle, Ns, xT, torch.full_like(cond, -2.0), tape)
+    pf = pkg.get_prior_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(0.9, 0, 0.1), pkg.InPainting(6, -2.0), noise=tape.t)
+    assert rel_l2(pf(xT.to(cuda)).cpu(), want) < tol
+
+
+def test_ddpm_device_rng_statistics(pkg, cuda):
+    """Seeded Philox path: finite, clipped, reproducible, seed-sensitive."""
+    net, ddpm, _ = ddpm_setup(pkg, cuda, "bf16", 1, 30)
+    fn = lambda seed: pkg.get_prior_sample_fn(pkg.EpsModel(net, ddpm), ddpm, None, None, seed=seed)(torch.randn(4, 1, 16, 16, generator=torch.Generator().manual_seed(0)).to(cuda))
+    a, b, c = fn(1), fn(1), fn(2)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert torch.isfinite(a).all() and a.abs().max() <= 1.0

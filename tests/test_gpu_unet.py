@@ -1,0 +1,121 @@
+"""GPU parity of one NFE: the CUDA engine (through the C ABI) against the CPU oracle and the
+committed golden vectors of the reference's own code.
+
+Tolerances (north_star): fp32 mode <= 1e-4 relative L2 per NFE; bf16 mode <= 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_configs import GOLDEN_CONFIGS
+from oracle import unet as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def build(pkg, cfg, params, precision, dev):
+    m = pkg.UNetModel(image_size=cfg.image_size, in_channels=cfg.in_channels, model_channels=cfg.model_channels,
+                      out_channels=cfg.out_channels, num_res_blocks=cfg.num_res_blocks,
+                      attention_resolutions=cfg.attention_ds, channel_mult=cfg.channel_mult, num_classes=cfg.num_classes,
+                      num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels,
+                      num_heads_upsample=cfg.num_heads_upsample, use_scale_shift_norm=cfg.use_scale_shift_norm,
+                      resblock_updown=cfg.resblock_updown, use_new_attention_order=cfg.use_new_attention_order,
+                      precision=precision)
+    m.load_state_dict(params)
+    return m.to(dev).eval()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
+def test_nfe_matches_reference_golden(pkg, cuda, name, precision):
+    cfg, _, _ = GOLDEN_CONFIGS[name]
+    g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
+    params = O.seeded_params(cfg, int(g["seed"]))
+    m = build(pkg, cfg, params, precision, cuda)
+    out = m(torch.from_numpy(g["x"]).to(cuda), torch.from_numpy(g["t"]).to(cuda)).cpu()
+    assert m.engine().param_count == int(g["n_params"])
+    r = rel_l2(out, torch.from_numpy(g["out"]))
+    print(f"{name}[{precision}] rel-L2 = {r:.3e}")
+    assert r < TOL[precision], r
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_wrapper_scalar_t_and_class_labels(pkg, cuda, precision):
+    # conditional_mnist.ipynb cell 2-4: UNetModel(dim=(1,28,28), num_channels=32, num_res_blocks=1, num_classes=10, class_cond=True)
+    cfg = O.config_from_wrapper((1, 28, 28), 32, 1, class_cond=True, num_classes=10)
+    params = O.seeded_params(cfg, 21)
+    m = pkg.UNetModelWrapper(dim=(1, 28, 28), num_channels=32, num_res_blocks=1, num_classes=10, class_cond=True,
+                             precision=precision)
+    m.load_state_dict(params)
+    m = m.to(cuda).eval()
+    x = torch.randn(20, 1, 28, 28)
+    y = torch.arange(10).repeat(2)
+    t0 = torch.tensor(0.4321)
+    want = O.wrapper_forward(cfg, params, t0, x, y)
+    got = m(t0.to(cuda), x.to(cuda), y.to(cuda)).cpu()           # 0-dim t: shared-row embedding path
+    assert rel_l2(got, want) < TOL[precision]
+    tb = torch.rand(20)
+    want = O.wrapper_forward(cfg, params, tb, x, y)
+    got = m(tb.to(cuda), x.to(cuda), y.to(cuda), args={}).cpu()  # per-sample t; torchdyn's extra kwarg tolerated
+    assert rel_l2(got, want) < TOL[precision]
+    with pytest.raises(AssertionError):
+        m(t0.to(cuda), x.to(cuda))                               # y required iff class conditional
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_inpaint_and_superres_wrappers(pkg, cuda, precision):
+    cfg = O.config_from_wrapper((1, 28, 28), 32, 1, extra_in_channels=1)
+    params = O.seeded_params(cfg, 22)
+    m = pkg.InPaintModelWrapper(dim=(1, 28, 28), num_channels=32, num_res_blocks=1, num_classes=None, class_cond=True,
+                                precision=precision)
+    m.load_state_dict(params)
+    m = m.to(cuda).eval()
+    x, con = torch.randn(3, 1, 28, 28), torch.rand(3, 1, 28, 28) * 2 - 1
+    con[:, :, 6:20, 7:21] = -2.0
+    t = torch.tensor(0.25)
+    want = O.inpaint_forward(cfg, params, x, t, con)
+    got = m.forward(x.to(cuda), t.to(cuda), con=con.to(cuda)).cpu()     # (x, t) order: utils_mnist.py:97
+    assert rel_l2(got, want) < TOL[precision]
+
+    cfg = O.config_from_wrapper((3, 32, 32), 32, 1, extra_in_channels=3, channel_mult=(1, 2))
+    params = O.seeded_params(cfg, 23)
+    s = pkg.SuperResModelWrapper(dim=(3, 32, 32), num_channels=32, num_res_blocks=1, channel_mult=(1, 2),
+                                 num_classes=None, class_cond=True, precision=precision)
+    s.load_state_dict(params)
+    s = s.to(cuda).eval()
+    x, lo = torch.randn(2, 3, 32, 32), torch.rand(2, 3, 8, 8)
+    want = O.superres_forward(cfg, params, x, t, lo)
+    got = s.forward(x.to(cuda), t.to(cuda), low_res=lo.to(cuda)).cpu()
+    assert rel_l2(got, want) < TOL[precision]
+
+
+def test_batch_independence_and_ragged_batches(pkg, cuda):
+    # samples are independent (per-sample GroupNorm / attention): any batch split gives the same rows
+    cfg, _, _ = GOLDEN_CONFIGS["tiny_neworder"]
+    params = O.seeded_params(cfg, 5)
+    for precision in ("fp32", "bf16"):
+        m = build(pkg, cfg, params, precision, cuda)
+        x = torch.randn(37, 3, 16, 16, device=cuda)
+        t = torch.rand(37, device=cuda)
+        full = m(x, t)
+        parts = torch.cat([m(x[:1], t[:1]), m(x[1:20], t[1:20]), m(x[20:], t[20:])])
+        assert torch.equal(full, parts)
+    with pytest.raises(ValueError):
+        m(torch.randn(2, 3, 15, 16, device=cuda), torch.rand(2, device=cuda))
+
+
+def test_engine_flops_and_param_accounting(pkg, cuda):
+    cfg, _, _ = GOLDEN_CONFIGS["cifar"]
+    m = build(pkg, cfg, O.seeded_params(cfg, 0), "bf16", cuda)
+    e = m.engine()
+    assert e.param_count == 35_746_307
+    assert abs(e.flops_per_sample / 1e9 - 12.444) < 0.01
+    m(torch.randn(1, 3, 32, 32, device=cuda), torch.rand(1, device=cuda))
+    assert e.last_launches > 0

@@ -1,0 +1,109 @@
+"""Oracle pinning (CPU): against the committed golden vectors (outputs of the reference's own
+code) and, when /root/reference is present, against the live vendored modules."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _refload import load_reference, reference_available
+from golden_configs import GOLDEN_CONFIGS
+from oracle import ddpm as D
+from oracle import unet as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
+def test_unet_oracle_matches_reference_golden(name):
+    cfg, batch, seed = GOLDEN_CONFIGS[name]
+    g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
+    assert int(g["n_params"]) == O.count_params(cfg)
+    p = O.seeded_params(cfg, int(g["seed"]))
+    out = O.unet_forward(cfg, p, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]))
+    want = torch.from_numpy(g["out"])
+    rel = float((out - want).norm() / want.norm())
+    assert rel < 1e-5, rel      # same ops, same machine class: essentially bit-identical
+
+
+def test_known_parameter_counts():
+    # SURVEY F4 / BASELINE.md: notebook prints 1.23M; CIFAR 35,746,307; flowers 68,156,163
+    assert O.count_params(GOLDEN_CONFIGS["cifar"][0]) == 35_746_307
+    assert O.count_params(GOLDEN_CONFIGS["flowers_ddpm"][0]) == 68_156_163
+    c = O.config_from_create_model(image_size=28, in_channels=1, out_channels=1, num_channels=32, num_res_blocks=1,
+                                   channel_mult="1, 2, 2", resblock_updown=True)
+    assert O.count_params(c) == 1_225_185
+    fl = O.flops_per_sample(GOLDEN_CONFIGS["cifar"][0])
+    assert abs(fl["total"] / 1e9 - 12.444) < 0.01
+
+
+def test_ddpm_tables_match_reference_golden():
+    g = np.load(os.path.join(GOLD, "ddpm_reference.npz"))
+    for Ns in (1000, 20):
+        tb = D.ddpm_tables(Ns)
+        for k in tb:
+            if k == "ts":
+                continue
+            assert np.array_equal(tb[k].numpy(), g[f"Ns{Ns}.{k}"]), (Ns, k)
+    tb = D.ddpm_tables(1000)
+    assert abs(float(tb["alphas_cumprod"][0]) - 0.9998998) < 1e-7
+    assert abs(float(tb["posterior_log_variance_clipped"][0]) + 46.0517) < 1e-3
+    x, e, z = (torch.from_numpy(g[f"step.{k}"]) for k in ("x", "eps", "z"))
+    for i in (0, 1, 500, 999):
+        got, _ = D.posterior_step(tb, x, e, i, z)
+        assert np.array_equal(got.numpy(), g[f"step.out{i}"]), i
+        assert float(D.eps_time(i, 1000)) == float(g[f"step.t{i}"][0])
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+def test_oracle_matches_live_reference_unet():
+    ref = load_reference()
+    cfg, _, _ = GOLDEN_CONFIGS["tiny_neworder"]
+    m = ref.unet.UNetModel(image_size=cfg.image_size, in_channels=cfg.in_channels, model_channels=cfg.model_channels,
+                           out_channels=cfg.out_channels, num_res_blocks=cfg.num_res_blocks,
+                           attention_resolutions=cfg.attention_ds, channel_mult=cfg.channel_mult,
+                           num_heads=cfg.num_heads, use_new_attention_order=True).eval()
+    assert list(m.state_dict().keys()) == list(O.param_shapes(cfg).keys())
+    p = O.seeded_params(cfg, 11)
+    m.load_state_dict(p)
+    x, t = torch.randn(2, 3, 16, 16), torch.rand(2)
+    with torch.no_grad():
+        want = m(x, t)
+    assert torch.equal(want, O.unet_forward(cfg, p, x, t))
+
+
+def test_mask_sampler_rng_order_and_bounds():
+    # h is drawn before w, both randint(5, S-p-5) from the global CPU generator (likelihoods.py:49-53)
+    img = torch.rand(5, 1, 28, 28) * 2 - 1
+    boxes = []
+    torch.manual_seed(3)
+    cond = D.inpainting_condition(img, 14, -2.0, boxes=boxes)
+    torch.manual_seed(3)
+    for (h, w) in boxes:
+        assert h == int(torch.randint(5, 28 - 14 - 5, size=())) and w == int(torch.randint(5, 28 - 14 - 5, size=()))
+        assert 5 <= h < 9 and 5 <= w < 9
+    for k, (h, w) in enumerate(boxes):
+        m = cond[k] == -2.0
+        assert int(m.sum()) == 14 * 14 and bool(m[:, h:h + 14, w:w + 14].all())
+        assert torch.equal(cond[k][~m], img[k][~m])
+    with pytest.raises(RuntimeError):   # MNIST with the default patch 20 cannot draw a box
+        D.inpainting_condition(img, 20)
+    out = D.outpainting_condition(img, 14, -2.0)
+    assert int((out != -2.0).sum()) == 5 * 14 * 14
+
+
+def test_samplers_consume_noise_in_reference_order():
+    calls = []
+
+    def noise(shape):
+        calls.append(tuple(shape))
+        return torch.zeros(shape)
+
+    eps = lambda x, t: torch.zeros(x.shape[0], 1, 8, 8)
+    xT = torch.randn(2, 1, 8, 8)
+    cond = torch.full((2, 1, 8, 8), -2.0); cond[:, :, :4] = 0.3
+    D.sample_replacement(eps, 30, xT, cond, noise)   # Ns > 20 keeps beta < 1
+    assert len(calls) == 30 + 29          # q_sample every step, posterior noise for i > 0
+    calls.clear()
+    out = D.sample_amortized(lambda x, t: torch.zeros(x.shape[0], 1, 8, 8), 30, xT, cond, noise)
+    assert len(calls) == 29 and out.abs().max() <= 1
