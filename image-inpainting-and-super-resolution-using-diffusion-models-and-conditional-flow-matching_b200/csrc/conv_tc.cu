@@ -1,10 +1,461 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the kernel lands in this file).
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+//   D[m, n] = sum_{segment, tap, c} A_seg[pixel(m) + tap, c] * W[kiter][n][c]      bf16 x bf16 -> fp32
+//
+// * M = output pixels.  A CTA tile is 128 pixels = a (bn x bh x bw) box of the NHWC tensor, so one
+//   4-D TMA box load per (tap, 64-channel chunk) lands as 128 rows x 128 B in shared memory in
+//   exactly the K-major SWIZZLE_128B layout tcgen05.mma consumes.  The 3x3 halo is produced by
+//   shifting the box origin by the tap offset; out-of-bounds rows/cols (the zero padding) are
+//   zero-filled by the TMA unit.  Stride-2 convs use the tensor map's element strides.
+// * K runs over up to three "segments": the main 3x3 (or 1x1) operand and the ResBlock's 1x1 skip
+//   operand(s), whose products accumulate into the same TMEM tile - so `skip_connection(x) + h`
+//   and the never-materialised channel concat `cat([h, hs.pop()])` cost no extra pass.
+// * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+//   warps 2..5 = epilogue (TMEM -> registers -> +bias +emb +residual -> bf16 -> global).  Two TMEM
+//   accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cstdio>
+#include <cstring>
+#include <map>
 #include "engine.h"
+#include "common.cuh"
+
 namespace cfm {
-bool tc_conv_supported(const Engine&, const Op&) { return false; }
-int tc_conv_prepare(Engine&, Op&, const std::vector<float>&, const std::vector<float>&) { return 0; }
-int tc_conv_launch(Engine& e, const Op&, int, cudaStream_t) { e.err = "tcgen05 conv not built"; return CFM_ERR_INTERNAL; }
-void tc_conv_release(Engine&) {}
+
+void* tensor_ptr(const Engine& e, int id, int B);
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
+constexpr int TC_MAX_N = 256;
+constexpr int TC_B_BYTES_MAX = TC_MAX_N * TC_BLOCK_K * 2; // 32 KB
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES_MAX) + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcSeg { int map; int n_chunks; int ks; int stride; };
+
+struct TcParams {
+  int n_seg; TcSeg seg[3];
+  int total_k;
+  int B, H, W;                 // output spatial size
+  int bw, bh, bn;              // tile box, bw*bh*bn == 128
+  int tiles_w, tiles_h, tiles_b, tiles_n, n_tiles;
+  int block_n, Cout;
+  const float* bias;
+  const float* emb; int emb_stride; const int* emb_row;
+  const bf16* res0; const bf16* res1; int R0, R1;
+  bf16* out;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+// start address >> 4 | LBO(ignored for swizzled K-major) = 1 | SBO = 1024 B (8 rows x 128 B) | layout 2.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+               const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;                                   // [stages][16 KB]
+  uint8_t* smem_b = smem + TC_STAGES * TC_A_BYTES;          // [stages][block_n * 128 B]
+  const int b_bytes = p.block_n * TC_BLOCK_K * 2;
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES_MAX));
+  uint64_t* full_bar = bars;                 // [stages]
+  uint64_t* empty_bar = bars + TC_STAGES;    // [stages]
+  uint64_t* tfull_bar = bars + 2 * TC_STAGES;      // [2]
+  uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2; // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+    if (p.n_seg > 1) prefetch_tmap(&mapA1);
+    if (p.n_seg > 2) prefetch_tmap(&mapA2);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int mt = tile / p.tiles_n;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tb = mt / p.tiles_h;
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tb * p.bn;
+        int kiter = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const TcSeg sg = p.seg[s];
+          const CUtensorMap* map = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
+          const int taps = sg.ks * sg.ks, pad = sg.ks >> 1;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = tap / sg.ks - pad, dx = tap % sg.ks - pad;
+            for (int ch = 0; ch < sg.n_chunks; ++ch, ++kiter) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], TC_A_BYTES + b_bytes);
+              tma_load_4d(smem_a + stage * TC_A_BYTES, map, &full_bar[stage], ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+              tma_load_2d(smem_b + stage * b_bytes, &mapB, &full_bar[stage], 0, kiter * p.Cout + nt * p.block_n);
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(TC_BLOCK_M, p.block_n);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+      for (int k = 0; k < p.total_k; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_desc_sw128(smem_u32(smem_a + stage * TC_A_BYTES));
+          const uint64_t bdesc = make_desc_sw128(smem_u32(smem_b + stage * b_bytes));
+#pragma unroll
+          for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk)
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
+          if (k == p.total_k - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      int mt = tile / p.tiles_n;
+      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tb = mt / p.tiles_h;
+      const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
+      const int n = tb * p.bn + ni, h = th * p.bh + hi, w = tw * p.bw + wi;
+      const bool valid = n < p.B;
+      const long long pix = ((long long)n * p.H + h) * p.W + w;
+      const float* embp = (p.emb && valid) ? p.emb + (long long)p.emb_row[n] * p.emb_stride : nullptr;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int cg = nt * p.block_n + c0;    // first output channel of this chunk
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg((const float4*)(p.bias + cg + j));
+            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (embp) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 e4 = __ldg((const float4*)(embp + cg + j));
+              f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
+            }
+          }
+          if (p.res0) {
+            const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cg : p.res1 + pix * p.R1 + (cg - p.R0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 r4 = *(const uint4*)(rp + j);
+              const __nv_bfloat162* rb = (const __nv_bfloat162*)&r4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
+            }
+          }
+          bf16* op = p.out + pix * p.Cout + cg;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o4;
+            __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+            *(uint4*)(op + j) = o4;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcMaps { CUtensorMap a[3]; CUtensorMap b; };
+
+struct TcConvPlan {
+  bf16* w_packed = nullptr;     // [total_k * Cout][64]
+  int n_seg = 0; TcSeg seg[3];
+  int seg_tensor[3] = {-1, -1, -1};
+  int total_k = 0, block_n = 0;
+  int bw = 0, bh = 0, bn = 0;
+  std::map<int, TcMaps> maps;   // per batch size
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::vector<TcConvPlan*> g_plans_dummy;
+
+static int get_encode(Engine& e) {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t st = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (st != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) { e.err = "cuTensorMapEncodeTiled entry point not available"; return CFM_ERR_CUDA; }
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static bool env_off(const char* name) { const char* v = getenv(name); return v && v[0] == '1'; }
+
+static int pick_block_n(int Cout) {
+  for (int n : {256, 192, 128, 96, 64, 32})
+    if (Cout % n == 0) return n;
+  return 0;
+}
+
+bool tc_conv_supported(const Engine& e, const Op& op) {
+  if (!e.bf16 || op.kind != OP_CONV || op.src_is_input || op.out_is_output) return false;
+  if (env_off("CFM_DISABLE_TC")) return false;
+  if (op.ups) return false;                                  // plan materialises the upsample in bf16 mode
+  if (op.stride != 1 && op.stride != 2) return false;
+  if (op.stride == 2 && env_off("CFM_DISABLE_TC_STRIDE2")) return false;
+  if (op.ks != 1 && op.ks != 3) return false;
+  if (pick_block_n(op.Cout) == 0) return false;
+  if (!pow2(op.Hout) || !pow2(op.Wout) || op.Wout > 128 || op.Hout > 128) return false;
+  if (op.stride == 2 && (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout || 2 * std::min(op.Wout, 128) > 256)) return false;
+  auto chan_ok = [&](int id) { return id < 0 || e.tensors[id].C % TC_BLOCK_K == 0; };
+  if (op.src1 >= 0) return false;                            // main operand is always a single (GN-output) tensor
+  if (!chan_ok(op.src0) || !chan_ok(op.skip0) || !chan_ok(op.skip1)) return false;
+  auto res_ok = [&](int id) { return id < 0 || e.tensors[id].C % 32 == 0; };
+  if (!res_ok(op.res0) || !res_ok(op.res1)) return false;
+  return true;
+}
+
+int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::vector<float>& ws) {
+  TcConvPlan* pl = new TcConvPlan();
+  const int Cout = op.Cout, Cin = op.Cin, ks = op.ks;
+  pl->block_n = pick_block_n(Cout);
+  pl->bw = std::min(op.Wout, 128);
+  pl->bh = std::min(op.Hout, 128 / pl->bw);
+  pl->bn = 128 / (pl->bw * pl->bh);
+  pl->seg[0] = {0, Cin / TC_BLOCK_K, ks, op.stride}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
+  if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
+  if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
+  pl->total_k = ks * ks * (Cin / TC_BLOCK_K) + op.Cskip / TC_BLOCK_K;
+  // pack: kiter-major, [Cout][64] per kiter, same iteration order as the producer warp
+  std::vector<bf16> packed((size_t)pl->total_k * Cout * TC_BLOCK_K);
+  size_t kiter = 0;
+  for (int tap = 0; tap < ks * ks; ++tap)
+    for (int ch = 0; ch < Cin / TC_BLOCK_K; ++ch, ++kiter)
+      for (int o = 0; o < Cout; ++o)
+        for (int j = 0; j < TC_BLOCK_K; ++j)
+          packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(w[((size_t)o * Cin + ch * TC_BLOCK_K + j) * ks * ks + tap]);
+  for (int ch = 0; ch < op.Cskip / TC_BLOCK_K; ++ch, ++kiter)
+    for (int o = 0; o < Cout; ++o)
+      for (int j = 0; j < TC_BLOCK_K; ++j)
+        packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(ws[(size_t)o * op.Cskip + ch * TC_BLOCK_K + j]);
+  void* d = nullptr;
+  if (cudaMalloc(&d, packed.size() * sizeof(bf16)) != cudaSuccess) { e.err = "cudaMalloc(packed conv weights) failed"; delete pl; return CFM_ERR_OOM; }
+  e.owned.push_back(d);
+  if (cudaMemcpy(d, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice) != cudaSuccess) { e.err = "weight upload failed"; delete pl; return CFM_ERR_CUDA; }
+  pl->w_packed = (bf16*)d;
+  op.tc = pl;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+      e.err = "cudaFuncSetAttribute(conv_tc_kernel, smem) failed"; return CFM_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  return get_encode(e);
+}
+
+static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
+  TcConvPlan* pl = op.tc;
+  std::memset(m, 0, sizeof(*m));
+  for (int s = 0; s < pl->n_seg; ++s) {
+    const TensorDesc& t = e.tensors[pl->seg_tensor[s]];
+    const int st = pl->seg[s].stride;
+    cuuint64_t dims[4] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)t.C * 2, (cuuint64_t)t.W * t.C * 2, (cuuint64_t)t.H * t.W * t.C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->bw * st), (cuuint32_t)(pl->bh * st), (cuuint32_t)pl->bn};
+    cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
+    CUresult r = g_encode(&m->a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, tensor_ptr(e, pl->seg_tensor[s], B), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
+  }
+  for (int s = pl->n_seg; s < 3; ++s) m->a[s] = m->a[0];
+  cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->total_k * op.Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)TC_BLOCK_K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)pl->block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->w_packed, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(B) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
+  return 0;
+}
+
+int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
+  TcConvPlan* pl = op.tc;
+  auto it = pl->maps.find(B);
+  if (it == pl->maps.end()) {
+    TcMaps m;
+    int rc = encode_maps(e, op, B, &m);
+    if (rc) return rc;
+    it = pl->maps.emplace(B, m).first;
+  }
+  TcParams p{};
+  p.n_seg = pl->n_seg;
+  for (int s = 0; s < 3; ++s) p.seg[s] = pl->seg[s];
+  p.total_k = pl->total_k;
+  p.B = B; p.H = op.Hout; p.W = op.Wout;
+  p.bw = pl->bw; p.bh = pl->bh; p.bn = pl->bn;
+  p.tiles_w = op.Wout / pl->bw; p.tiles_h = op.Hout / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
+  p.tiles_n = op.Cout / pl->block_n;
+  p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+  p.block_n = pl->block_n; p.Cout = op.Cout;
+  p.bias = op.bias;
+  if (op.emb_off >= 0) { p.emb = e.emb_out + op.emb_off; p.emb_stride = e.emb_total; p.emb_row = e.row_of_sample; }
+  p.res0 = (const bf16*)tensor_ptr(e, op.res0, B); p.R0 = op.res0 >= 0 ? e.tensors[op.res0].C : 0;
+  p.res1 = (const bf16*)tensor_ptr(e, op.res1, B); p.R1 = op.res1 >= 0 ? e.tensors[op.res1].C : 0;
+  p.out = (bf16*)tensor_ptr(e, op.out, B);
+  const int grid = std::min(p.n_tiles, e.sm_count);
+  conv_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+  return 0;
+}
+
+void tc_conv_release(Engine& e) {
+  for (Op& op : e.ops)
+    if (op.tc) op.tc->maps.clear();
+}
+
 bool gn_bf16_supported(const Engine&, const Op&) { return false; }
 int gn_bf16_launch(Engine& e, const Op&, int, cudaStream_t) { e.err = "bf16 groupnorm not built"; return CFM_ERR_INTERNAL; }
+
 }  // namespace cfm

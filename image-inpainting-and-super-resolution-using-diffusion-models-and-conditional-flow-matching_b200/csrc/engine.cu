@@ -270,7 +270,14 @@ static int build_plan(Engine& e) {
           if ((rc = add_resblock(e, pu, h, Cur{-1, 0, 0, 0}, h.C, true, false, emb_pieces, &h))) return rc;
         } else if (c.conv_resample) {
           const int t = new_tensor(e, h.C, h.H * 2, h.W * 2);
-          if ((rc = add_conv(e, pu + ".conv", pu + ".conv", 3, 1, 1, h.id, -1, false, h.C, h.H, h.W, h.C, "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
+          if (e.bf16) {
+            // tensor-core path: materialise the nearest-neighbour upsample once, then a plain 3x3 conv
+            const int u = new_tensor(e, h.C, h.H * 2, h.W * 2);
+            add_resample(e, pu + ".interpolate", h.id, u, 1);
+            if ((rc = add_conv(e, pu + ".conv", pu + ".conv", 3, 1, 0, u, -1, false, h.C, h.H * 2, h.W * 2, h.C, "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
+          } else {
+            if ((rc = add_conv(e, pu + ".conv", pu + ".conv", 3, 1, 1, h.id, -1, false, h.C, h.H, h.W, h.C, "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
+          }
           h = {t, h.C, h.H * 2, h.W * 2};
         } else {
           const int t = new_tensor(e, h.C, h.H * 2, h.W * 2);
@@ -446,7 +453,14 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         a.out = (T*)tensor_ptr(e, op.out, B);
         a.exact = e.bf16 ? 0 : 1;
         const int n = (op.Cin / 32) * a.HW;
-        const int cap = 48 * 1024 / 4;   // stay within the default dynamic smem limit
+        constexpr int kGnSmemBytes = 200 * 1024;
+        static bool gn_attr_set = false;
+        if (!gn_attr_set) {
+          CU_CHECK(e, cudaFuncSetAttribute(groupnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemBytes));
+          CU_CHECK(e, cudaFuncSetAttribute(groupnorm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemBytes));
+          gn_attr_set = true;
+        }
+        const int cap = kGnSmemBytes / 4;
         a.smem_elems = n <= cap ? n : 0;
         groupnorm_kernel<T><<<B * 32, 256, (size_t)a.smem_elems * 4, st>>>(a);
         e.launches++;

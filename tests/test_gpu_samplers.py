@@ -172,10 +172,11 @@ def test_ddpm_replacement_inpainting(pkg, cuda, precision, tol):
     print(f"ddpm replacement[{precision}] final-sample drift = {d:.3e}")
     assert d < tol
     # start_fraction < 1 and un-noised condition variants take the same code path as the oracle
-    tape2 = NoiseTape(Ns, xT.shape, "replacement")
-    want2 = D.sample_replacement(eps_oracle, Ns, xT, cond, lambda s: torch.zeros(s), start_fraction=0.5, noise_condition=False)
+    # (a noise-free chain through a random-weight net is chaotic: 1e-6 perturbations grow to 1e-3, so keep the noise)
+    tape2 = NoiseTape(Ns, xT.shape, "amortized")     # noise=False: only the posterior draw is consumed
+    want2 = D.sample_replacement(eps_oracle, Ns, xT, cond, tape2, start_fraction=0.5, noise_condition=False)
     fn2 = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Replacement(start_fraction=0.5, noise=False),
-                                        pkg.InPainting(6, -2.0), noise=torch.zeros_like(tape2.t), use_graph=True)
+                                        pkg.InPainting(6, -2.0), noise=tape2.t, use_graph=True)
     assert rel_l2(fn2(xT.to(cuda), cond.to(cuda)).cpu(), want2) < tol
 
 
