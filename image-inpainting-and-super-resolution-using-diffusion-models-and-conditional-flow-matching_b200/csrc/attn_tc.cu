@@ -1,0 +1,220 @@
+// Fused attention core on tcgen05/TMEM for the U-Net's AttentionBlock (unet.py:424-483):
+//   a = softmax((q s)^T (k s)) v,  s = ch^-1/4, per (sample, head); T = 256 tokens, ch = 64.
+//
+// One CTA per (sample, head, 128-query tile).  TMA brings the head's Q tile, K and V (128-byte
+// channel rows of the NHWC qkv tensor) into SWIZZLE_128B shared memory.  S = Q K^T is one
+// 128x256x64 UMMA chain into TMEM; each of the 128 threads owns one query row, reads it back with
+// tcgen05.ld, does an exact two-pass softmax in fp32 and writes bf16 P into shared memory in the
+// K-major swizzled layout (re-using the Q/K buffers); O = P V is a second UMMA chain (V consumed
+// as an MN-major B operand straight from its NHWC rows) into the same TMEM columns; the epilogue
+// normalises by the row sum and stores bf16.  96 KB smem + 256 TMEM columns -> 2 CTAs per SM, so
+// one CTA's softmax overlaps the other's MMAs and loads.
+#include <cstring>
+#include <map>
+#include "engine.h"
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace cfm {
+
+void* tensor_ptr(const Engine& e, int id, int B);
+
+constexpr int AT_T = 256, AT_D = 64, AT_M = 128;
+constexpr int AT_V_OFF = 0, AT_Q_OFF = 32768, AT_K_OFF = 49152, AT_P_OFF = 32768;
+constexpr int AT_BAR_OFF = 98304;
+constexpr int AT_SMEM = AT_BAR_OFF + 64 + 1024;
+
+struct AttnTcParams { int heads, C, new_order; float scale_log2; bf16* out; };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar_qk = (uint64_t*)(smem + AT_BAR_OFF);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;
+  uint64_t* bar_o = bar_qk + 3;
+  uint32_t* tmem_slot = (uint32_t*)(bar_qk + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
+  const int qcol = p.new_order ? h * AT_D : h * 3 * AT_D;
+  const int kcol = p.new_order ? p.C + h * AT_D : h * 3 * AT_D + AT_D;
+  const int vcol = p.new_order ? 2 * p.C + h * AT_D : h * 3 * AT_D + 2 * AT_D;
+  const int row0 = b * AT_T;
+
+  if (tid == 0) {
+    prefetch_tmap(&map);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_qk, 3 * 16384);
+      tma_load_2d(smem + AT_Q_OFF, &map, bar_qk, qcol, row0 + mt * AT_M);
+      tma_load_2d(smem + AT_K_OFF, &map, bar_qk, kcol, row0);
+      tma_load_2d(smem + AT_K_OFF + 16384, &map, bar_qk, kcol, row0 + 128);
+      mbar_expect_tx(bar_v, 2 * 16384);
+      tma_load_2d(smem + AT_V_OFF, &map, bar_v, vcol, row0);
+      tma_load_2d(smem + AT_V_OFF + 16384, &map, bar_v, vcol, row0 + 128);
+    }
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(AT_M, AT_T);
+      const uint64_t ad = make_desc_sw128(smem_u32(smem + AT_Q_OFF)), bd = make_desc_sw128(smem_u32(smem + AT_K_OFF));
+#pragma unroll
+      for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k > 0);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+  }
+
+  // ---- softmax: thread = query row (TMEM lane) ----
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  float mx = -INFINITY;
+  for (int c0 = 0; c0 < AT_T; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_row + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  const float mxs = mx * p.scale_log2;
+  float sum = 0.f;
+  const int r = tid;
+  uint8_t* prow = smem + AT_P_OFF + r * 128;
+  for (int c0 = 0; c0 < AT_T; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_row + (uint32_t)c0, v);
+    tmem_ld_wait();
+    uint8_t* pchunk = prow + (c0 >> 6) * 16384;
+    const int c16 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o4;
+      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(v[i * 8 + 2 * q]), p.scale_log2, -mxs));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(v[i * 8 + 2 * q + 1]), p.scale_log2, -mxs));
+        sum += e0 + e1;
+        o2[q] = __floats2bfloat162_rn(e0, e1);
+      }
+      *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+    }
+  }
+  fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy
+  tc_fence_before();
+  __syncthreads();
+
+  if (warp == 0) {
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_major(AT_M, AT_D, 0, 1);
+      const uint32_t pbase = smem_u32(smem + AT_P_OFF), vbase = smem_u32(smem + AT_V_OFF);
+#pragma unroll
+      for (int j = 0; j < AT_T / 16; ++j) {
+        const uint64_t ad = make_desc_sw128(pbase + (j >> 2) * 16384 + (j & 3) * 32);
+        const uint64_t bd = make_desc_sw128_mn(vbase + j * 2048, 1024);
+        umma_bf16(tmem, ad, bd, idesc, j > 0);
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  const float inv = 1.0f / sum;
+  bf16* op = p.out + ((long long)(row0 + mt * AT_M + r)) * p.C + h * AT_D;
+#pragma unroll
+  for (int c0 = 0; c0 < AT_D; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_row + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o4;
+      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o2[q] = __floats2bfloat162_rn(__uint_as_float(v[i * 8 + 2 * q]) * inv, __uint_as_float(v[i * 8 + 2 * q + 1]) * inv);
+      *(uint4*)(op + c0 + i * 8) = o4;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct AttnTcPlan { std::map<int, CUtensorMap> maps; };
+static std::map<const Op*, AttnTcPlan> g_attn_plans;   // keyed by op address (ops vector is stable after build)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_attn_encode = nullptr;
+
+bool attn_tc_supported(const Engine& e, const Op& op) {
+  if (!e.bf16 || op.kind != OP_ATTN) return false;
+  const char* off = getenv("CFM_DISABLE_TC_ATTN");
+  if (off && off[0] == '1') return false;
+  return op.ch == AT_D && op.Hin * op.Win == AT_T;
+}
+
+int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
+  if (!g_attn_encode) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
+    g_attn_encode = (EncodeTiledFn)fn;
+    if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_tc_kernel) failed"; return CFM_ERR_CUDA; }
+  }
+  AttnTcPlan& pl = g_attn_plans[&op];
+  const void* qkv = tensor_ptr(e, op.src0, B);
+  auto it = pl.maps.find(B);
+  if (it == pl.maps.end()) {
+    CUtensorMap m;
+    const int C3 = 3 * op.Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)C3, (cuuint64_t)B * AT_T};
+    cuuint64_t strides[1] = {(cuuint64_t)C3 * 2};
+    cuuint32_t box[2] = {(cuuint32_t)AT_D, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_attn_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(qkv) failed"; return CFM_ERR_CUDA; }
+    it = pl.maps.emplace(B, m).first;
+  }
+  AttnTcParams p{};
+  p.heads = op.heads; p.C = op.Cin; p.new_order = e.cfg.use_new_attention_order;
+  p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
+  p.out = (bf16*)tensor_ptr(e, op.out, B);
+  attn_tc_kernel<<<dim3(AT_T / AT_M, B * op.heads), 128, AT_SMEM, st>>>(it->second, p);
+  return 0;
+}
+
+void attn_tc_release(Engine& e) {
+  for (const Op& op : e.ops) {
+    auto it = g_attn_plans.find(&op);
+    if (it != g_attn_plans.end()) it->second.maps.clear();
+  }
+}
+
+void attn_tc_forget(Engine& e) {
+  for (const Op& op : e.ops) g_attn_plans.erase(&op);
+}
+
+}  // namespace cfm

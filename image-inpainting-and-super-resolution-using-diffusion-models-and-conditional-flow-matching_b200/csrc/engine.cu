@@ -367,6 +367,7 @@ static int ensure_batch(Engine& e, int B) {
   if (B > e.arena_batch) {
     if (e.arena) { cudaFree(e.arena); e.arena = nullptr; }
     tc_conv_release(e);   // tensor maps hold arena addresses
+    attn_tc_release(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
     CU_CHECK(e, cudaMalloc(&e.arena, bytes));
     e.arena_batch = B;
@@ -404,13 +405,26 @@ __global__ void setup_rows_kernel(int B, int rows, int uniform, float t_scalar, 
 
 template <typename T>
 static int run_ops(Engine& e, int B, const float* x, const float* cond, float* out, cudaStream_t st) {
-  const int Cx = cond ? e.cfg.in_channels - (e.cfg.in_channels - e.x_channels()) : e.cfg.in_channels;
-  (void)Cx;
+  int op_index = 0;
   for (const Op& op : e.ops) {
+    if (e.profiling) cudaEventRecord(e.prof_events[op_index], st);
+    ++op_index;
     switch (op.kind) {
       case OP_CONV: {
         if (op.tc) {
           int rc = tc_conv_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
+        if (head_conv_supported(e, op)) {
+          int rc = head_conv_launch(e, op, B, out, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
+        if (stem_conv_supported(e, op)) {
+          int rc = stem_conv_launch(e, op, B, x, cond, st);
           if (rc) return rc;
           e.launches++;
           break;
@@ -467,6 +481,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_RESAMPLE: {
+        if (resample_bf16_supported(e, op)) {
+          int rc = resample_bf16_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
         const long long total = (long long)B * e.tensors[op.out].elems();
         const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.sm_count * 16);
         resample_kernel<T><<<blocks, 256, 0, st>>>((const T*)tensor_ptr(e, op.src0, B), (T*)tensor_ptr(e, op.out, B), B, op.Hin, op.Win, op.Cin, op.up);
@@ -474,12 +494,22 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_ATTN: {
+        if (attn_tc_supported(e, op)) {
+          int rc = attn_tc_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
         AttnArgs<T> a{(const T*)tensor_ptr(e, op.src0, B), (T*)tensor_ptr(e, op.out, B), B, op.Hin * op.Win, op.heads, op.ch, e.cfg.use_new_attention_order};
         const int nw = 8;
         dim3 grid((a.T_len + nw - 1) / nw, B * op.heads);
         const size_t smem = sizeof(float) * (32 * (op.ch + 1) + 32 * op.ch);
         const int cpl = (op.ch + 31) / 32;
-        if (smem > 48 * 1024 || cpl > 16) return fail(e, CFM_ERR_INVALID, "attention head width too large for the generic kernel");
+        if (smem > 200 * 1024 || cpl > 16) return fail(e, CFM_ERR_INVALID, "attention head width too large for the generic kernel");
+        if (smem > 48 * 1024) {
+          cudaFuncSetAttribute(attention_generic_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(attention_generic_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        }
         if (cpl <= 1) attention_generic_kernel<T, 1><<<grid, nw * 32, smem, st>>>(a);
         else if (cpl <= 2) attention_generic_kernel<T, 2><<<grid, nw * 32, smem, st>>>(a);
         else if (cpl <= 4) attention_generic_kernel<T, 4><<<grid, nw * 32, smem, st>>>(a);
@@ -490,6 +520,7 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
       }
     }
   }
+  if (e.profiling) cudaEventRecord(e.prof_events[op_index], st);
   return 0;
 }
 
@@ -579,7 +610,9 @@ void cfm_engine_destroy(cfm_engine* h) {
   Engine& e = h->impl;
   cudaSetDevice(e.device);
   tc_conv_release(e);
+  attn_tc_forget(e);
   for (void* p : e.owned) cudaFree(p);
+  for (cudaEvent_t ev : e.prof_events) cudaEventDestroy(ev);
   for (void* p : {(void*)e.arena, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf})
     if (p) cudaFree(p);
   delete h;
@@ -600,6 +633,47 @@ int cfm_engine_forward(cfm_engine* h, int32_t batch, const float* x_dev, const f
   cudaSetDevice(e.device);
   e.launches = 0;
   return forward_impl(e, batch, x_dev, cond_dev, t_dev, t_scalar, y_dev, out_dev, (cudaStream_t)stream);
+}
+
+// Per-op device timing of one NFE (CUDA events around every launch; not for use under graph capture).
+int cfm_engine_profile_forward(cfm_engine* h, int32_t batch, const float* x_dev, const float* cond_dev, float t_scalar,
+                               const int64_t* y_dev, float* out_dev, int32_t repeats, void* stream) {
+  if (!h || repeats < 1) return CFM_ERR_INVALID;
+  Engine& e = h->impl;
+  cudaSetDevice(e.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_ev = e.ops.size() + 1;
+  while (e.prof_events.size() < n_ev) { cudaEvent_t ev; CU_CHECK(e, cudaEventCreate(&ev)); e.prof_events.push_back(ev); }
+  e.prof_ms.assign(e.ops.size(), 0.0);
+  int rc = forward_impl(e, batch, x_dev, cond_dev, nullptr, t_scalar, y_dev, out_dev, st);   // warm (tensor maps, arena)
+  if (rc) return rc;
+  for (int r = 0; r < repeats; ++r) {
+    e.profiling = true;
+    rc = forward_impl(e, batch, x_dev, cond_dev, nullptr, t_scalar, y_dev, out_dev, st);
+    e.profiling = false;
+    if (rc) return rc;
+    CU_CHECK(e, cudaStreamSynchronize(st));
+    for (size_t i = 0; i < e.ops.size(); ++i) {
+      float ms = 0.f;
+      CU_CHECK(e, cudaEventElapsedTime(&ms, e.prof_events[i], e.prof_events[i + 1]));
+      e.prof_ms[i] += ms / repeats;
+    }
+  }
+  return 0;
+}
+
+int32_t cfm_engine_profile_count(const cfm_engine* h) { return h ? (int32_t)h->impl.prof_ms.size() : 0; }
+
+// kind: 0 generic conv, 1 groupnorm, 2 resample, 3 attention, 4 tcgen05 conv
+int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t name_cap, int32_t* kind, double* ms,
+                           double* flops_per_sample) {
+  if (!h || i < 0 || i >= (int32_t)h->impl.prof_ms.size()) return CFM_ERR_INVALID;
+  const Op& op = h->impl.ops[i];
+  if (name && name_cap > 0) { std::strncpy(name, op.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (kind) *kind = op.kind == OP_CONV ? (op.tc ? 4 : 0) : (int)op.kind;
+  if (ms) *ms = h->impl.prof_ms[i];
+  if (flops_per_sample) *flops_per_sample = op.flops;
+  return 0;
 }
 
 int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev, const int64_t* y_dev,

@@ -69,6 +69,9 @@ struct Engine {
   int launches = 0;
   int n_tc_convs = 0;
   int sm_count = 148;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<double> prof_ms;
   int x_channels() const { return cfg.out_channels; }
 };
 
@@ -79,6 +82,17 @@ int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 void tc_conv_release(Engine& e);
 // bf16 fast kernels (kernels_bf16.cu)
 int  gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+// attn_tc.cu
+bool attn_tc_supported(const Engine& e, const Op& op);
+int  attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+void attn_tc_release(Engine& e);
+void attn_tc_forget(Engine& e);
 bool gn_bf16_supported(const Engine& e, const Op& op);
+bool resample_bf16_supported(const Engine& e, const Op& op);
+int  resample_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+bool head_conv_supported(const Engine& e, const Op& op);
+int  head_conv_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t st);
+bool stem_conv_supported(const Engine& e, const Op& op);
+int  stem_conv_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st);
 
 }  // namespace cfm

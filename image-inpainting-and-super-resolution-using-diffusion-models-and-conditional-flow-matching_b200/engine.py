@@ -163,6 +163,27 @@ class Engine:
         _lib.check(rc, self._h)
         return out
 
+    def profile_forward(self, x: torch.Tensor, t: float = 0.5, y=None, cond=None, repeats: int = 3):
+        """Per-op device times of one NFE: list of dicts {name, kind, ms, flops} (flops for the whole batch)."""
+        B = x.shape[0]
+        xd = _as_f32_cuda(x, self.device)
+        cd = None if cond is None else _as_f32_cuda(cond, self.device)
+        yd = None if y is None else y.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty((B, self.config.out_channels, self.config.image_size, self.config.image_size),
+                          device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.cfm_engine_profile_forward(self._h, B, _ptr(xd), _ptr(cd), float(t), _ptr(yd), _ptr(out),
+                                                     repeats, _stream_ptr(self.device))
+        _lib.check(rc, self._h)
+        kinds = {0: "conv_generic", 1: "groupnorm", 2: "resample", 3: "attention", 4: "conv_tcgen05"}
+        rows = []
+        for i in range(self.lib.cfm_engine_profile_count(self._h)):
+            name = C.create_string_buffer(128)
+            kind, ms, fl = C.c_int32(), C.c_double(), C.c_double()
+            _lib.check(self.lib.cfm_engine_profile_get(self._h, i, name, 128, C.byref(kind), C.byref(ms), C.byref(fl)), self._h)
+            rows.append({"name": name.value.decode(), "kind": kinds[kind.value], "ms": ms.value, "flops": fl.value * B})
+        return rows
+
     # --- fused fixed-step Euler loop ----------------------------------------------------------------
     def sample_euler(self, x0: torch.Tensor, t_grid: Sequence[float], dt_grid: Sequence[float],
                      y: Optional[torch.Tensor] = None, cond: Optional[torch.Tensor] = None,

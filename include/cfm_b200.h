@@ -114,6 +114,16 @@ int cfm_engine_forward(cfm_engine* e, int32_t batch, const float* x_dev, const f
                        const float* t_dev, float t_scalar, const int64_t* y_dev,
                        float* out_dev, void* stream);
 
+/* Per-op device timing of one NFE (CUDA events around every launch, averaged over `repeats`
+ * evaluations after one warm-up).  Results are read back with cfm_engine_profile_count/_get;
+ * kind: 0 generic conv, 1 groupnorm, 2 resample, 3 attention, 4 tcgen05 conv. */
+int cfm_engine_profile_forward(cfm_engine* e, int32_t batch, const float* x_dev, const float* cond_dev,
+                               float t_scalar, const int64_t* y_dev, float* out_dev, int32_t repeats,
+                               void* stream);
+int32_t cfm_engine_profile_count(const cfm_engine* e);
+int cfm_engine_profile_get(const cfm_engine* e, int32_t i, char* name, int32_t name_cap, int32_t* kind,
+                           double* ms, double* flops_per_sample);
+
 /* Flags for cfm_sample_euler. */
 #define CFM_EULER_COND_DRIFT   1u  /* conditioning is ODE state with d(con)/dt = con */
 #define CFM_EULER_USE_GRAPH    2u  /* capture the whole fixed-step loop into one CUDA graph      */
