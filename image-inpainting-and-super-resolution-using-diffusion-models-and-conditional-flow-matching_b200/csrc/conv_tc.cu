@@ -24,14 +24,15 @@ namespace cfm {
 
 void* tensor_ptr(const Engine& e, int id, int B);
 
-constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_M = 128;         // rows of one UMMA; a CTA tile is 128 * mh rows (mh = 1 or 2 M-halves)
 constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
-constexpr int TC_MAX_N = 256;
-constexpr int TC_B_BYTES_MAX = TC_MAX_N * TC_BLOCK_K * 2; // 32 KB
-constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES_MAX) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB per M-half
+constexpr int TC_STAGE_BYTES = 48 * 1024;                 // A (16 KB * mh) + B (block_n * 128 B) <= 48 KB
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;        // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr int TC_MAX_COUT = 1024;                         // bias staged in smem
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_MAX_COUT * 4 + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcSeg { int map; int n_chunks; int ks; int stride; };
 
@@ -39,7 +40,8 @@ struct TcParams {
   int n_seg; TcSeg seg[3];
   int total_k;
   int B, H, W;                 // output spatial size
-  int bw, bh, bn;              // tile box, bw*bh*bn == 128
+  int bw, bh, bn;              // tile box, bw*bh*bn == 128 * mh
+  int mh;                      // M-halves per CTA tile (2: two UMMAs share one B tile)
   int tiles_w, tiles_h, tiles_b, tiles_n, n_tiles;
   int block_n, Cout;
   const float* bias;
@@ -57,10 +59,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_a = smem;                                   // [stages][16 KB]
-  uint8_t* smem_b = smem + TC_STAGES * TC_A_BYTES;          // [stages][block_n * 128 B]
+  const int a_bytes = TC_A_BYTES * p.mh;
   const int b_bytes = p.block_n * TC_BLOCK_K * 2;
-  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES_MAX));
+  float* s_bias = (float*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES + TC_MAX_COUT * 4);
   uint64_t* full_bar = bars;                 // [stages]
   uint64_t* empty_bar = bars + TC_STAGES;    // [stages]
   uint64_t* tfull_bar = bars + 2 * TC_STAGES;      // [2]
@@ -74,14 +76,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (p.n_seg > 1) prefetch_tmap(&mapA1);
     if (p.n_seg > 2) prefetch_tmap(&mapA2);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = p.block_n * p.mh;     // TMEM columns per accumulator stage
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -103,9 +107,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int dy = tap / sg.ks - pad, dx = tap % sg.ks - pad;
             for (int ch = 0; ch < sg.n_chunks; ++ch, ++kiter) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], TC_A_BYTES + b_bytes);
-              tma_load_4d(smem_a + stage * TC_A_BYTES, map, &full_bar[stage], ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
-              tma_load_2d(smem_b + stage * b_bytes, &mapB, &full_bar[stage], 0, kiter * p.Cout + nt * p.block_n);
+              mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+              tma_load_4d(sa, map, &full_bar[stage], ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+              tma_load_2d(sa + a_bytes, &mapB, &full_bar[stage], 0, kiter * p.Cout + nt * p.block_n);
               if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -120,16 +125,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
       for (int k = 0; k < p.total_k; ++k) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t adesc = make_desc_sw128(smem_u32(smem_a + stage * TC_A_BYTES));
-          const uint64_t bdesc = make_desc_sw128(smem_u32(smem_b + stage * b_bytes));
+          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint64_t adesc = make_desc_sw128(sa);
+          const uint64_t bdesc = make_desc_sw128(sa + a_bytes);
 #pragma unroll
-          for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk)
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk) {
+            const uint32_t accum = (k > 0 || kk > 0) ? 1u : 0u;
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+            if (p.mh == 2)   // second M-half re-uses the same B tile: halves the B traffic per FLOP
+              umma_bf16(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)(TC_A_BYTES >> 4) + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+          }
           umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
           if (k == p.total_k - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
         }
@@ -139,9 +149,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quad * 32 + lane;
+    // ===================== epilogue (warps 2..9) =====================
+    // warp%4 selects the TMEM lane quarter the hardware lets this warp read; the two warps sharing a
+    // quarter split the (M-half, 32-column chunk) work items between them.
+    const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;           // 0 or 1
+    const int chunks_per_half = p.block_n >> 5;
+    const int n_items = chunks_per_half * p.mh;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
@@ -149,29 +163,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int tw = mt % p.tiles_w; mt /= p.tiles_w;
       const int th = mt % p.tiles_h;
       const int tb = mt / p.tiles_h;
-      const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
-      const int n = tb * p.bn + ni, h = th * p.bh + hi, w = tw * p.bw + wi;
-      const bool valid = n < p.B;
-      const long long pix = ((long long)n * p.H + h) * p.W + w;
-      const float* embp = (p.emb && valid) ? p.emb + (long long)p.emb_row[n] * p.emb_stride : nullptr;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
+      for (int item = sub; item < n_items; item += 2) {
+        const int half = item / chunks_per_half;
+        const int c0 = (item - half * chunks_per_half) << 5;
+        const int row = half * 128 + quad * 32 + lane;
+        const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
+        const int n = tb * p.bn + ni, h = th * p.bh + hi, w = tw * p.bw + wi;
+        const bool valid = n < p.B;
+        const long long pix = ((long long)n * p.H + h) * p.W + w;
         uint32_t v[32];
-        tmem_ld32(t_addr + (uint32_t)c0, v);
+        tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
         tmem_ld_wait();
         if (valid) {
           const int cg = nt * p.block_n + c0;    // first output channel of this chunk
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg((const float4*)(p.bias + cg + j));
+            const float4 b4 = *(const float4*)(s_bias + cg + j);
             f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
             f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
-          if (embp) {
+          if (p.emb) {
+            const float* embp = p.emb + (long long)p.emb_row[n] * p.emb_stride;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 e4 = __ldg((const float4*)(embp + cg + j));
@@ -182,7 +199,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cg : p.res1 + pix * p.R1 + (cg - p.R0);
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 r4 = *(const uint4*)(rp + j);
+              const uint4 r4 = __ldg((const uint4*)(rp + j));
               const __nv_bfloat162* rb = (const __nv_bfloat162*)&r4;
 #pragma unroll
               for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
@@ -221,7 +238,7 @@ struct TcConvPlan {
   int n_seg = 0; TcSeg seg[3];
   int seg_tensor[3] = {-1, -1, -1};
   int total_k = 0, block_n = 0;
-  int bw = 0, bh = 0, bn = 0;
+  int bw = 0, bh = 0, bn = 0, mh = 1;
   std::map<int, TcMaps> maps;   // per batch size
 };
 
@@ -257,7 +274,7 @@ bool tc_conv_supported(const Engine& e, const Op& op) {
   if (op.stride != 1 && op.stride != 2) return false;
   if (op.stride == 2 && env_off("CFM_DISABLE_TC_STRIDE2")) return false;
   if (op.ks != 1 && op.ks != 3) return false;
-  if (pick_block_n(op.Cout) == 0) return false;
+  if (pick_block_n(op.Cout) == 0 || op.Cout > TC_MAX_COUT) return false;
   if (!pow2(op.Hout) || !pow2(op.Wout) || op.Wout > 128 || op.Hout > 128) return false;
   if (op.stride == 2 && (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout || 2 * std::min(op.Wout, 128) > 256)) return false;
   auto chan_ok = [&](int id) { return id < 0 || e.tensors[id].C % TC_BLOCK_K == 0; };
@@ -272,9 +289,13 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   TcConvPlan* pl = new TcConvPlan();
   const int Cout = op.Cout, Cin = op.Cin, ks = op.ks;
   pl->block_n = pick_block_n(Cout);
-  pl->bw = std::min(op.Wout, 128);
-  pl->bh = std::min(op.Hout, 128 / pl->bw);
-  pl->bn = 128 / (pl->bw * pl->bh);
+  // N <= 128 tiles are shared-memory-bandwidth bound with a 128-row tile (A and B stream at 1:1);
+  // a 256-row tile (two UMMAs per B tile) restores the 2:1 ratio of the N = 256 case.
+  pl->mh = (pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;
+  const int rows = 128 * pl->mh;
+  pl->bw = std::min(op.Wout, rows);
+  pl->bh = std::min(op.Hout, rows / pl->bw);
+  pl->bn = rows / (pl->bw * pl->bh);
   pl->seg[0] = {0, Cin / TC_BLOCK_K, ks, op.stride}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
   if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
   if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
@@ -348,7 +369,7 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   for (int s = 0; s < 3; ++s) p.seg[s] = pl->seg[s];
   p.total_k = pl->total_k;
   p.B = B; p.H = op.Hout; p.W = op.Wout;
-  p.bw = pl->bw; p.bh = pl->bh; p.bn = pl->bn;
+  p.bw = pl->bw; p.bh = pl->bh; p.bn = pl->bn; p.mh = pl->mh;
   p.tiles_w = op.Wout / pl->bw; p.tiles_h = op.Hout / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
   p.tiles_n = op.Cout / pl->block_n;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;

@@ -9,49 +9,71 @@ namespace cfm {
 void* tensor_ptr(const Engine& e, int id, int B);
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm32 over NHWC bf16.  One CTA per (sample, channel slab); the slab (a whole number of groups
-// and of 8-channel vectors, >= 64 B per pixel) for all HW pixels is staged once in shared memory,
-// statistics are reduced from there (warp shuffles + a few shared atomics) and the normalised,
-// FiLM-modulated, SiLU-activated result is written back with 16-byte stores.
+// GroupNorm32 over NHWC bf16, register-resident.
+// An "item" is one (sample, channel slab); a slab is a whole number of groups and of 8-channel
+// 16-byte vectors (>= 64 B per pixel: 32 or 48 channels).  TPI threads own an item: each thread
+// loads up to GN_VPT vectors straight into registers (all loads in flight at once - the kernel is
+// HBM-bound, so bytes in flight are what matters), statistics are reduced deterministically
+// through shared memory (no atomics -> bit-reproducible), and the normalised / FiLM-modulated /
+// SiLU-activated values are stored from the same registers: one global read, one global write.
+// Small feature maps pack several items into one CTA.
 // ------------------------------------------------------------------------------------------------
 struct GnFastArgs {
   const bf16* src0; const bf16* src1; int C0, C1;
-  int HW, cpg, slab;                 // slab channels per CTA (multiple of 8 and of cpg)
+  int HW, cpg, slab;                 // slab channels per item (multiple of 8 and of cpg)
+  int tpi, ipc, n_items;             // threads per item, items per CTA, total items
   const float* gamma; const float* beta; float eps; int silu;
   const float* film; int film_stride; const int* film_row;
   bf16* out;
 };
 
-constexpr int GN_THREADS = 256;
+constexpr int GN_VPT = 16;
 constexpr int GN_MAX_SLAB = 64;
+constexpr int GN_MAX_THREADS = 256;
 
-__global__ void __launch_bounds__(GN_THREADS) groupnorm_bf16_kernel(GnFastArgs a) {
-  extern __shared__ uint4 stage[];                       // [HW][slab/8] vectors
-  __shared__ float ch_sum[GN_MAX_SLAB], ch_sq[GN_MAX_SLAB];
-  __shared__ float ch_scale[GN_MAX_SLAB], ch_shift[GN_MAX_SLAB];
-  __shared__ float part_sum[GN_THREADS][8], part_sq[GN_THREADS][8];
+__global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFastArgs a) {
+  extern __shared__ float gn_smem[];
+  // layout: part_sum[threads][8] | part_sq[threads][8] | ch_scale[ipc][64] | ch_shift[ipc][64] | ch_sum[ipc][64] | ch_sq[ipc][64]
+  float* part_sum = gn_smem;
+  float* part_sq = part_sum + blockDim.x * 8;
+  float* ch_scale = part_sq + blockDim.x * 8;
+  float* ch_shift = ch_scale + a.ipc * GN_MAX_SLAB;
+  float* ch_sum = ch_shift + a.ipc * GN_MAX_SLAB;
+  float* ch_sq = ch_sum + a.ipc * GN_MAX_SLAB;
+
   const int C = a.C0 + a.C1;
   const int slabs = C / a.slab;
-  const int b = blockIdx.x / slabs, sl = blockIdx.x % slabs;
-  const int c_base = sl * a.slab;
-  const int vpp = a.slab / 8;                            // 16-byte vectors per pixel
+  const int vpp = a.slab / 8;
   const int nvec = a.HW * vpp;
-
-  // GN_THREADS % vpp == 0 is guaranteed by the launcher (vpp in {3,4,6,8}: blockDim is chosen), so a
-  // thread always sees the same vector slot q -> the same 8 channels.
-  const int q = threadIdx.x % vpp;
-  const int cq = c_base + q * 8;                         // first channel of this thread's vector
+  const int il = threadIdx.x / a.tpi;                    // item within the CTA
+  const int ti = threadIdx.x - il * a.tpi;               // thread within the item
+  const int item = blockIdx.x * a.ipc + il;
+  const bool active = item < a.n_items;
+  const int b = active ? item / slabs : 0, sl = active ? item % slabs : 0;
+  const int c_base = sl * a.slab;
+  const int q = ti % vpp;                                // tpi % vpp == 0 -> fixed vector slot per thread
+  const int cq = c_base + q * 8;
   const bf16* sp; int sC, sc;
   if (cq < a.C0) { sp = a.src0; sC = a.C0; sc = cq; } else { sp = a.src1; sC = a.C1; sc = cq - a.C0; }
+  const long long pix0 = (long long)b * a.HW;
+  const int p0 = ti / vpp, pstep = a.tpi / vpp;          // this thread's pixels: p0 + k*pstep
+
+  uint4 regs[GN_VPT];
+  {
+    const bf16* lp = sp + (pix0 + p0) * sC + sc;
+    const long long lstep = (long long)pstep * sC;
+#pragma unroll
+    for (int k = 0; k < GN_VPT; ++k) {
+      regs[k] = (active && p0 + k * pstep < a.HW) ? __ldg((const uint4*)lp) : make_uint4(0, 0, 0, 0);
+      lp += lstep;
+    }
+  }
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
-  const long long pix0 = (long long)b * a.HW;
-  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-    const int p = v / vpp;
-    const uint4 raw = __ldg((const uint4*)(sp + (pix0 + p) * sC + sc));
-    stage[v] = raw;
-    const __nv_bfloat162* h2 = (const __nv_bfloat162*)&raw;
+#pragma unroll
+  for (int k = 0; k < GN_VPT; ++k) {
+    const __nv_bfloat162* h2 = (const __nv_bfloat162*)&regs[k];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __bfloat1622float2(h2[j]);
@@ -59,103 +81,123 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_bf16_kernel(GnFastArgs a
       s[2 * j + 1] += f.y; ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
     }
   }
-  // deterministic reduction: every thread parks its 8 channel partials, then one thread per channel
-  // adds the partials of the threads sharing its vector slot q in a fixed order (no atomics).
+  // keep only the packed bf16 words live across the reduction (stops the compiler from parking 128 unpacked floats)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { part_sum[threadIdx.x][j] = s[j]; part_sq[threadIdx.x][j] = ss[j]; }
+  for (int k = 0; k < GN_VPT; ++k) asm volatile("" : "+r"(regs[k].x), "+r"(regs[k].y), "+r"(regs[k].z), "+r"(regs[k].w));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { part_sum[threadIdx.x * 8 + j] = s[j]; part_sq[threadIdx.x * 8 + j] = ss[j]; }
   __syncthreads();
-  if (threadIdx.x < a.slab) {
-    const int qq = threadIdx.x >> 3, j = threadIdx.x & 7;
+  // one thread per (item, channel): fixed-order sum over the item's threads that share the vector slot
+  for (int w = threadIdx.x; w < a.ipc * a.slab; w += blockDim.x) {
+    const int wi = w / a.slab, c = w - wi * a.slab;
+    const int qq = c >> 3, j = c & 7;
     float ts = 0.f, tq = 0.f;
-    for (int t = qq; t < (int)blockDim.x; t += vpp) { ts += part_sum[t][j]; tq += part_sq[t][j]; }
-    ch_sum[threadIdx.x] = ts; ch_sq[threadIdx.x] = tq;
+    for (int t = wi * a.tpi + qq; t < (wi + 1) * a.tpi; t += vpp) { ts += part_sum[t * 8 + j]; tq += part_sq[t * 8 + j]; }
+    ch_sum[wi * GN_MAX_SLAB + c] = ts; ch_sq[wi * GN_MAX_SLAB + c] = tq;
   }
   __syncthreads();
-  if (threadIdx.x < a.slab) {
-    const int c = threadIdx.x, g0 = (c / a.cpg) * a.cpg;
+  for (int w = threadIdx.x; w < a.ipc * a.slab; w += blockDim.x) {
+    const int wi = w / a.slab, c = w - wi * a.slab;
+    const int it = blockIdx.x * a.ipc + wi;
+    if (it >= a.n_items) continue;
+    const int bb = it / slabs, cb = (it % slabs) * a.slab;
+    const int g0 = (c / a.cpg) * a.cpg;
     float gs = 0.f, gq = 0.f;
-    for (int j = 0; j < a.cpg; ++j) { gs += ch_sum[g0 + j]; gq += ch_sq[g0 + j]; }
+    for (int j = 0; j < a.cpg; ++j) { gs += ch_sum[wi * GN_MAX_SLAB + g0 + j]; gq += ch_sq[wi * GN_MAX_SLAB + g0 + j]; }
     const float inv_n = 1.0f / (float)(a.cpg * a.HW);
     const float mean = gs * inv_n;
     const float var = fmaxf(gq * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + a.eps);
-    float sc_ = rstd * a.gamma[c_base + c];
-    float sh_ = a.beta[c_base + c] - mean * sc_;
+    float sc_ = rstd * a.gamma[cb + c];
+    float sh_ = a.beta[cb + c] - mean * sc_;
     if (a.film) {
-      const float* f = a.film + (long long)a.film_row[b] * a.film_stride;
-      const float m = 1.0f + f[c_base + c];
-      sc_ *= m; sh_ = sh_ * m + f[C + c_base + c];
+      const float* f = a.film + (long long)a.film_row[bb] * a.film_stride;
+      const float m = 1.0f + f[cb + c];
+      sc_ *= m; sh_ = sh_ * m + f[C + cb + c];
     }
-    ch_scale[c] = sc_; ch_shift[c] = sh_;
+    ch_scale[wi * GN_MAX_SLAB + c] = sc_; ch_shift[wi * GN_MAX_SLAB + c] = sh_;
   }
   __syncthreads();
+  if (!active) return;
   float sc8[8], sh8[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc8[j] = ch_scale[q * 8 + j]; sh8[j] = ch_shift[q * 8 + j]; }
-  bf16* op = a.out + pix0 * C + cq;
-  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-    const int p = v / vpp;
-    const uint4 raw = stage[v];
-    const __nv_bfloat162* h2 = (const __nv_bfloat162*)&raw;
-    uint4 o4;
-    __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+  for (int j = 0; j < 8; ++j) { sc8[j] = ch_scale[il * GN_MAX_SLAB + q * 8 + j]; sh8[j] = ch_shift[il * GN_MAX_SLAB + q * 8 + j]; }
+  bf16* op = a.out + (pix0 + p0) * C + cq;
+  const long long ostep = (long long)pstep * C;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(h2[j]);
-      float y0 = fmaf(f.x, sc8[2 * j], sh8[2 * j]), y1 = fmaf(f.y, sc8[2 * j + 1], sh8[2 * j + 1]);
-      if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      o2[j] = __floats2bfloat162_rn(y0, y1);
+  for (int k = 0; k < GN_VPT; ++k, op += ostep) {
+    if (p0 + k * pstep < a.HW) {
+      const __nv_bfloat162* h2 = (const __nv_bfloat162*)&regs[k];
+      uint4 o4;
+      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        float y0 = fmaf(f.x, sc8[2 * j], sh8[2 * j]), y1 = fmaf(f.y, sc8[2 * j + 1], sh8[2 * j + 1]);
+        if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+        o2[j] = __floats2bfloat162_rn(y0, y1);
+      }
+      *(uint4*)op = o4;
     }
-    *(uint4*)(op + (long long)p * C) = o4;
   }
 }
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-static void gn_geometry(const Engine& e, const Op& op, int* cpg, int* slab, int* threads, size_t* smem) {
+struct GnGeom { int cpg, slab, tpi, ipc, threads; size_t smem; bool ok; };
+
+static GnGeom gn_geometry(const Op& op) {
+  GnGeom g{};
   const int C = op.Cin;
-  *cpg = C / 32;
-  int base = *cpg / gcd_i(*cpg, 8) * 8;            // lcm(cpg, 8)
-  int sl = base;
-  while (sl < 32 && C % (sl * 2) == 0) sl *= 2;
-  *slab = sl;
-  const int vpp = sl / 8;
-  *threads = (GN_THREADS / vpp) * vpp;
-  *smem = (size_t)op.Hin * op.Win * sl * 2;
+  g.cpg = C / 32;
+  const int base = g.cpg / gcd_i(g.cpg, 8) * 8;        // lcm(cpg, 8): smallest legal slab
+  // widest slab (<= 64 channels, dividing C) whose item still fits GN_VPT vectors/thread in <= 256 threads
+  for (int sl = base; sl <= GN_MAX_SLAB && C % sl == 0; sl *= 2) {
+    const int vpp = sl / 8;
+    const int unit = 32 / gcd_i(32, vpp) * vpp;        // lcm(32, vpp): whole warps, multiple of vpp
+    const int nvec = op.Hin * op.Win * vpp;
+    int tpi = ((nvec + GN_VPT - 1) / GN_VPT + unit - 1) / unit * unit;
+    tpi = std::max(tpi, unit);
+    if (tpi > GN_MAX_THREADS) break;
+    g.slab = sl; g.tpi = tpi; g.ok = true;
+  }
+  if (!g.ok) return g;
+  g.ipc = std::max(1, GN_MAX_THREADS / g.tpi);
+  g.threads = g.tpi * g.ipc;
+  g.smem = sizeof(float) * ((size_t)g.threads * 16 + (size_t)g.ipc * GN_MAX_SLAB * 4);
+  return g;
 }
 
 bool gn_bf16_supported(const Engine& e, const Op& op) {
   if (!e.bf16 || op.kind != OP_GN) return false;
   const char* off = getenv("CFM_DISABLE_FAST_GN");
   if (off && off[0] == '1') return false;
-  int cpg, slab, threads; size_t smem;
-  gn_geometry(e, op, &cpg, &slab, &threads, &smem);
-  if (slab > GN_MAX_SLAB || op.Cin % slab) return false;
-  if (smem > 200 * 1024) return false;
-  const int C0 = e.tensors[op.src0].C;
-  if (C0 % 8) return false;
+  const GnGeom g = gn_geometry(op);
+  if (!g.ok || g.smem > 96 * 1024) return false;
+  if (e.tensors[op.src0].C % 8) return false;
   return true;
 }
 
 int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(groupnorm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(groupnorm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(groupnorm_bf16_kernel) failed"; return CFM_ERR_CUDA;
     }
     attr = true;
   }
+  const GnGeom g = gn_geometry(op);
   GnFastArgs a{};
-  int threads; size_t smem;
-  gn_geometry(e, op, &a.cpg, &a.slab, &threads, &smem);
+  a.cpg = g.cpg; a.slab = g.slab; a.tpi = g.tpi; a.ipc = g.ipc;
   a.src0 = (const bf16*)tensor_ptr(e, op.src0, B); a.C0 = e.tensors[op.src0].C;
   a.src1 = (const bf16*)tensor_ptr(e, op.src1, B); a.C1 = op.src1 >= 0 ? e.tensors[op.src1].C : 0;
   a.HW = op.Hin * op.Win;
+  a.n_items = B * (op.Cin / g.slab);
   a.gamma = op.gamma; a.beta = op.beta; a.eps = 1e-5f; a.silu = op.silu;
   if (op.film) { a.film = e.emb_out + op.emb_off; a.film_stride = e.emb_total; a.film_row = e.row_of_sample; }
   a.out = (bf16*)tensor_ptr(e, op.out, B);
-  const int blocks = B * (op.Cin / a.slab);
-  groupnorm_bf16_kernel<<<blocks, threads, smem, st>>>(a);
+  const int blocks = (a.n_items + g.ipc - 1) / g.ipc;
+  groupnorm_bf16_kernel<<<blocks, g.threads, g.smem, st>>>(a);
   return 0;
 }
 
@@ -227,6 +269,7 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const bf16* __restrict__
     if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
     const bf16* sp = src + (((long long)b * H + iy) * W + ix) * C;
     const float4* wp = (const float4*)(ws + (long long)tap * C * HEAD_MAX_COUT);
+#pragma unroll 4
     for (int c = 0; c < C; c += 8) {
       const uint4 raw = __ldg((const uint4*)(sp + c));
       const __nv_bfloat162* h2 = (const __nv_bfloat162*)&raw;
@@ -267,49 +310,85 @@ int head_conv_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t st
 // ------------------------------------------------------------------------------------------------
 constexpr int STEM_MAX_CIN = 8;
 
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0, int C1,
+// One thread per output pixel: the <= 9*8 input taps are loaded once into registers, then all Cout
+// channels are produced 32 at a time from weights broadcast out of shared memory.
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0, int C1,
                                                         const float* __restrict__ w /*[9*Cin][Cout]*/, const float* __restrict__ bias,
                                                         bf16* __restrict__ out, int B, int H, int W, int Cout) {
+  extern __shared__ float sw[];        // [9*Cin][Cout] then bias[Cout]
   const int Cin = C0 + C1;
-  const int cv = Cout / 8;
-  const long long total = (long long)B * H * W * cv;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int co = (int)(i % cv) * 8;
-  const long long m = i / cv;
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
+  float* sb = sw + K * Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const long long total = (long long)B * H * W;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= total) return;
   const int x = (int)(m % W), y = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
-  float acc[8];
+  float in[9 * STEM_MAX_CIN];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bias[co + j];
   for (int tap = 0; tap < 9; ++tap) {
     const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    for (int c = 0; c < Cin; ++c) {
-      const float v = (c < C0) ? __ldg(x0 + (((long long)b * C0 + c) * H + iy) * W + ix)
-                               : __ldg(x1 + (((long long)b * C1 + (c - C0)) * H + iy) * W + ix);
-      const float4 w0 = __ldg((const float4*)(w + (long long)(tap * Cin + c) * Cout + co));
-      const float4 w1 = __ldg((const float4*)(w + (long long)(tap * Cin + c) * Cout + co + 4));
-      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-      acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+    for (int c = 0; c < STEM_MAX_CIN; ++c) {
+      float v = 0.f;
+      if (ok && c < Cin)
+        v = (c < C0) ? __ldg(x0 + (((long long)b * C0 + c) * H + iy) * W + ix)
+                     : __ldg(x1 + (((long long)b * C1 + (c - C0)) * H + iy) * W + ix);
+      in[tap * STEM_MAX_CIN + c] = v;
     }
   }
-  uint4 o4;
-  __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+  bf16* op = out + m * Cout;
+  for (int co = 0; co < Cout; co += 32) {
+    float acc[32];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-  *(uint4*)(out + m * Cout + co) = o4;
+    for (int j = 0; j < 32; ++j) acc[j] = sb[co + j];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+      for (int c = 0; c < STEM_MAX_CIN; ++c) {
+        if (c < Cin) {
+          const float v = in[tap * STEM_MAX_CIN + c];
+          const float4* wr = (const float4*)(sw + (tap * Cin + c) * Cout + co);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w4 = wr[j];
+            acc[4 * j] = fmaf(v, w4.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 o4;
+      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(acc[j + 2 * q], acc[j + 2 * q + 1]);
+      *(uint4*)(op + co + j) = o4;
+    }
+  }
 }
 
 bool stem_conv_supported(const Engine& e, const Op& op) {
   return e.bf16 && op.kind == OP_CONV && op.src_is_input && !op.out_is_output && op.ks == 3 && op.stride == 1 && !op.ups &&
-         op.skip0 < 0 && op.res0 < 0 && op.emb_off < 0 && op.Cin <= STEM_MAX_CIN && op.Cout % 8 == 0;
+         op.skip0 < 0 && op.res0 < 0 && op.emb_off < 0 && op.Cin <= STEM_MAX_CIN && op.Cout % 32 == 0 &&
+         (size_t)(9 * op.Cin + 1) * op.Cout * 4 <= 96 * 1024;
 }
 
 int stem_conv_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st) {
   const int cx = cond ? e.x_channels() : e.cfg.in_channels;
-  const long long total = (long long)B * op.Hout * op.Wout * (op.Cout / 8);
-  stem_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, cond, cx, e.cfg.in_channels - cx, op.w_main, op.bias,
-                                                                  (bf16*)tensor_ptr(e, op.out, B), B, op.Hout, op.Wout, op.Cout);
+  const size_t smem = (size_t)(9 * op.Cin + 1) * op.Cout * 4;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) { e.err = "cudaFuncSetAttribute(stem_conv_kernel) failed"; return CFM_ERR_CUDA; }
+    attr = true;
+  }
+  const long long total = (long long)B * op.Hout * op.Wout;
+  stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, smem, st>>>(x, cond, cx, e.cfg.in_channels - cx, op.w_main, op.bias,
+                                                                     (bf16*)tensor_ptr(e, op.out, B), B, op.Hout, op.Wout, op.Cout);
   return 0;
 }
 

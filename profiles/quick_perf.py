@@ -27,3 +27,9 @@ for k,(ms,fl,n) in sorted(agg.items(), key=lambda kv:-kv[1][0]):
 print("--- slowest ops")
 for r in sorted(rows, key=lambda r:-r['ms'])[:25]:
     print(f"{r['name']:34s} {r['kind']:13s} {r['ms']:7.3f} ms {r['flops']/r['ms']/1e9 if r['ms'] else 0:8.1f} TF/s")
+
+import os
+os.makedirs('gpurun_out', exist_ok=True)
+with open('gpurun_out/profile_ops.txt','w') as f:
+    for r in rows:
+        f.write(f"{r['name']:36s} {r['kind']:13s} {r['ms']:8.4f} ms {r['flops']/r['ms']/1e9 if r['ms'] else 0:8.1f} TF/s\n")
