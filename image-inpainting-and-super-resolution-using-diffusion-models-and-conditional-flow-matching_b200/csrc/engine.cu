@@ -363,17 +363,24 @@ static int build_plan(Engine& e) {
 // ---------------------------------------------------------------------------------------------
 static size_t esize(const Engine& e) { return e.bf16 ? 2 : 4; }
 
+static void drop_graphs(Engine& e) {
+  for (auto& kv : e.graphs) cudaGraphExecDestroy(kv.second);
+  e.graphs.clear();
+}
+
 static int ensure_batch(Engine& e, int B) {
   if (B > e.arena_batch) {
     if (e.arena) { cudaFree(e.arena); e.arena = nullptr; }
     tc_conv_release(e);   // tensor maps hold arena addresses
     attn_tc_release(e);
+    drop_graphs(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
     CU_CHECK(e, cudaMalloc(&e.arena, bytes));
     e.arena_batch = B;
   }
   const int rows_needed = std::max(B, std::max(1, e.cfg.num_classes));
   if (rows_needed > e.rows_cap) {
+    drop_graphs(e);
     for (void* p : {(void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample})
       if (p) cudaFree(p);
     CU_CHECK(e, cudaMalloc(&e.t_rows, sizeof(float) * rows_needed));
@@ -394,8 +401,10 @@ void* tensor_ptr(const Engine& e, int id, int B) {
 
 // rows of the embedding table: uniform t -> one row (or one per class); per-sample t -> one per sample
 __global__ void setup_rows_kernel(int B, int rows, int uniform, float t_scalar, const float* t_dev,
+                                  const float* t_table, const int* step_counter,
                                   const long long* y, float* t_rows, long long* label_idx, int* row_of_sample) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_table) t_scalar = t_table[*step_counter];      // sampler loops: time of the current step lives on the device
   if (i < rows) {
     t_rows[i] = uniform ? t_scalar : t_dev[i];
     label_idx[i] = uniform ? (long long)i : (y ? y[i] : 0);
@@ -525,7 +534,8 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
 }
 
 static int forward_impl(Engine& e, int B, const float* x, const float* cond, const float* t_dev, float t_scalar,
-                        const int64_t* y, float* out, cudaStream_t st) {
+                        const int64_t* y, float* out, cudaStream_t st, const float* t_table = nullptr,
+                        const int* step_counter = nullptr) {
   if (B <= 0) return fail(e, CFM_ERR_INVALID, "batch must be positive");
   if (!x || !out) return fail(e, CFM_ERR_INVALID, "x_dev and out_dev must be non-NULL");
   if ((y != nullptr) != (e.cfg.num_classes > 0))
@@ -536,7 +546,7 @@ static int forward_impl(Engine& e, int B, const float* x, const float* cond, con
   const int uniform = t_dev == nullptr;
   const int rows = uniform ? std::max(1, e.cfg.num_classes) : B;
   const int n = std::max(rows, B);
-  setup_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, rows, uniform, t_scalar, t_dev, (const long long*)y, e.t_rows, e.label_idx, e.row_of_sample);
+  setup_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, rows, uniform, t_scalar, t_dev, t_table, step_counter, (const long long*)y, e.t_rows, e.label_idx, e.row_of_sample);
   time_hidden_kernel<<<rows, 256, sizeof(float) * e.cfg.model_channels, st>>>(e.t_rows, e.cfg.model_channels, e.ted, e.w_t1, e.b_t1, e.hidden);
   linear_rows_kernel<<<dim3((e.ted + 7) / 8, rows), 256, 0, st>>>(e.hidden, e.ted, e.w_t2, e.b_t2, e.ted, e.label_emb, e.label_idx, 1, e.semb);
   linear_rows_kernel<<<dim3((e.emb_total + 7) / 8, rows), 256, 0, st>>>(e.semb, e.ted, e.w_emb_cat, e.b_emb_cat, e.emb_total, nullptr, nullptr, 0, e.emb_out);
@@ -547,17 +557,76 @@ static int forward_impl(Engine& e, int B, const float* x, const float* cond, con
   return 0;
 }
 
-static int ensure_v(Engine& e, long long n) {
-  if (n > e.v_cap) {
-    if (e.v_buf) cudaFree(e.v_buf);
-    CU_CHECK(e, cudaMalloc(&e.v_buf, sizeof(float) * n));
-    e.v_cap = n;
-  }
+static int ew_blocks(const Engine& e, long long n) {
+  return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)e.sm_count * 8));
+}
+
+template <typename T>
+static int grow(Engine& e, T** p, long long* cap, long long n) {
+  if (n <= *cap) return 0;
+  drop_graphs(e);
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  CU_CHECK(e, cudaMalloc((void**)p, sizeof(T) * (size_t)n));
+  *cap = n;
   return 0;
 }
 
-static int ew_blocks(const Engine& e, long long n) {
-  return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)e.sm_count * 8));
+// Engine-owned sampler buffers: the step graphs only ever reference these, so a captured step can be
+// replayed for any caller buffers (state is copied in/out around the loop).
+static int ensure_sampler(Engine& e, long long n, long long n_cond, int B, int n_steps) {
+  int rc;
+  if ((rc = grow(e, &e.v_buf, &e.v_cap, n))) return rc;
+  if ((rc = grow(e, &e.x_work, &e.x_cap, n))) return rc;
+  if ((rc = grow(e, &e.cond_work, &e.cond_cap, std::max<long long>(n_cond, 1)))) return rc;
+  if ((rc = grow(e, &e.img_work, &e.img_cap, n))) return rc;
+  if ((rc = grow(e, &e.y_work, &e.y_cap, (long long)B))) return rc;
+  if ((rc = grow(e, &e.t_table, &e.t_cap, (long long)std::max(n_steps, 1)))) return rc;
+  if ((rc = grow(e, &e.dt_table, &e.dt_cap, (long long)std::max(n_steps, 1)))) return rc;
+  if ((rc = grow(e, &e.ddpm_table, &e.ddpm_cap, (long long)std::max(n_steps, 1)))) return rc;
+  if (!e.step_counter) CU_CHECK(e, cudaMalloc((void**)&e.step_counter, sizeof(int)));
+  return 0;
+}
+
+__global__ void counter_add_kernel(int* c) { *c += 1; }
+
+// Runs `body(stream)` n_steps times: directly, or as one captured-and-cached CUDA graph replayed per step.
+template <typename Body>
+static int run_steps(Engine& e, const std::string& key, bool use_graph, int n_steps, cudaStream_t st, Body body) {
+  if (n_steps <= 0) return 0;
+  if (!use_graph) {
+    for (int k = 0; k < n_steps; ++k) { int rc = body(st); if (rc) return rc; }
+    return 0;
+  }
+  auto it = e.graphs.find(key);
+  if (it == e.graphs.end()) {
+    cudaStream_t cap = nullptr;
+    CU_CHECK(e, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) { cudaStreamDestroy(cap); return fail(e, CFM_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(ce)); }
+    const int saved_launches = e.launches;
+    int rc = body(cap);
+    e.launches = saved_launches;
+    cudaGraph_t graph = nullptr;
+    ce = cudaStreamEndCapture(cap, &graph);
+    cudaStreamDestroy(cap);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(e, CFM_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    size_t n_nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &n_nodes);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(e, CFM_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+    e.graph_nodes[key] = (int)n_nodes;
+    it = e.graphs.emplace(key, exec).first;
+  }
+  for (int k = 0; k < n_steps; ++k) {
+    cudaError_t ce = cudaGraphLaunch(it->second, st);
+    if (ce != cudaSuccess) return fail(e, CFM_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(ce));
+  }
+  e.launches += e.graph_nodes[key] * n_steps;
+  return 0;
 }
 
 }  // namespace cfm
@@ -611,6 +680,10 @@ void cfm_engine_destroy(cfm_engine* h) {
   cudaSetDevice(e.device);
   tc_conv_release(e);
   attn_tc_forget(e);
+  drop_graphs(e);
+  for (void* p : {(void*)e.x_work, (void*)e.cond_work, (void*)e.img_work, (void*)e.y_work, (void*)e.t_table, (void*)e.dt_table,
+                  (void*)e.ddpm_table, (void*)e.step_counter})
+    if (p) cudaFree(p);
   for (void* p : e.owned) cudaFree(p);
   for (cudaEvent_t ev : e.prof_events) cudaEventDestroy(ev);
   for (void* p : {(void*)e.arena, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf})
@@ -681,55 +754,53 @@ int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev
                      float* traj_dev, uint8_t* img_u8_dev, void* stream) {
   if (!h) return CFM_ERR_INVALID;
   Engine& e = h->impl;
-  if (!x_dev || !t_host || !dt_host || n_steps < 0 || batch <= 0) return fail(e, CFM_ERR_INVALID, "bad argument to cfm_sample_euler");
+  if (!x_dev || (n_steps > 0 && (!t_host || !dt_host)) || n_steps < 0 || batch <= 0) return fail(e, CFM_ERR_INVALID, "bad argument to cfm_sample_euler");
+  if ((y_dev != nullptr) != (e.cfg.num_classes > 0)) return fail(e, CFM_ERR_INVALID, "must specify y if and only if the model is class-conditional");
   cudaSetDevice(e.device);
   cudaStream_t st = (cudaStream_t)stream;
   const int S = e.cfg.image_size;
   const long long n = (long long)batch * e.x_channels() * S * S;
   const long long n_cond = cond_dev ? (long long)batch * (e.cfg.in_channels - e.x_channels()) * S * S : 0;
   int rc = ensure_batch(e, batch); if (rc) return rc;
-  if ((rc = ensure_v(e, n))) return rc;
+  if ((rc = ensure_sampler(e, n, n_cond, batch, n_steps))) return rc;
   e.launches = 0;
+  // stage state and per-step scalars on the device (stream-ordered; host tables are pageable -> copied before return)
+  CU_CHECK(e, cudaMemcpyAsync(e.x_work, x_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (cond_dev) CU_CHECK(e, cudaMemcpyAsync(e.cond_work, cond_dev, sizeof(float) * n_cond, cudaMemcpyDeviceToDevice, st));
+  if (y_dev) CU_CHECK(e, cudaMemcpyAsync(e.y_work, y_dev, sizeof(long long) * batch, cudaMemcpyDeviceToDevice, st));
+  if (n_steps > 0) {
+    CU_CHECK(e, cudaMemcpyAsync(e.t_table, t_host, sizeof(float) * n_steps, cudaMemcpyHostToDevice, st));
+    CU_CHECK(e, cudaMemcpyAsync(e.dt_table, dt_host, sizeof(float) * n_steps, cudaMemcpyHostToDevice, st));
+  }
+  CU_CHECK(e, cudaMemsetAsync(e.step_counter, 0, sizeof(int), st));
   if (traj_dev) CU_CHECK(e, cudaMemcpyAsync(traj_dev, x_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   if (n_steps == 0 && img_u8_dev) { quantize_u8_kernel<<<ew_blocks(e, n), 256, 0, st>>>(img_u8_dev, x_dev, n); e.launches++; }
 
-  const bool use_graph = (flags & CFM_EULER_USE_GRAPH) && n_steps > 0;
-  cudaStream_t work = st;
-  cudaStream_t cap_stream = nullptr;
-  if (use_graph) {
-    // capture on a private stream so a legacy default stream can be the launch stream
-    CU_CHECK(e, cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
-    CU_CHECK(e, cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-    work = cap_stream;
+  const bool drift = (flags & CFM_EULER_COND_DRIFT) && cond_dev;
+  const float* cond_w = cond_dev ? e.cond_work : nullptr;
+  const int64_t* y_w = y_dev ? (const int64_t*)e.y_work : nullptr;
+  auto body = [&](cudaStream_t s2) -> int {
+    int r = forward_impl(e, batch, e.x_work, cond_w, nullptr, 0.f, y_w, e.v_buf, s2, e.t_table, e.step_counter);
+    if (r) return r;
+    euler_step_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.dt_table, e.step_counter, n_steps, n,
+                                                      drift ? e.cond_work : nullptr, n_cond, traj_dev,
+                                                      img_u8_dev ? e.img_work : nullptr);
+    counter_add_kernel<<<1, 1, 0, s2>>>(e.step_counter);
+    e.launches += 2;
+    return 0;
+  };
+  char key[160];
+  snprintf(key, sizeof(key), "euler:%d:%d:%d:%d:%d:%p:%d", batch, n_steps, cond_dev != nullptr, y_dev != nullptr, (int)drift,
+           (void*)traj_dev, img_u8_dev != nullptr);
+  const bool use_graph = (flags & CFM_EULER_USE_GRAPH) != 0;
+  if (use_graph && n_steps > 0 && !e.graphs.count(key)) {
+    // un-captured dry run first: all lazy host-side setup (tensor maps, kernel attributes) happens outside capture
+    if ((rc = forward_impl(e, batch, e.x_work, cond_w, nullptr, 0.f, y_w, e.v_buf, st, e.t_table, e.step_counter))) return rc;
   }
-  for (int k = 0; k < n_steps && rc == 0; ++k) {
-    rc = forward_impl(e, batch, x_dev, cond_dev, nullptr, t_host[k], y_dev, e.v_buf, work);
-    if (rc) break;
-    const bool last = k == n_steps - 1;
-    euler_step_kernel<<<ew_blocks(e, n), 256, 0, work>>>(
-        x_dev, e.v_buf, dt_host[k], n, (flags & CFM_EULER_COND_DRIFT) ? cond_dev : nullptr, n_cond,
-        traj_dev ? traj_dev + (long long)(k + 1) * n : nullptr, (last && img_u8_dev) ? img_u8_dev : nullptr);
-    e.launches++;
-  }
-  if (use_graph) {
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
-    if (rc == 0 && ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-    cudaGraphExec_t exec = nullptr;
-    if (rc == 0) {
-      ce = cudaGraphInstantiate(&exec, graph, 0);
-      if (ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
-    }
-    if (rc == 0) {
-      ce = cudaGraphLaunch(exec, st);
-      if (ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(ce));
-      cudaStreamSynchronize(st);
-    }
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
-    cudaStreamDestroy(cap_stream);
-  }
-  if (rc) return rc;
+  if ((rc = run_steps(e, key, use_graph, n_steps, st, body))) return rc;
+  CU_CHECK(e, cudaMemcpyAsync(x_dev, e.x_work, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (drift) CU_CHECK(e, cudaMemcpyAsync(cond_dev, e.cond_work, sizeof(float) * n_cond, cudaMemcpyDeviceToDevice, st));
+  if (img_u8_dev && n_steps > 0) CU_CHECK(e, cudaMemcpyAsync(img_u8_dev, e.img_work, (size_t)n, cudaMemcpyDeviceToDevice, st));
   CU_CHECK(e, cudaGetLastError());
   return 0;
 }
@@ -741,33 +812,23 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   Engine& e = h->impl;
   if (!x_dev || !tb || !opt || batch <= 0 || tb->Ns <= 0) return fail(e, CFM_ERR_INVALID, "bad argument to cfm_sample_ddpm");
   if (opt->mode != CFM_DDPM_PRIOR && !condition_dev) return fail(e, CFM_ERR_INVALID, "condition_dev required for conditional sampling");
+  if (e.cfg.num_classes > 0) return fail(e, CFM_ERR_INVALID, "class-conditional DDPM sampling is not part of the reference path");
   cudaSetDevice(e.device);
   cudaStream_t st = (cudaStream_t)stream;
   const int S = e.cfg.image_size, Ns = tb->Ns;
   const long long n = (long long)batch * e.x_channels() * S * S;
-  int rc = ensure_batch(e, batch); if (rc) return rc;
-  if ((rc = ensure_v(e, n))) return rc;
-  e.launches = 0;
   const bool repl = opt->mode == CFM_DDPM_REPLACEMENT;
-  const float* amort_cond = opt->mode == CFM_DDPM_AMORTIZED ? condition_dev : nullptr;
+  const bool amort = opt->mode == CFM_DDPM_AMORTIZED;
+  int rc = ensure_batch(e, batch); if (rc) return rc;
+  if ((rc = ensure_sampler(e, n, condition_dev ? n : 0, batch, Ns))) return rc;
+  e.launches = 0;
   auto blend_at = [&](int i) { return repl && i >= 0 && i < opt->replace_below_step; };
-  auto zslot = [&](int i, int which) -> const float* { return noise_dev ? noise_dev + ((long long)i * 2 + which) * n : nullptr; };
 
-  const bool use_graph = opt->use_graph != 0;
-  cudaStream_t work = st, cap_stream = nullptr;
-  if (use_graph) {
-    CU_CHECK(e, cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
-    CU_CHECK(e, cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-    work = cap_stream;
-  }
-  if (blend_at(Ns - 1)) {
-    ddpm_blend_kernel<<<ew_blocks(e, n), 256, 0, work>>>(x_dev, condition_dev, tb->sqrt_alphas_cumprod[Ns - 1],
-        tb->sqrt_one_minus_alphas_cumprod[Ns - 1], opt->pad_value, opt->noise_condition, zslot(Ns - 1, 0), seed, 2u * (Ns - 1), n);
-    e.launches++;
-  }
-  for (int i = Ns - 1; i >= 0 && rc == 0; --i) {
-    rc = forward_impl(e, batch, x_dev, amort_cond, nullptr, tb->model_time[i], nullptr, e.v_buf, work);
-    if (rc) break;
+  // per-step scalars in execution order k = 0..Ns-1  <->  chain index i = Ns-1-k
+  std::vector<DdpmStepScalars> tab(Ns);
+  std::vector<float> tt(Ns);
+  for (int k = 0; k < Ns; ++k) {
+    const int i = Ns - 1 - k;
     DdpmStepScalars s{};
     s.a = tb->sqrt_recip_alphas_cumprod[i]; s.b = tb->sqrt_recipm1_alphas_cumprod[i];
     s.c1 = tb->posterior_mean_coef1[i]; s.c2 = tb->posterior_mean_coef2[i];
@@ -777,25 +838,38 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
     s.noise_condition = opt->noise_condition; s.pad_value = opt->pad_value;
     if (s.blend_next) { s.sa = tb->sqrt_alphas_cumprod[i - 1]; s.sb = tb->sqrt_one_minus_alphas_cumprod[i - 1]; }
     s.final_clip = i == 0;
-    ddpm_step_kernel<<<ew_blocks(e, n), 256, 0, work>>>(x_dev, e.v_buf, s, condition_dev, zslot(i, 1),
-        s.blend_next ? zslot(i - 1, 0) : nullptr, seed, 2u * i + 1u, s.blend_next ? 2u * (i - 1) : 0u, n);
+    s.chain_index = i;
+    tab[k] = s;
+    tt[k] = tb->model_time[i];
+  }
+  CU_CHECK(e, cudaMemcpyAsync(e.x_work, x_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (condition_dev) CU_CHECK(e, cudaMemcpyAsync(e.cond_work, condition_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  CU_CHECK(e, cudaMemcpyAsync(e.ddpm_table, tab.data(), sizeof(DdpmStepScalars) * Ns, cudaMemcpyHostToDevice, st));
+  CU_CHECK(e, cudaMemcpyAsync(e.t_table, tt.data(), sizeof(float) * Ns, cudaMemcpyHostToDevice, st));
+  CU_CHECK(e, cudaMemsetAsync(e.step_counter, 0, sizeof(int), st));
+  CU_CHECK(e, cudaStreamSynchronize(st));   // host staging vectors go out of scope below
+  if (blend_at(Ns - 1)) {
+    ddpm_blend_kernel<<<ew_blocks(e, n), 256, 0, st>>>(e.x_work, e.cond_work, tb->sqrt_alphas_cumprod[Ns - 1],
+        tb->sqrt_one_minus_alphas_cumprod[Ns - 1], opt->pad_value, opt->noise_condition,
+        noise_dev ? noise_dev + ((long long)(Ns - 1) * 2) * n : nullptr, seed, 2u * (Ns - 1), n);
     e.launches++;
   }
-  if (use_graph) {
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
-    if (rc == 0 && ce != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-    cudaGraphExec_t exec = nullptr;
-    if (rc == 0 && (ce = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
-    if (rc == 0) {
-      if ((ce = cudaGraphLaunch(exec, st)) != cudaSuccess) rc = fail(e, CFM_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(ce));
-      cudaStreamSynchronize(st);
-    }
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
-    cudaStreamDestroy(cap_stream);
+  auto body = [&](cudaStream_t s2) -> int {
+    int r = forward_impl(e, batch, e.x_work, amort ? e.cond_work : nullptr, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
+    if (r) return r;
+    ddpm_step_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter,
+                                                     condition_dev ? e.cond_work : nullptr, noise_dev, seed, n);
+    counter_add_kernel<<<1, 1, 0, s2>>>(e.step_counter);
+    e.launches += 2;
+    return 0;
+  };
+  char key[160];
+  snprintf(key, sizeof(key), "ddpm:%d:%d:%d:%p:%llu", batch, opt->mode, condition_dev != nullptr, (const void*)noise_dev, (unsigned long long)seed);
+  if (opt->use_graph && !e.graphs.count(key)) {
+    if ((rc = forward_impl(e, batch, e.x_work, amort ? e.cond_work : nullptr, nullptr, 0.f, nullptr, e.v_buf, st, e.t_table, e.step_counter))) return rc;
   }
-  if (rc) return rc;
+  if ((rc = run_steps(e, key, opt->use_graph != 0, Ns, st, body))) return rc;
+  CU_CHECK(e, cudaMemcpyAsync(x_dev, e.x_work, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   CU_CHECK(e, cudaGetLastError());
   return 0;
 }

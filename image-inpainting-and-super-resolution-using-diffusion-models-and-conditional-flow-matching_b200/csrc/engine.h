@@ -64,6 +64,16 @@ struct Engine {
   long long* label_idx = nullptr; int* row_of_sample = nullptr; int rows_cap = 0;
   // scratch for samplers
   float* v_buf = nullptr; long long v_cap = 0;
+  float* x_work = nullptr; long long x_cap = 0;
+  float* cond_work = nullptr; long long cond_cap = 0;
+  uint8_t* img_work = nullptr; long long img_cap = 0;
+  long long* y_work = nullptr; long long y_cap = 0;
+  float* t_table = nullptr; long long t_cap = 0;
+  float* dt_table = nullptr; long long dt_cap = 0;
+  struct DdpmStepScalars* ddpm_table = nullptr; long long ddpm_cap = 0;
+  int* step_counter = nullptr;
+  std::map<std::string, cudaGraphExec_t> graphs;      // one captured step per sampler configuration
+  std::map<std::string, int> graph_nodes;
   int64_t param_count = 0;
   double flops_per_sample = 0;
   int launches = 0;

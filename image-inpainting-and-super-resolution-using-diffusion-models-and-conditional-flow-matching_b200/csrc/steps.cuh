@@ -39,15 +39,20 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
 // --- Euler:  x <- x + dt * v   (torchdyn fixed-step driver) ----------------------------------------
 // cond (optional, COND_DRIFT): con <- con + dt * con  (the reference's ode_func returns x[1] as d(con)/dt)
 // traj (optional): next trajectory slot receives the new x.  img (optional): uint8 quantisation.
-__global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict__ v, float dt, long long n,
+__global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ dt_table,
+                                  const int* __restrict__ step_counter, int n_steps, long long n,
                                   float* __restrict__ cond, long long n_cond,
-                                  float* __restrict__ traj_slot, uint8_t* __restrict__ img) {
+                                  float* __restrict__ traj, uint8_t* __restrict__ img) {
+  const int k = *step_counter;
+  const float dt = dt_table[k];
+  float* traj_slot = traj ? traj + (long long)(k + 1) * n : nullptr;
+  const bool want_img = img && k == n_steps - 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float nx = __fadd_rn(x[i], __fmul_rn(dt, v[i]));
     x[i] = nx;
     if (traj_slot) traj_slot[i] = nx;
-    if (img) img[i] = (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(nx, 127.5f), 128.0f), 0.0f), 255.0f);
+    if (want_img) img[i] = (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(nx, 127.5f), 128.0f), 0.0f), 255.0f);
   }
   if (cond)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cond; i += stride)
@@ -68,14 +73,22 @@ struct DdpmStepScalars {
   // blend for the NEXT step (i-1), applied to the freshly computed x
   int blend_next; int noise_condition; float sa, sb, pad_value;   // sqrt_ac[i-1], sqrt_1mac[i-1]
   int final_clip;              // i == 0: clip(x, -1, 1)
+  int chain_index;             // i (noise slots / Philox streams are indexed by it)
 };
 
 // x: in = xi (already blended for step i), out = state handed to the next U-Net call.
-// z_post / z_blend: injected noise (may be null -> Philox with streams 2i+1 / 2(i-1)).
-__global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, DdpmStepScalars s,
-                                 const float* __restrict__ cond, const float* __restrict__ z_post,
-                                 const float* __restrict__ z_blend, unsigned long long seed,
-                                 unsigned stream_post, unsigned stream_blend, long long n) {
+// The step's scalars come from a device table indexed by the device-side step counter, so one captured
+// launch serves every step.  noise (optional): [Ns, 2, n]; slot (i,0) = blend draw, (i,1) = posterior draw;
+// without it a Philox generator is used (streams 2i / 2i+1).
+__global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                 const DdpmStepScalars* __restrict__ table, const int* __restrict__ step_counter,
+                                 const float* __restrict__ cond, const float* __restrict__ noise,
+                                 unsigned long long seed, long long n) {
+  const DdpmStepScalars s = table[*step_counter];
+  const int ci = s.chain_index;
+  const float* z_post = noise ? noise + ((long long)ci * 2 + 1) * n : nullptr;
+  const float* z_blend = (noise && s.blend_next) ? noise + ((long long)(ci - 1) * 2) * n : nullptr;
+  const unsigned stream_post = 2u * ci + 1u, stream_blend = 2u * (ci - 1);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float xi = x[i];
