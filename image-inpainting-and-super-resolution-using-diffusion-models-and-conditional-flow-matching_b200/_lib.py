@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcfm_b200.so")
+LIB_PATH = os.environ.get("CFM_B200_LIB") or os.path.join(_HERE, "libcfm_b200.so")   # env override: A/B kernel variants
 MAX_LEVELS = 8
 
 PRECISION_FP32 = 0

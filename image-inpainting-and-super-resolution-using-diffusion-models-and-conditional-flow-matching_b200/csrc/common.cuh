@@ -15,6 +15,9 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// SiLU for the bf16 path with ONE special-function op: silu(y) = h*tanh(h) + h, h = y/2  (tanh.approx: ~2^-11 rel. error)
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float silu_from_half(float h) { return fmaf(h, tanh_approx(h), h); }
 // exact-mode SiLU (fp32 path): expf instead of the fast intrinsic
 __device__ __forceinline__ float silu_exact(float v) { return v / (1.0f + expf(-v)); }
 

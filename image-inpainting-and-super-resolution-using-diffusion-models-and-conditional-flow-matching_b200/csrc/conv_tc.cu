@@ -29,7 +29,10 @@ constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB per M-half
 constexpr int TC_STAGE_BYTES = 48 * 1024;                 // A (16 KB * mh) + B (block_n * 128 B) <= 48 KB
-constexpr int TC_EPI_WARPS = 8;
+#ifndef CFM_TC_EPI_WARPS
+#define CFM_TC_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = CFM_TC_EPI_WARPS;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;        // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr int TC_MAX_COUT = 1024;                         // bias staged in smem
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_MAX_COUT * 4 + 1024 /*align*/ + 256 /*barriers*/;
@@ -48,6 +51,7 @@ struct TcParams {
   const float* emb; int emb_stride; const int* emb_row;
   const bf16* res0; const bf16* res1; int R0, R1;
   bf16* out;
+  float* out_nchw; int cout_real;   // network head: fp32 NCHW output of the first cout_real channels
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -167,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
-      for (int item = sub; item < n_items; item += 2) {
+      for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
         const int half = item / chunks_per_half;
         const int c0 = (item - half * chunks_per_half) << 5;
         const int row = half * 128 + quad * 32 + lane;
@@ -205,14 +209,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
             }
           }
-          bf16* op = p.out + pix * p.Cout + cg;
+          if (p.out_nchw) {
+            // head conv: channel-planar fp32; lanes are consecutive pixels -> coalesced per channel
+            const long long hw = (long long)p.H * p.W;
+            float* op = p.out_nchw + (long long)n * p.cout_real * hw + (long long)h * p.W + w;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o4;
-            __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
+            for (int j = 0; j < 32; ++j)
+              if (cg + j < p.cout_real) op[(long long)(cg + j) * hw] = f[j];
+          } else {
+            bf16* op = p.out + pix * p.Cout + cg;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-            *(uint4*)(op + j) = o4;
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o4;
+              __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+              *(uint4*)(op + j) = o4;
+            }
           }
         }
       }
@@ -239,6 +252,8 @@ struct TcConvPlan {
   int seg_tensor[3] = {-1, -1, -1};
   int total_k = 0, block_n = 0;
   int bw = 0, bh = 0, bn = 0, mh = 1;
+  int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
+  float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
 };
 
@@ -268,13 +283,14 @@ static int pick_block_n(int Cout) {
 }
 
 bool tc_conv_supported(const Engine& e, const Op& op) {
-  if (!e.bf16 || op.kind != OP_CONV || op.src_is_input || op.out_is_output) return false;
+  if (!e.bf16 || op.kind != OP_CONV || op.src_is_input) return false;
+  if (op.out_is_output && (op.Cout > 32 || env_off("CFM_DISABLE_TC_HEAD"))) return false;   // head: Cout padded to 32
   if (env_off("CFM_DISABLE_TC")) return false;
   if (op.ups) return false;                                  // plan materialises the upsample in bf16 mode
   if (op.stride != 1 && op.stride != 2) return false;
   if (op.stride == 2 && env_off("CFM_DISABLE_TC_STRIDE2")) return false;
   if (op.ks != 1 && op.ks != 3) return false;
-  if (pick_block_n(op.Cout) == 0 || op.Cout > TC_MAX_COUT) return false;
+  if (!op.out_is_output && (pick_block_n(op.Cout) == 0 || op.Cout > TC_MAX_COUT)) return false;
   if (!pow2(op.Hout) || !pow2(op.Wout) || op.Wout > 128 || op.Hout > 128) return false;
   if (op.stride == 2 && (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout || 2 * std::min(op.Wout, 128) > 256)) return false;
   auto chan_ok = [&](int id) { return id < 0 || e.tensors[id].C % TC_BLOCK_K == 0; };
@@ -287,7 +303,9 @@ bool tc_conv_supported(const Engine& e, const Op& op) {
 
 int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::vector<float>& ws) {
   TcConvPlan* pl = new TcConvPlan();
-  const int Cout = op.Cout, Cin = op.Cin, ks = op.ks;
+  const int Cin = op.Cin, ks = op.ks;
+  const int Cout = op.out_is_output ? 32 : op.Cout;      // padded rows of W are zero
+  pl->cout_pad = Cout;
   pl->block_n = pick_block_n(Cout);
   // N <= 128 tiles are shared-memory-bandwidth bound with a 128-row tile (A and B stream at 1:1);
   // a 256-row tile (two UMMAs per B tile) restores the 2:1 ratio of the N = 256 case.
@@ -307,7 +325,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
     for (int ch = 0; ch < Cin / TC_BLOCK_K; ++ch, ++kiter)
       for (int o = 0; o < Cout; ++o)
         for (int j = 0; j < TC_BLOCK_K; ++j)
-          packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(w[((size_t)o * Cin + ch * TC_BLOCK_K + j) * ks * ks + tap]);
+          packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(o < op.Cout ? w[((size_t)o * Cin + ch * TC_BLOCK_K + j) * ks * ks + tap] : 0.f);
   for (int ch = 0; ch < op.Cskip / TC_BLOCK_K; ++ch, ++kiter)
     for (int o = 0; o < Cout; ++o)
       for (int j = 0; j < TC_BLOCK_K; ++j)
@@ -317,6 +335,16 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   e.owned.push_back(d);
   if (cudaMemcpy(d, packed.data(), packed.size() * sizeof(bf16), cudaMemcpyHostToDevice) != cudaSuccess) { e.err = "weight upload failed"; delete pl; return CFM_ERR_CUDA; }
   pl->w_packed = (bf16*)d;
+  if (op.out_is_output) {
+    std::vector<float> hb(op.Cout);
+    if (cudaMemcpy(hb.data(), op.bias, sizeof(float) * op.Cout, cudaMemcpyDeviceToHost) != cudaSuccess) { e.err = "bias readback failed"; delete pl; return CFM_ERR_CUDA; }
+    hb.resize(Cout, 0.f);
+    void* bp = nullptr;
+    if (cudaMalloc(&bp, sizeof(float) * Cout) != cudaSuccess) { e.err = "cudaMalloc(bias_pad) failed"; delete pl; return CFM_ERR_OOM; }
+    e.owned.push_back(bp);
+    cudaMemcpy(bp, hb.data(), sizeof(float) * Cout, cudaMemcpyHostToDevice);
+    pl->bias_pad = (float*)bp;
+  }
   op.tc = pl;
   static bool attr_set = false;
   if (!attr_set) {
@@ -344,7 +372,7 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
     if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
   }
   for (int s = pl->n_seg; s < 3; ++s) m->a[s] = m->a[0];
-  cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->total_k * op.Cout};
+  cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->total_k * pl->cout_pad};
   cuuint64_t strides[1] = {(cuuint64_t)TC_BLOCK_K * 2};
   cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)pl->block_n};
   cuuint32_t estr[2] = {1, 1};
@@ -355,7 +383,7 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
   return 0;
 }
 
-int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
+int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_nchw) {
   TcConvPlan* pl = op.tc;
   auto it = pl->maps.find(B);
   if (it == pl->maps.end()) {
@@ -371,14 +399,15 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.B = B; p.H = op.Hout; p.W = op.Wout;
   p.bw = pl->bw; p.bh = pl->bh; p.bn = pl->bn; p.mh = pl->mh;
   p.tiles_w = op.Wout / pl->bw; p.tiles_h = op.Hout / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
-  p.tiles_n = op.Cout / pl->block_n;
+  p.tiles_n = pl->cout_pad / pl->block_n;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
-  p.block_n = pl->block_n; p.Cout = op.Cout;
-  p.bias = op.bias;
+  p.block_n = pl->block_n; p.Cout = pl->cout_pad;
+  p.bias = pl->bias_pad ? pl->bias_pad : op.bias;
   if (op.emb_off >= 0) { p.emb = e.emb_out + op.emb_off; p.emb_stride = e.emb_total; p.emb_row = e.row_of_sample; }
   p.res0 = (const bf16*)tensor_ptr(e, op.res0, B); p.R0 = op.res0 >= 0 ? e.tensors[op.res0].C : 0;
   p.res1 = (const bf16*)tensor_ptr(e, op.res1, B); p.R1 = op.res1 >= 0 ? e.tensors[op.res1].C : 0;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
+  if (op.out_is_output) { p.out_nchw = out_nchw; p.cout_real = op.Cout; }
   const int grid = std::min(p.n_tiles, e.sm_count);
   conv_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
   return 0;

@@ -206,6 +206,42 @@ static int add_attention(Engine& e, const std::string& p, Cur x, int heads, Cur*
   return 0;
 }
 
+// Tensor-core stem: im2col (hi/lo bf16 split of the fp32 input) + a K_pad-deep 1x1 GEMM.  *done stays false
+// (and nothing is added) when the tcgen05 kernel cannot take the shape.
+static int add_stem_tc(Engine& e, int Cin, int S, int Cout, int out, bool* done) {
+  const int K9 = 9 * Cin, Kpad = (2 * K9 + 63) / 64 * 64;
+  Op op; op.kind = OP_CONV; op.name = "input_blocks.0.0";
+  op.ks = 1; op.stride = 1; op.ups = 0; op.Cin = Kpad; op.Hin = op.Win = op.Hout = op.Wout = S; op.Cout = Cout;
+  op.out = out;
+  TensorDesc probe; probe.C = Kpad; probe.H = S; probe.W = S;
+  e.tensors.push_back(probe);
+  op.src0 = (int)e.tensors.size() - 1;
+  if (!tc_conv_supported(e, op)) { e.tensors.pop_back(); return 0; }
+  const float *w = nullptr, *b = nullptr; int rc;
+  if ((rc = fetch(e, "input_blocks.0.0.weight", (int64_t)Cout * Cin * 9, &w))) return rc;
+  if ((rc = fetch(e, "input_blocks.0.0.bias", Cout, &b))) return rc;
+  std::vector<float> w_eff((size_t)Cout * Kpad, 0.f);          // [Cout][Kpad]: k = tap*Cin + c, duplicated for the lo term
+  for (int o = 0; o < Cout; ++o)
+    for (int cc = 0; cc < Cin; ++cc)
+      for (int tap = 0; tap < 9; ++tap) {
+        const float v = w[((size_t)o * Cin + cc) * 9 + tap];
+        w_eff[(size_t)o * Kpad + tap * Cin + cc] = v;
+        w_eff[(size_t)o * Kpad + K9 + tap * Cin + cc] = v;
+      }
+  std::vector<float> wkn = to_kn(w_eff.data(), Cout, Kpad, 1);
+  if ((rc = upload(e, wkn.data(), wkn.size(), &op.w_main))) return rc;
+  if ((rc = upload(e, b, Cout, &op.bias))) return rc;
+  op.flops = 2.0 * S * S * Cout * K9;
+  Op col; col.kind = OP_IM2COL; col.name = "input_blocks.0.0.im2col"; col.out = op.src0;
+  col.Cin = Cin; col.Cout = Kpad; col.Hin = col.Win = S;
+  e.ops.push_back(col);
+  if ((rc = tc_conv_prepare(e, op, w_eff, {}))) return rc;
+  e.n_tc_convs++;
+  e.ops.push_back(op);
+  *done = true;
+  return 0;
+}
+
 static int build_plan(Engine& e) {
   const cfm_unet_config& c = e.cfg;
   const int mc = c.model_channels;
@@ -219,8 +255,12 @@ static int build_plan(Engine& e) {
   Cur h;
   {
     const int t = new_tensor(e, ch, S, S);
-    if ((rc = add_conv(e, "input_blocks.0.0", "input_blocks.0.0", 3, 1, 0, -1, -1, true, c.in_channels, S, S, ch,
-                       "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
+    bool done = false;
+    if (e.bf16 && 18 * c.in_channels <= 128) {
+      if ((rc = add_stem_tc(e, c.in_channels, S, ch, t, &done))) return rc;
+    }
+    if (!done && (rc = add_conv(e, "input_blocks.0.0", "input_blocks.0.0", 3, 1, 0, -1, -1, true, c.in_channels, S, S, ch,
+                                "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
     h = {t, ch, S, S};
     hs.push_back(h);
   }
@@ -421,7 +461,7 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
     switch (op.kind) {
       case OP_CONV: {
         if (op.tc) {
-          int rc = tc_conv_launch(e, op, B, st);
+          int rc = tc_conv_launch(e, op, B, st, out);
           if (rc) return rc;
           e.launches++;
           break;
@@ -486,6 +526,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         const int cap = kGnSmemBytes / 4;
         a.smem_elems = n <= cap ? n : 0;
         groupnorm_kernel<T><<<B * 32, 256, (size_t)a.smem_elems * 4, st>>>(a);
+        e.launches++;
+        break;
+      }
+      case OP_IM2COL: {
+        int rc = stem_im2col_launch(e, op, B, x, cond, st);
+        if (rc) return rc;
         e.launches++;
         break;
       }
@@ -743,7 +789,7 @@ int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t n
   if (!h || i < 0 || i >= (int32_t)h->impl.prof_ms.size()) return CFM_ERR_INVALID;
   const Op& op = h->impl.ops[i];
   if (name && name_cap > 0) { std::strncpy(name, op.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
-  if (kind) *kind = op.kind == OP_CONV ? (op.tc ? 4 : 0) : (int)op.kind;
+  if (kind) *kind = op.kind == OP_CONV ? (op.tc ? 4 : 0) : (op.kind == OP_IM2COL ? 2 : (int)op.kind);
   if (ms) *ms = h->impl.prof_ms[i];
   if (flops_per_sample) *flops_per_sample = op.flops;
   return 0;

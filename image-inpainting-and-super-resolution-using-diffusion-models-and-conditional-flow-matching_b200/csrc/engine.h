@@ -20,7 +20,7 @@ struct TensorDesc {
   long long elems() const { return (long long)C * H * W; }
 };
 
-enum OpKind { OP_CONV = 0, OP_GN = 1, OP_RESAMPLE = 2, OP_ATTN = 3 };
+enum OpKind { OP_CONV = 0, OP_GN = 1, OP_RESAMPLE = 2, OP_ATTN = 3, OP_IM2COL = 4 };
 
 struct TcConvPlan;   // tcgen05 implicit-GEMM lowering of a conv op (conv_tc.cu)
 
@@ -88,7 +88,7 @@ struct Engine {
 // conv_tc.cu
 bool tc_conv_supported(const Engine& e, const Op& op);
 int  tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w_main_oihw, const std::vector<float>& w_skip_oi);
-int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_nchw = nullptr);
 void tc_conv_release(Engine& e);
 // bf16 fast kernels (kernels_bf16.cu)
 int  gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
@@ -104,5 +104,6 @@ bool head_conv_supported(const Engine& e, const Op& op);
 int  head_conv_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t st);
 bool stem_conv_supported(const Engine& e, const Op& op);
 int  stem_conv_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st);
+int  stem_im2col_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st);
 
 }  // namespace cfm

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
       const float m = 1.0f + f[cb + c];
       sc_ *= m; sh_ = sh_ * m + f[C + cb + c];
     }
+    if (a.silu) { sc_ *= 0.5f; sh_ *= 0.5f; }          // the activation works on h = y/2: silu(y) = h*tanh(h) + h
     ch_scale[wi * GN_MAX_SLAB + c] = sc_; ch_shift[wi * GN_MAX_SLAB + c] = sh_;
   }
   __syncthreads();
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
       for (int j = 0; j < 4; ++j) {
         const float2 f = __bfloat1622float2(h2[j]);
         float y0 = fmaf(f.x, sc8[2 * j], sh8[2 * j]), y1 = fmaf(f.y, sc8[2 * j + 1], sh8[2 * j + 1]);
-        if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+        if (a.silu) { y0 = silu_from_half(y0); y1 = silu_from_half(y1); }
         o2[j] = __floats2bfloat162_rn(y0, y1);
       }
       *(uint4*)op = o4;
@@ -310,9 +311,10 @@ int head_conv_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t st
 // ------------------------------------------------------------------------------------------------
 constexpr int STEM_MAX_CIN = 8;
 
-// One thread per output pixel: the <= 9*8 input taps are loaded once into registers, then all Cout
-// channels are produced 32 at a time from weights broadcast out of shared memory.
-__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0, int C1,
+// One thread per (pixel, 8 output channels); the Cout/8 threads of a pixel are adjacent lanes, so their
+// input-tap loads are one broadcast transaction and their 16-byte stores tile the pixel's NHWC row
+// contiguously (fully coalesced writes - this kernel is bound by writing the [B,H,W,Cout] tensor).
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0, int C1,
                                                         const float* __restrict__ w /*[9*Cin][Cout]*/, const float* __restrict__ bias,
                                                         bf16* __restrict__ out, int B, int H, int W, int Cout) {
   extern __shared__ float sw[];        // [9*Cin][Cout] then bias[Cout]
@@ -322,53 +324,34 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   float* sb = sw + K * Cout;
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
-  const long long total = (long long)B * H * W;
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= total) return;
-  const int x = (int)(m % W), y = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
-  float in[9 * STEM_MAX_CIN];
+  const int cv = Cout >> 3;
+  const long long total = (long long)B * H * W * cv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int co = (int)(i % cv) << 3;
+    const long long m = i / cv;
+    const int x = (int)(m % W), y = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+    float acc[8];
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-#pragma unroll
-    for (int c = 0; c < STEM_MAX_CIN; ++c) {
-      float v = 0.f;
-      if (ok && c < Cin)
-        v = (c < C0) ? __ldg(x0 + (((long long)b * C0 + c) * H + iy) * W + ix)
-                     : __ldg(x1 + (((long long)b * C1 + (c - C0)) * H + iy) * W + ix);
-      in[tap * STEM_MAX_CIN + c] = v;
-    }
-  }
-  bf16* op = out + m * Cout;
-  for (int co = 0; co < Cout; co += 32) {
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = sb[co + j];
+    for (int j = 0; j < 8; ++j) acc[j] = sb[co + j];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-      for (int c = 0; c < STEM_MAX_CIN; ++c) {
-        if (c < Cin) {
-          const float v = in[tap * STEM_MAX_CIN + c];
-          const float4* wr = (const float4*)(sw + (tap * Cin + c) * Cout + co);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w4 = wr[j];
-            acc[4 * j] = fmaf(v, w4.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
-          }
-        }
+      const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      for (int c = 0; c < Cin; ++c) {
+        const float v = (c < C0) ? __ldg(x0 + (((long long)b * C0 + c) * H + iy) * W + ix)
+                                 : __ldg(x1 + (((long long)b * C1 + (c - C0)) * H + iy) * W + ix);
+        const float4 w0 = *(const float4*)(sw + (tap * Cin + c) * Cout + co);
+        const float4 w1 = *(const float4*)(sw + (tap * Cin + c) * Cout + co + 4);
+        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
       }
     }
+    uint4 o4;
+    __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 o4;
-      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(acc[j + 2 * q], acc[j + 2 * q + 1]);
-      *(uint4*)(op + co + j) = o4;
-    }
+    for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    *(uint4*)(out + m * Cout + co) = o4;
   }
 }
 
@@ -386,9 +369,58 @@ int stem_conv_launch(Engine& e, const Op& op, int B, const float* x, const float
     if (cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) { e.err = "cudaFuncSetAttribute(stem_conv_kernel) failed"; return CFM_ERR_CUDA; }
     attr = true;
   }
-  const long long total = (long long)B * op.Hout * op.Wout;
-  stem_conv_kernel<<<(unsigned)((total + 127) / 128), 128, smem, st>>>(x, cond, cx, e.cfg.in_channels - cx, op.w_main, op.bias,
+  const long long total = (long long)B * op.Hout * op.Wout * (op.Cout / 8);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.sm_count * 8);
+  stem_conv_kernel<<<blocks, 256, smem, st>>>(x, cond, cx, e.cfg.in_channels - cx, op.w_main, op.bias,
                                                                      (bf16*)tensor_ptr(e, op.out, B), B, op.Hout, op.Wout, op.Cout);
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Stem im2col: fp32 NCHW network input (x [+ cond]) -> bf16 NHWC rows of K_pad values per pixel:
+//   [0, 9*Cin)        hi = bf16(x_tap)            (tap-major, channel-minor; zero outside the image)
+//   [9*Cin, 18*Cin)   lo = bf16(x_tap - hi)       (second bf16 term: the input keeps ~16 mantissa bits)
+//   rest              0
+// so the 3x3 stem conv becomes a K_pad-deep 1x1 GEMM on the tensor cores (weights duplicated for hi/lo).
+// ------------------------------------------------------------------------------------------------
+__global__ void stem_im2col_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0, int C1,
+                                   bf16* __restrict__ out, int B, int H, int W, int Kpad) {
+  const int Cin = C0 + C1, K9 = 9 * Cin;
+  const int cv = Kpad >> 3;
+  const long long total = (long long)B * H * W * cv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k0 = (int)(i % cv) << 3;
+    const long long m = i / cv;
+    const int x = (int)(m % W), y = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+    uint4 o4;
+    bf16* ob = (bf16*)&o4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int k = k0 + j;
+      const bool lo = k >= K9;
+      if (lo) k -= K9;
+      float v = 0.f;
+      if (k < K9) {
+        const int tap = k / Cin, c = k - tap * Cin;
+        const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v = (c < C0) ? __ldg(x0 + (((long long)b * C0 + c) * H + iy) * W + ix)
+                       : __ldg(x1 + (((long long)b * C1 + (c - C0)) * H + iy) * W + ix);
+        if (lo) v = v - __bfloat162float(__float2bfloat16_rn(v));
+      }
+      ob[j] = __float2bfloat16_rn(v);
+    }
+    *(uint4*)(out + i * 8) = o4;
+  }
+}
+
+int stem_im2col_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st) {
+  const int cx = cond ? e.x_channels() : e.cfg.in_channels;
+  const long long total = (long long)B * op.Hin * op.Win * (op.Cout / 8);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.sm_count * 16);
+  stem_im2col_kernel<<<blocks, 256, 0, st>>>(x, cond, cx, e.cfg.in_channels - cx, (bf16*)tensor_ptr(e, op.out, B), B, op.Hin, op.Win, op.Cout);
   return 0;
 }
 

@@ -18,7 +18,12 @@ for _ in range(5): e.forward(x, 0.5)
 torch.cuda.synchronize()
 dt=(time.time()-t0)/5
 print(f"B={B} NFE {dt*1e3:.2f} ms  -> {e.flops_per_sample*B/dt/1e12:.1f} TFLOP/s, ws={e.workspace_bytes(B)/2**30:.2f} GiB, launches={e.last_launches}")
-rows = e.profile_forward(x, 0.5, repeats=3)
+import subprocess
+def clk():
+    return subprocess.run(["nvidia-smi","--query-gpu=clocks.sm,power.draw","--format=csv,noheader"],capture_output=True,text=True).stdout.strip()
+print("clocks before profile:", clk())
+rows = e.profile_forward(x, 0.5, repeats=10)
+print("clocks after profile:", clk())
 agg = collections.defaultdict(lambda:[0.0,0.0,0])
 for r in rows:
     a=agg[r['kind']]; a[0]+=r['ms']; a[1]+=r['flops']; a[2]+=1
