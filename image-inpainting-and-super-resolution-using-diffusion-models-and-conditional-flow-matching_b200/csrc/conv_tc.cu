@@ -242,9 +242,199 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two SMs of a cluster cooperate on a 256-row x N tile.  Each CTA loads
+// its own 128-row A half and HALF of the weight tile (N/2 rows) - so the bytes pulled from L2 and
+// written to / read from shared memory per FLOP drop by a third versus the single-CTA 128 x N tile,
+// and the freed shared memory buys a deeper ring (6 stages at N = 256).  The leader CTA's MMA warp
+// issues one 256 x N x 16 UMMA per K step; tcgen05.commit multicasts stage-free / accumulator-ready
+// signals to both CTAs; both CTAs' epilogues drain their own 128 TMEM lanes and report back to the
+// leader's accumulator-empty barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int TC2_MAX_STAGES = 8;
+constexpr int TC2_RING_BYTES = 192 * 1024;
+constexpr int TC2_SMEM_BYTES = TC2_RING_BYTES + TC_MAX_COUT * 4 + 1024 + 256;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+                const TcParams p, const int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = TC_A_BYTES;                              // 128 rows per CTA
+  const int b_bytes = (p.block_n >> 1) * TC_BLOCK_K * 2;       // half of the weight tile per CTA
+  const int stage_bytes = a_bytes + b_bytes;
+  float* s_bias = (float*)(smem + TC2_RING_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + TC2_RING_BYTES + TC_MAX_COUT * 4);
+  uint64_t* full_bar = bars;                          // [8]  (leader's are used)
+  uint64_t* empty_bar = bars + TC2_MAX_STAGES;        // [8]  per CTA, signalled by the leader's commit multicast
+  uint64_t* tfull_bar = bars + 2 * TC2_MAX_STAGES;    // [2]  per CTA, commit multicast
+  uint64_t* tempty_bar = bars + 2 * TC2_MAX_STAGES + 2;   // [2]  leader's are used: 2 * TC_EPI_WARPS arrivals
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC2_MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int pair_tiles = ((tiles128 + 1) >> 1) * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+    if (p.n_seg > 1) prefetch_tmap(&mapA1);
+    if (p.n_seg > 2) prefetch_tmap(&mapA2);
+    for (int s = 0; s < TC2_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * TC_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // peer barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+        const int nt = pt % p.tiles_n;
+        int mt = (pt / p.tiles_n) * 2 + (int)rank;             // this CTA's 128-row tile
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tb = mt / p.tiles_h;                         // may equal tiles_b for the odd tail: all-OOB loads
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tb * p.bn;
+        int kiter = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const TcSeg sg = p.seg[s];
+          const CUtensorMap* map = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
+          const int taps = sg.ks * sg.ks, pad = sg.ks >> 1;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = tap / sg.ks - pad, dx = tap % sg.ks - pad;
+            for (int ch = 0; ch < sg.n_chunks; ++ch, ++kiter) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);       // leader's full barrier
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);      // bytes of BOTH CTAs
+              uint8_t* sa = smem + stage * stage_bytes;
+              tma_load_4d_2sm(sa, map, bar, ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+              tma_load_2d_2sm(sa + a_bytes, &mapB, bar, 0, kiter * p.Cout + nt * p.block_n + (int)rank * (p.block_n >> 1));
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      const uint32_t idesc = make_idesc(256, p.block_n);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        for (int k = 0; k < p.total_k; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+            const uint64_t adesc = make_desc_sw128(sa);
+            const uint64_t bdesc = make_desc_sw128(sa + a_bytes);
+#pragma unroll
+            for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk)
+              umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage], 3);                       // both CTAs may refill this stage
+            if (k == p.total_k - 1) umma_commit_2sm(&tfull_bar[acc], 3); // both CTAs' epilogues may drain
+          }
+          __syncwarp();
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int n_items = p.block_n >> 5;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+      const int nt = pt % p.tiles_n;
+      int mt = (pt / p.tiles_n) * 2 + (int)rank;
+      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tb = mt / p.tiles_h;
+      const int row = quad * 32 + lane;
+      const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
+      const int n = tb * p.bn + ni, h = th * p.bh + hi, w = tw * p.bw + wi;
+      const bool valid = n < p.B;
+      const long long pix = ((long long)n * p.H + h) * p.W + w;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
+      for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
+        const int c0 = item << 5;
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int cg = nt * p.block_n + c0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *(const float4*)(s_bias + cg + j);
+            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (p.emb) {
+            const float* embp = p.emb + (long long)p.emb_row[n] * p.emb_stride;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 e4 = __ldg((const float4*)(embp + cg + j));
+              f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
+            }
+          }
+          if (p.res0) {
+            const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cg : p.res1 + pix * p.R1 + (cg - p.R0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 r4 = __ldg((const uint4*)(rp + j));
+              const __nv_bfloat162* rb = (const __nv_bfloat162*)&r4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
+            }
+          }
+          bf16* op = p.out + pix * p.Cout + cg;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o4;
+            __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+            *(uint4*)(op + j) = o4;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // report to the leader
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // neither CTA may retire (smem / TMEM) while its peer can still touch it
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct TcMaps { CUtensorMap a[3]; CUtensorMap b; };
+struct TcMaps { CUtensorMap a[3]; CUtensorMap b; CUtensorMap a2[3]; CUtensorMap b2; };   // a2/b2: CTA-pair boxes (128 rows, N/2 rows)
 
 struct TcConvPlan {
   bf16* w_packed = nullptr;     // [total_k * Cout][64]
@@ -252,6 +442,8 @@ struct TcConvPlan {
   int seg_tensor[3] = {-1, -1, -1};
   int total_k = 0, block_n = 0;
   int bw = 0, bh = 0, bn = 0, mh = 1;
+  bool pair = false;           // CTA-pair (cta_group::2) kernel
+  int pbw = 0, pbh = 0, pbn = 0;   // 128-row box of the pair kernel
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
@@ -314,6 +506,10 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   pl->bw = std::min(op.Wout, rows);
   pl->bh = std::min(op.Hout, rows / pl->bw);
   pl->bn = rows / (pl->bw * pl->bh);
+  pl->pair = !op.out_is_output && pl->block_n >= 192 && !env_off("CFM_DISABLE_TC_2CTA");   // N = 128 tiles are A-traffic bound: 256-row single-CTA tiles win there
+  pl->pbw = std::min(op.Wout, 128);
+  pl->pbh = std::min(op.Hout, 128 / pl->pbw);
+  pl->pbn = 128 / (pl->pbw * pl->pbh);
   pl->seg[0] = {0, Cin / TC_BLOCK_K, ks, op.stride}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
   if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
   if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
@@ -348,7 +544,8 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   op.tc = pl;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(conv_tc_kernel, smem) failed"; return CFM_ERR_CUDA;
     }
     attr_set = true;
@@ -372,6 +569,29 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
     if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
   }
   for (int s = pl->n_seg; s < 3; ++s) m->a[s] = m->a[0];
+  if (pl->pair) {
+    for (int s = 0; s < pl->n_seg; ++s) {
+      const TensorDesc& t = e.tensors[pl->seg_tensor[s]];
+      const int st = pl->seg[s].stride;
+      cuuint64_t dims[4] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)t.C * 2, (cuuint64_t)t.W * t.C * 2, (cuuint64_t)t.H * t.W * t.C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->pbw * st), (cuuint32_t)(pl->pbh * st), (cuuint32_t)pl->pbn};
+      cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
+      CUresult r = g_encode(&m->a2[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, tensor_ptr(e, pl->seg_tensor[s], B), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A pair) failed for " + op.name; return CFM_ERR_CUDA; }
+    }
+    for (int s = pl->n_seg; s < 3; ++s) m->a2[s] = m->a2[0];
+    cuuint64_t dims2[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->total_k * pl->cout_pad};
+    cuuint64_t strides2[1] = {(cuuint64_t)TC_BLOCK_K * 2};
+    cuuint32_t box2[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->block_n / 2)};
+    cuuint32_t estr2[2] = {1, 1};
+    CUresult r2 = g_encode(&m->b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->w_packed, dims2, strides2, box2, estr2,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r2 != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(B pair) failed for " + op.name; return CFM_ERR_CUDA; }
+  }
   cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->total_k * pl->cout_pad};
   cuuint64_t strides[1] = {(cuuint64_t)TC_BLOCK_K * 2};
   cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)pl->block_n};
@@ -408,6 +628,26 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.res1 = (const bf16*)tensor_ptr(e, op.res1, B); p.R1 = op.res1 >= 0 ? e.tensors[op.res1].C : 0;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
   if (op.out_is_output) { p.out_nchw = out_nchw; p.cout_real = op.Cout; }
+  if (pl->pair) {
+    p.bw = pl->pbw; p.bh = pl->pbh; p.bn = pl->pbn; p.mh = 1;
+    p.tiles_w = op.Wout / p.bw; p.tiles_h = op.Hout / p.bh; p.tiles_b = (B + p.bn - 1) / p.bn;
+    const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n;
+    const int stage_bytes = TC_A_BYTES + (pl->block_n / 2) * TC_BLOCK_K * 2;
+    const int n_stages = std::min(TC2_MAX_STAGES, TC2_RING_BYTES / stage_bytes);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * std::min(pair_tiles, e.sm_count / 2));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC2_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, it->second.a2[0], it->second.a2[1], it->second.a2[2], it->second.b2, p, n_stages);
+    if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
+    return 0;
+  }
   const int grid = std::min(p.n_tiles, e.sm_count);
   conv_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
   return 0;
