@@ -34,7 +34,7 @@ constexpr int TC_STAGE_BYTES = 48 * 1024;                 // A (16 KB * mh) + B 
 #endif
 constexpr int TC_EPI_WARPS = CFM_TC_EPI_WARPS;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;        // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
-constexpr int TC_MAX_COUT = 1024;                         // bias staged in smem
+constexpr int TC_MAX_COUT = 2048;                         // bias staged in smem
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_MAX_COUT * 4 + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcSeg { int map; int n_chunks; int ks; int stride; };

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include "engine.h"
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cfm {
 
@@ -22,6 +23,7 @@ struct GnFastArgs {
   const bf16* src0; const bf16* src1; int C0, C1;
   int HW, cpg, slab;                 // slab channels per item (multiple of 8 and of cpg)
   int tpi, ipc, n_items;             // threads per item, items per CTA, total items
+  int cs;                            // CTAs (of one cluster) sharing an item's pixels; 1 = no cluster
   const float* gamma; const float* beta; float eps; int silu;
   const float* film; int film_stride; const int* film_row;
   bf16* out;
@@ -47,7 +49,11 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
   const int nvec = a.HW * vpp;
   const int il = threadIdx.x / a.tpi;                    // item within the CTA
   const int ti = threadIdx.x - il * a.tpi;               // thread within the item
-  const int item = blockIdx.x * a.ipc + il;
+  // cs > 1: the CTAs of a cluster split one item's pixels (large feature maps); then ipc == 1
+  const int crank = a.cs > 1 ? (int)cluster_ctarank() : 0;
+  const int item = a.cs > 1 ? (int)(blockIdx.x / a.cs) : blockIdx.x * a.ipc + il;
+  const int HWl = a.HW / a.cs;                           // pixels owned by this CTA
+  const int pbase = crank * HWl;
   const bool active = item < a.n_items;
   const int b = active ? item / slabs : 0, sl = active ? item % slabs : 0;
   const int c_base = sl * a.slab;
@@ -55,8 +61,8 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
   const int cq = c_base + q * 8;
   const bf16* sp; int sC, sc;
   if (cq < a.C0) { sp = a.src0; sC = a.C0; sc = cq; } else { sp = a.src1; sC = a.C1; sc = cq - a.C0; }
-  const long long pix0 = (long long)b * a.HW;
-  const int p0 = ti / vpp, pstep = a.tpi / vpp;          // this thread's pixels: p0 + k*pstep
+  const long long pix0 = (long long)b * a.HW + pbase;
+  const int p0 = ti / vpp, pstep = a.tpi / vpp;          // this thread's pixels: p0 + k*pstep (within the CTA's range)
 
   uint4 regs[GN_VPT];
   {
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
     const long long lstep = (long long)pstep * sC;
 #pragma unroll
     for (int k = 0; k < GN_VPT; ++k) {
-      regs[k] = (active && p0 + k * pstep < a.HW) ? __ldg((const uint4*)lp) : make_uint4(0, 0, 0, 0);
+      regs[k] = (active && p0 + k * pstep < HWl) ? __ldg((const uint4*)lp) : make_uint4(0, 0, 0, 0);
       lp += lstep;
     }
   }
@@ -96,9 +102,23 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
     ch_sum[wi * GN_MAX_SLAB + c] = ts; ch_sq[wi * GN_MAX_SLAB + c] = tq;
   }
   __syncthreads();
+  if (a.cs > 1) {
+    // combine the per-CTA channel sums across the cluster through distributed shared memory, in rank order
+    cluster_sync_all();
+    float ts = 0.f, tq = 0.f;
+    if (threadIdx.x < a.slab) {
+      for (int r = 0; r < a.cs; ++r) {
+        ts += ld_dsmem_f32(mapa_u32(smem_u32(&ch_sum[threadIdx.x]), r));
+        tq += ld_dsmem_f32(mapa_u32(smem_u32(&ch_sq[threadIdx.x]), r));
+      }
+    }
+    cluster_sync_all();              // everyone has read the partials before they are overwritten
+    if (threadIdx.x < a.slab) { ch_sum[threadIdx.x] = ts; ch_sq[threadIdx.x] = tq; }
+    __syncthreads();
+  }
   for (int w = threadIdx.x; w < a.ipc * a.slab; w += blockDim.x) {
     const int wi = w / a.slab, c = w - wi * a.slab;
-    const int it = blockIdx.x * a.ipc + wi;
+    const int it = a.cs > 1 ? (int)(blockIdx.x / a.cs) : blockIdx.x * a.ipc + wi;
     if (it >= a.n_items) continue;
     const int bb = it / slabs, cb = (it % slabs) * a.slab;
     const int g0 = (c / a.cpg) * a.cpg;
@@ -127,7 +147,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
   const long long ostep = (long long)pstep * C;
 #pragma unroll
   for (int k = 0; k < GN_VPT; ++k, op += ostep) {
-    if (p0 + k * pstep < a.HW) {
+    if (p0 + k * pstep < HWl) {
       const __nv_bfloat162* h2 = (const __nv_bfloat162*)&regs[k];
       uint4 o4;
       __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
@@ -145,25 +165,38 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-struct GnGeom { int cpg, slab, tpi, ipc, threads; size_t smem; bool ok; };
+struct GnGeom { int cpg, slab, tpi, ipc, threads, cs; size_t smem; bool ok; };
 
 static GnGeom gn_geometry(const Op& op) {
   GnGeom g{};
-  const int C = op.Cin;
+  const int C = op.Cin, HW = op.Hin * op.Win;
   g.cpg = C / 32;
+  g.cs = 1;
   const int base = g.cpg / gcd_i(g.cpg, 8) * 8;        // lcm(cpg, 8): smallest legal slab
   // widest slab (<= 64 channels, dividing C) whose item still fits GN_VPT vectors/thread in <= 256 threads
   for (int sl = base; sl <= GN_MAX_SLAB && C % sl == 0; sl *= 2) {
     const int vpp = sl / 8;
     const int unit = 32 / gcd_i(32, vpp) * vpp;        // lcm(32, vpp): whole warps, multiple of vpp
-    const int nvec = op.Hin * op.Win * vpp;
+    const int nvec = HW * vpp;
     int tpi = ((nvec + GN_VPT - 1) / GN_VPT + unit - 1) / unit * unit;
     tpi = std::max(tpi, unit);
     if (tpi > GN_MAX_THREADS) break;
     g.slab = sl; g.tpi = tpi; g.ok = true;
   }
+  if (!g.ok && base <= GN_MAX_SLAB && C % base == 0) {
+    // large feature map: split the item's pixels over a cluster of 2..8 CTAs (partials combined through DSMEM)
+    const int vpp = base / 8;
+    const int unit = 32 / gcd_i(32, vpp) * vpp;
+    for (int cs = 2; cs <= 8; cs *= 2) {
+      if (HW % cs) break;
+      const int nvec = (HW / cs) * vpp;
+      int tpi = ((nvec + GN_VPT - 1) / GN_VPT + unit - 1) / unit * unit;
+      tpi = std::max(tpi, unit);
+      if (tpi <= GN_MAX_THREADS) { g.slab = base; g.tpi = tpi; g.cs = cs; g.ok = true; break; }
+    }
+  }
   if (!g.ok) return g;
-  g.ipc = std::max(1, GN_MAX_THREADS / g.tpi);
+  g.ipc = g.cs > 1 ? 1 : std::max(1, GN_MAX_THREADS / g.tpi);
   g.threads = g.tpi * g.ipc;
   g.smem = sizeof(float) * ((size_t)g.threads * 16 + (size_t)g.ipc * GN_MAX_SLAB * 4);
   return g;
@@ -189,7 +222,7 @@ int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   }
   const GnGeom g = gn_geometry(op);
   GnFastArgs a{};
-  a.cpg = g.cpg; a.slab = g.slab; a.tpi = g.tpi; a.ipc = g.ipc;
+  a.cpg = g.cpg; a.slab = g.slab; a.tpi = g.tpi; a.ipc = g.ipc; a.cs = g.cs;
   a.src0 = (const bf16*)tensor_ptr(e, op.src0, B); a.C0 = e.tensors[op.src0].C;
   a.src1 = (const bf16*)tensor_ptr(e, op.src1, B); a.C1 = op.src1 >= 0 ? e.tensors[op.src1].C : 0;
   a.HW = op.Hin * op.Win;
@@ -197,6 +230,19 @@ int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   a.gamma = op.gamma; a.beta = op.beta; a.eps = 1e-5f; a.silu = op.silu;
   if (op.film) { a.film = e.emb_out + op.emb_off; a.film_stride = e.emb_total; a.film_row = e.row_of_sample; }
   a.out = (bf16*)tensor_ptr(e, op.out, B);
+  if (g.cs > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(a.n_items * g.cs));
+    cfg.blockDim = dim3(g.threads);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, groupnorm_bf16_kernel, a) != cudaSuccess) { e.err = "groupnorm cluster launch failed"; return CFM_ERR_CUDA; }
+    return 0;
+  }
   const int blocks = (a.n_items + g.ipc - 1) / g.ipc;
   groupnorm_bf16_kernel<<<blocks, g.threads, g.smem, st>>>(a);
   return 0;
