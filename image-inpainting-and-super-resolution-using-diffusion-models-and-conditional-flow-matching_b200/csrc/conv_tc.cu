@@ -54,6 +54,80 @@ struct TcParams {
   float* out_nchw; int cout_real;   // network head: fp32 NCHW output of the first cout_real channels
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// epilogue helpers (shared by the single-CTA and the CTA-pair kernel)
+// ------------------------------------------------------------------------------------------------
+struct EpiRow { bool valid; int n, h, w; long long pix; };
+
+__device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, int tb, int th, int tw, int row) {
+  EpiRow r;
+  const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
+  r.n = tb * p.bn + ni; r.h = th * p.bh + hi; r.w = tw * p.bw + wi;
+  r.valid = r.n < p.B;
+  r.pix = ((long long)r.n * p.H + r.h) * p.W + r.w;
+  return r;
+}
+// issue the residual loads of one (row, 32-channel chunk) early: they are the only DRAM-latency operand of the epilogue
+__device__ __forceinline__ void epi_load_res(const TcParams& p, const EpiRow& r, int cg, uint4 (&res)[4]) {
+  if (p.res0 && r.valid) {
+    const bf16* rp = (cg < p.R0) ? p.res0 + r.pix * p.R0 + cg : p.res1 + r.pix * p.R1 + (cg - p.R0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) res[j] = __ldg((const uint4*)(rp + 8 * j));
+  }
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// accumulator chunk (32 fp32 from TMEM) + bias + embedding vector + residual -> bf16 NHWC (or fp32 NCHW for the head)
+__device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], const uint4 (&res)[4],
+                                           uint32_t s_bias_addr) {
+  if (!r.valid) return;
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = lds_f4(s_bias_addr + (uint32_t)(cg + j) * 4u);
+    f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+  }
+  if (p.emb) {
+    const float* embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 e4 = __ldg((const float4*)(embp + cg + j));
+      f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
+    }
+  }
+  if (p.res0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
+    }
+  }
+  if (p.out_nchw) {
+    // head conv: channel-planar fp32; lanes are consecutive pixels -> coalesced per channel
+    const long long hw = (long long)p.H * p.W;
+    float* op = p.out_nchw + (long long)r.n * p.cout_real * hw + (long long)r.h * p.W + r.w;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (cg + j < p.cout_real) op[(long long)(cg + j) * hw] = f[j];
+  } else {
+    bf16* op = p.out + r.pix * p.Cout + cg;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 o4;
+      __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+      *(uint4*)(op + j) = o4;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
@@ -155,11 +229,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // warp%4 selects the TMEM lane quarter the hardware lets this warp read; the two warps sharing a
-    // quarter split the (M-half, 32-column chunk) work items between them.
+    // quarter split the (M-half, 32-column chunk) work items between them.  The residual operand of the
+    // first item is fetched BEFORE waiting for the accumulator, and that of item i+1 while item i is
+    // being finished, so no DRAM latency sits between "accumulator ready" and "accumulator released".
     const int quad = warp & 3;
     const int sub = (warp - 2) >> 2;           // 0 or 1
     const int chunks_per_half = p.block_n >> 5;
     const int n_items = chunks_per_half * p.mh;
+    const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
@@ -167,67 +244,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int tw = mt % p.tiles_w; mt /= p.tiles_w;
       const int th = mt % p.tiles_h;
       const int tb = mt / p.tiles_h;
-
+      EpiRow rows[2];
+      rows[0] = epi_decode_row(p, tb, th, tw, quad * 32 + lane);
+      rows[1] = p.mh == 2 ? epi_decode_row(p, tb, th, tw, 128 + quad * 32 + lane) : rows[0];
+      uint4 res_cur[4], res_nxt[4];
+      if (sub < n_items) {
+        const int half = sub / chunks_per_half;
+        epi_load_res(p, rows[half], nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
         const int half = item / chunks_per_half;
         const int c0 = (item - half * chunks_per_half) << 5;
-        const int row = half * 128 + quad * 32 + lane;
-        const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
-        const int n = tb * p.bn + ni, h = th * p.bh + hi, w = tw * p.bw + wi;
-        const bool valid = n < p.B;
-        const long long pix = ((long long)n * p.H + h) * p.W + w;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
-        tmem_ld_wait();
-        if (valid) {
-          const int cg = nt * p.block_n + c0;    // first output channel of this chunk
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *(const float4*)(s_bias + cg + j);
-            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-          }
-          if (p.emb) {
-            const float* embp = p.emb + (long long)p.emb_row[n] * p.emb_stride;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 e4 = __ldg((const float4*)(embp + cg + j));
-              f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
-            }
-          }
-          if (p.res0) {
-            const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cg : p.res1 + pix * p.R1 + (cg - p.R0);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 r4 = __ldg((const uint4*)(rp + j));
-              const __nv_bfloat162* rb = (const __nv_bfloat162*)&r4;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
-            }
-          }
-          if (p.out_nchw) {
-            // head conv: channel-planar fp32; lanes are consecutive pixels -> coalesced per channel
-            const long long hw = (long long)p.H * p.W;
-            float* op = p.out_nchw + (long long)n * p.cout_real * hw + (long long)h * p.W + w;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cg + j < p.cout_real) op[(long long)(cg + j) * hw] = f[j];
-          } else {
-            bf16* op = p.out + pix * p.Cout + cg;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o4;
-              __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-              *(uint4*)(op + j) = o4;
-            }
-          }
+        for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
+        const int nxt = item + TC_EPI_WARPS / 4;
+        if (nxt < n_items) {
+          const int nh = nxt / chunks_per_half;
+          epi_load_res(p, rows[nh], nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
+        tmem_ld_wait();
+        epi_finish(p, rows[half], nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();
@@ -359,6 +400,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int quad = warp & 3;
     const int sub = (warp - 2) >> 2;
     const int n_items = p.block_n >> 5;
+    const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const int nt = pt % p.tiles_n;
@@ -366,12 +408,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const int tw = mt % p.tiles_w; mt /= p.tiles_w;
       const int th = mt % p.tiles_h;
       const int tb = mt / p.tiles_h;
-      const int row = quad * 32 + lane;
-      const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
-      const int n = tb * p.bn + ni, h = th * p.bh + hi, w = tw * p.bw + wi;
-      const bool valid = n < p.B;
-      const long long pix = ((long long)n * p.H + h) * p.W + w;
-
+      const EpiRow row = epi_decode_row(p, tb, th, tw, quad * 32 + lane);
+      uint4 res_cur[4], res_nxt[4];
+      if (sub < n_items) epi_load_res(p, row, nt * p.block_n + (sub << 5), res_nxt);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
@@ -379,44 +418,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int c0 = item << 5;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
+        const int nxt = item + TC_EPI_WARPS / 4;
+        if (nxt < n_items) epi_load_res(p, row, nt * p.block_n + (nxt << 5), res_nxt);
         tmem_ld_wait();
-        if (valid) {
-          const int cg = nt * p.block_n + c0;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *(const float4*)(s_bias + cg + j);
-            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-          }
-          if (p.emb) {
-            const float* embp = p.emb + (long long)p.emb_row[n] * p.emb_stride;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 e4 = __ldg((const float4*)(embp + cg + j));
-              f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
-            }
-          }
-          if (p.res0) {
-            const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cg : p.res1 + pix * p.R1 + (cg - p.R0);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 r4 = __ldg((const uint4*)(rp + j));
-              const __nv_bfloat162* rb = (const __nv_bfloat162*)&r4;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
-            }
-          }
-          bf16* op = p.out + pix * p.Cout + cg;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o4;
-            __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-            *(uint4*)(op + j) = o4;
-          }
-        }
+        epi_finish(p, row, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();

@@ -174,7 +174,9 @@ static GnGeom gn_geometry(const Op& op) {
   g.cs = 1;
   const int base = g.cpg / gcd_i(g.cpg, 8) * 8;        // lcm(cpg, 8): smallest legal slab
   // widest slab (<= 64 channels, dividing C) whose item still fits GN_VPT vectors/thread in <= 256 threads
-  for (int sl = base; sl <= GN_MAX_SLAB && C % sl == 0; sl *= 2) {
+  static const int max_slab = [] { const char* v = getenv("CFM_GN_MAXSLAB"); return v ? atoi(v) : GN_MAX_SLAB; }();
+  static const int cta_threads = [] { const char* v = getenv("CFM_GN_CTA"); return v ? atoi(v) : GN_MAX_THREADS; }();
+  for (int sl = base; sl <= std::max(max_slab, base) && sl <= GN_MAX_SLAB && C % sl == 0; sl *= 2) {
     const int vpp = sl / 8;
     const int unit = 32 / gcd_i(32, vpp) * vpp;        // lcm(32, vpp): whole warps, multiple of vpp
     const int nvec = HW * vpp;
@@ -183,8 +185,12 @@ static GnGeom gn_geometry(const Op& op) {
     if (tpi > GN_MAX_THREADS) break;
     g.slab = sl; g.tpi = tpi; g.ok = true;
   }
-  if (!g.ok && base <= GN_MAX_SLAB && C % base == 0) {
+  static const bool wide = [] { const char* v = getenv("CFM_GN_WIDE"); return v && v[0] == '1'; }();
+  int wbase = base;
+  if (wide && g.ok && g.slab < 64 && C % 64 == 0 && 64 % g.cpg == 0 && HW >= 256) { g.ok = false; wbase = 64; }   // experiment: full 128 B lines per CTA
+  if (!g.ok && wbase <= GN_MAX_SLAB && C % wbase == 0) {
     // large feature map: split the item's pixels over a cluster of 2..8 CTAs (partials combined through DSMEM)
+    const int base = wbase;
     const int vpp = base / 8;
     const int unit = 32 / gcd_i(32, vpp) * vpp;
     for (int cs = 2; cs <= 8; cs *= 2) {
@@ -196,7 +202,7 @@ static GnGeom gn_geometry(const Op& op) {
     }
   }
   if (!g.ok) return g;
-  g.ipc = g.cs > 1 ? 1 : std::max(1, GN_MAX_THREADS / g.tpi);
+  g.ipc = g.cs > 1 ? 1 : std::max(1, cta_threads / g.tpi);
   g.threads = g.tpi * g.ipc;
   g.smem = sizeof(float) * ((size_t)g.threads * 16 + (size_t)g.ipc * GN_MAX_SLAB * 4);
   return g;
