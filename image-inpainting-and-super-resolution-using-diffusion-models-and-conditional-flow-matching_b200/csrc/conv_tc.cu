@@ -46,6 +46,7 @@ struct TcParams {
   int bw, bh, bn;              // tile box, bw*bh*bn == 128 * mh
   int mh;                      // M-halves per CTA tile (2: two UMMAs share one B tile)
   int tiles_w, tiles_h, tiles_b, tiles_n, n_tiles;
+  int n_phase;                 // 4: nearest-x2 upsample folded into the conv as four 2x2 sub-pixel convs (H, W = source size)
   int block_n, Cout;
   const float* bias;
   const float* emb; int emb_stride; const int* emb_row;
@@ -60,20 +61,85 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------
 struct EpiRow { bool valid; int n, h, w; long long pix; };
 
-__device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, int tb, int th, int tw, int row) {
+struct TileCoord { int nt, ph, tw, th, tb; };
+// tile index -> (N tile, sub-pixel phase, spatial tile).  N tile and phase vary fastest, so the CTAs that share an
+// A tile run at the same time and the tile is fetched from DRAM once.
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
+  TileCoord c;
+  c.nt = tile % p.tiles_n; tile /= p.tiles_n;
+  c.ph = tile % p.n_phase; tile /= p.n_phase;
+  c.tw = tile % p.tiles_w; tile /= p.tiles_w;
+  c.th = tile % p.tiles_h;
+  c.tb = tile / p.tiles_h;
+  return c;
+}
+// tap offset of K-iteration `tap` of a segment: plain ks x ks conv, or (ks == 2) phase `ph` of the sub-pixel
+// decomposition of "nearest x2 upsample, then 3x3 conv": output (2y+py, 2x+px) reads source rows y-1+py, y+py.
+__device__ __forceinline__ void tap_offset(int ks, int tap, int ph, int* dy, int* dx) {
+  if (ks == 2) { *dy = (tap >> 1) - 1 + (ph >> 1); *dx = (tap & 1) - 1 + (ph & 1); }
+  else { const int pad = ks >> 1; *dy = tap / ks - pad; *dx = tap % ks - pad; }
+}
+// CTA-pair kernel: a pair tile is two consecutive 128-row tiles; `rank` picks this CTA's half
+__device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& p, int pt, int rank) {
+  TileCoord c;
+  c.nt = pt % p.tiles_n; pt /= p.tiles_n;
+  c.ph = pt % p.n_phase; pt /= p.n_phase;
+  int mt = pt * 2 + rank;
+  c.tw = mt % p.tiles_w; mt /= p.tiles_w;
+  c.th = mt % p.tiles_h;
+  c.tb = mt / p.tiles_h;
+  return c;
+}
+__device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCoord& c, int row) {
   EpiRow r;
   const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
-  r.n = tb * p.bn + ni; r.h = th * p.bh + hi; r.w = tw * p.bw + wi;
+  r.n = c.tb * p.bn + ni; r.h = c.th * p.bh + hi; r.w = c.tw * p.bw + wi;
   r.valid = r.n < p.B;
-  r.pix = ((long long)r.n * p.H + r.h) * p.W + r.w;
+  if (p.n_phase == 4) {   // rows index the source grid; this phase's outputs interleave into the 2H x 2W map
+    r.h = 2 * r.h + (c.ph >> 1); r.w = 2 * r.w + (c.ph & 1);
+    r.pix = ((long long)r.n * (2 * p.H) + r.h) * (2 * p.W) + r.w;
+  } else {
+    r.pix = ((long long)r.n * p.H + r.h) * p.W + r.w;
+  }
   return r;
 }
-// issue the residual loads of one (row, 32-channel chunk) early: they are the only DRAM-latency operand of the epilogue
-__device__ __forceinline__ void epi_load_res(const TcParams& p, const EpiRow& r, int cg, uint4 (&res)[4]) {
-  if (p.res0 && r.valid) {
-    const bf16* rp = (cg < p.R0) ? p.res0 + r.pix * p.R0 + cg : p.res1 + r.pix * p.R1 + (cg - p.R0);
+// 4x4 transpose of 16-byte chunks inside each aligned group of 4 lanes: in  c[k] = chunk k of this lane's row,
+// out c[k] = chunk (lane & 3) of the row owned by lane (lane & ~3) + k.  An involution: the same call maps back.
+// It turns "one lane = one 64 B row segment" (32 half-sector accesses per instruction) into "4 lanes = one row
+// segment" (8 fully written 64 B runs per instruction) for the epilogue's global loads and stores.
+__device__ __forceinline__ void quad_transpose(uint4 (&c)[4], int lane) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) res[j] = __ldg((const uint4*)(rp + 8 * j));
+  for (int m = 1; m <= 2; m <<= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (a & m) continue;
+      const int b = a | m;
+      const uint4 send = up ? c[a] : c[b];
+      uint4 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, m); recv.y = __shfl_xor_sync(0xffffffffu, send.y, m);
+      recv.z = __shfl_xor_sync(0xffffffffu, send.z, m); recv.w = __shfl_xor_sync(0xffffffffu, send.w, m);
+      if (up) c[a] = recv; else c[b] = recv;
+    }
+  }
+}
+// pixel index of row (lane & ~3) + k of this lane's group: the 4 rows of a group are consecutive output pixels
+// (box width % 4 == 0), two apart in the interleaved map of a sub-pixel phase
+__device__ __forceinline__ long long epi_group_pix(const TcParams& p, const EpiRow& r, int lane, int k) {
+  const int step = p.n_phase == 4 ? 2 : 1;
+  return r.pix + (long long)((k - (lane & 3)) * step);
+}
+// issue the residual loads of one 32-channel chunk early (they are the only DRAM-latency operand of the epilogue),
+// in the transposed (coalesced) pattern: res[k] = 8 channels (lane & 3) of row (lane & ~3) + k
+__device__ __forceinline__ void epi_load_res(const TcParams& p, const EpiRow& r, int lane, int cg, uint4 (&res)[4]) {
+  if (p.res0 && r.valid) {
+    const int cj = cg + 8 * (lane & 3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long pix = epi_group_pix(p, r, lane, k);
+      const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cj : p.res1 + pix * p.R1 + (cj - p.R0);
+      res[k] = __ldg((const uint4*)rp);
+    }
   }
 }
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
@@ -81,10 +147,10 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
-// accumulator chunk (32 fp32 from TMEM) + bias + embedding vector + residual -> bf16 NHWC (or fp32 NCHW for the head)
-__device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], const uint4 (&res)[4],
+// accumulator chunk (32 fp32 from TMEM) + bias + embedding vector + residual -> bf16 NHWC (or fp32 NCHW for the head).
+// Called by all 32 lanes (it shuffles); `res` arrives in the transposed pattern of epi_load_res.
+__device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, int lane, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
                                            uint32_t s_bias_addr) {
-  if (!r.valid) return;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -92,7 +158,7 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
     f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
     f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
   }
-  if (p.emb) {
+  if (p.emb && r.valid) {
     const float* embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -100,7 +166,18 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
       f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
     }
   }
+  if (p.out_nchw) {
+    // head conv: channel-planar fp32; lanes are consecutive pixels -> coalesced per channel
+    if (!r.valid) return;
+    const long long hw = (long long)p.H * p.W;
+    float* op = p.out_nchw + (long long)r.n * p.cout_real * hw + (long long)r.h * p.W + r.w;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (cg + j < p.cout_real) op[(long long)(cg + j) * hw] = f[j];
+    return;
+  }
   if (p.res0) {
+    quad_transpose(res, lane);          // back to "this lane's row": single rounding of acc + bias + emb + residual
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
@@ -108,23 +185,18 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
       for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
     }
   }
-  if (p.out_nchw) {
-    // head conv: channel-planar fp32; lanes are consecutive pixels -> coalesced per channel
-    const long long hw = (long long)p.H * p.W;
-    float* op = p.out_nchw + (long long)r.n * p.cout_real * hw + (long long)r.h * p.W + r.w;
+  uint4 o[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (cg + j < p.cout_real) op[(long long)(cg + j) * hw] = f[j];
-  } else {
-    bf16* op = p.out + r.pix * p.Cout + cg;
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162* ob = (__nv_bfloat162*)&o[j];
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 o4;
-      __nv_bfloat162* ob = (__nv_bfloat162*)&o4;
+    for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+  }
+  quad_transpose(o, lane);
+  if (r.valid) {
+    const int cj = cg + 8 * (lane & 3);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-      *(uint4*)(op + j) = o4;
-    }
+    for (int k = 0; k < 4; ++k) *(uint4*)(p.out + epi_group_pix(p, r, lane, k) * p.Cout + cj) = o[k];
   }
 }
 
@@ -170,19 +242,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        int mt = tile / p.tiles_n;
-        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int tb = mt / p.tiles_h;
-        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tb * p.bn;
-        int kiter = 0;
+        const TileCoord tc = decode_tile(p, tile);
+        const int nt = tc.nt;
+        const int w0 = tc.tw * p.bw, h0 = tc.th * p.bh, n0 = tc.tb * p.bn;
+        int kiter = tc.ph * p.total_k;
         for (int s = 0; s < p.n_seg; ++s) {
           const TcSeg sg = p.seg[s];
           const CUtensorMap* map = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-          const int taps = sg.ks * sg.ks, pad = sg.ks >> 1;
+          const int taps = sg.ks * sg.ks;
           for (int tap = 0; tap < taps; ++tap) {
-            const int dy = tap / sg.ks - pad, dx = tap % sg.ks - pad;
+            int dy, dx; tap_offset(sg.ks, tap, tc.ph, &dy, &dx);
             for (int ch = 0; ch < sg.n_chunks; ++ch, ++kiter) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
@@ -239,18 +308,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n;
-      int mt = tile / p.tiles_n;
-      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int tb = mt / p.tiles_h;
+      const TileCoord tc = decode_tile(p, tile);
+      const int nt = tc.nt;
       EpiRow rows[2];
-      rows[0] = epi_decode_row(p, tb, th, tw, quad * 32 + lane);
-      rows[1] = p.mh == 2 ? epi_decode_row(p, tb, th, tw, 128 + quad * 32 + lane) : rows[0];
+      rows[0] = epi_decode_row(p, tc, quad * 32 + lane);
+      rows[1] = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : rows[0];
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
         const int half = sub / chunks_per_half;
-        epi_load_res(p, rows[half], nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
+        epi_load_res(p, rows[half], lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -265,14 +331,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int nxt = item + TC_EPI_WARPS / 4;
         if (nxt < n_items) {
           const int nh = nxt / chunks_per_half;
-          epi_load_res(p, rows[nh], nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
+          epi_load_res(p, rows[nh], lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
-        epi_finish(p, rows[half], nt * p.block_n + c0, v, res_cur, s_bias_addr);
+        epi_finish(p, rows[half], lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) mbar_arrive_relaxed(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -317,7 +383,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int pair_tiles = ((tiles128 + 1) >> 1) * p.tiles_n;
+  const int pair_tiles = ((tiles128 + 1) >> 1) * p.tiles_n * p.n_phase;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
@@ -340,19 +406,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
-        const int nt = pt % p.tiles_n;
-        int mt = (pt / p.tiles_n) * 2 + (int)rank;             // this CTA's 128-row tile
-        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int tb = mt / p.tiles_h;                         // may equal tiles_b for the odd tail: all-OOB loads
-        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tb * p.bn;
-        int kiter = 0;
+        const TileCoord tc = decode_pair_tile(p, pt, (int)rank);   // tb may equal tiles_b for the odd tail: all-OOB loads
+        const int nt = tc.nt;
+        const int w0 = tc.tw * p.bw, h0 = tc.th * p.bh, n0 = tc.tb * p.bn;
+        int kiter = tc.ph * p.total_k;
         for (int s = 0; s < p.n_seg; ++s) {
           const TcSeg sg = p.seg[s];
           const CUtensorMap* map = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-          const int taps = sg.ks * sg.ks, pad = sg.ks >> 1;
+          const int taps = sg.ks * sg.ks;
           for (int tap = 0; tap < taps; ++tap) {
-            const int dy = tap / sg.ks - pad, dx = tap % sg.ks - pad;
+            int dy, dx; tap_offset(sg.ks, tap, tc.ph, &dy, &dx);
             for (int ch = 0; ch < sg.n_chunks; ++ch, ++kiter) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);       // leader's full barrier
@@ -403,14 +466,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
-      const int nt = pt % p.tiles_n;
-      int mt = (pt / p.tiles_n) * 2 + (int)rank;
-      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int tb = mt / p.tiles_h;
-      const EpiRow row = epi_decode_row(p, tb, th, tw, quad * 32 + lane);
+      const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
+      const int nt = tc.nt;
+      const EpiRow row = epi_decode_row(p, tc, quad * 32 + lane);
       uint4 res_cur[4], res_nxt[4];
-      if (sub < n_items) epi_load_res(p, row, nt * p.block_n + (sub << 5), res_nxt);
+      if (sub < n_items) epi_load_res(p, row, lane, nt * p.block_n + (sub << 5), res_nxt);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
@@ -421,13 +481,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
         const int nxt = item + TC_EPI_WARPS / 4;
-        if (nxt < n_items) epi_load_res(p, row, nt * p.block_n + (nxt << 5), res_nxt);
+        if (nxt < n_items) epi_load_res(p, row, lane, nt * p.block_n + (nxt << 5), res_nxt);
         tmem_ld_wait();
-        epi_finish(p, row, nt * p.block_n + c0, v, res_cur, s_bias_addr);
+        epi_finish(p, row, lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // report to the leader
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // report to the leader
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -449,6 +509,7 @@ struct TcConvPlan {
   int seg_tensor[3] = {-1, -1, -1};
   int total_k = 0, block_n = 0;
   int bw = 0, bh = 0, bn = 0, mh = 1;
+  int n_phase = 1, Hg = 0, Wg = 0;   // sub-pixel phases (4 for the folded upsample) and the grid the M tiles walk
   bool pair = false;           // CTA-pair (cta_group::2) kernel
   int pbw = 0, pbh = 0, pbn = 0;   // 128-row box of the pair kernel
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
@@ -485,12 +546,13 @@ bool tc_conv_supported(const Engine& e, const Op& op) {
   if (!e.bf16 || op.kind != OP_CONV || op.src_is_input) return false;
   if (op.out_is_output && (op.Cout > 32 || env_off("CFM_DISABLE_TC_HEAD"))) return false;   // head: Cout padded to 32
   if (env_off("CFM_DISABLE_TC")) return false;
-  if (op.ups) return false;                                  // plan materialises the upsample in bf16 mode
+  if (op.ups && (op.ks != 3 || op.stride != 1 || op.skip0 >= 0 || op.res0 >= 0 || op.out_is_output || env_off("CFM_DISABLE_TC_UPS"))) return false;
   if (op.stride != 1 && op.stride != 2) return false;
   if (op.stride == 2 && env_off("CFM_DISABLE_TC_STRIDE2")) return false;
   if (op.ks != 1 && op.ks != 3) return false;
   if (!op.out_is_output && (pick_block_n(op.Cout) == 0 || op.Cout > TC_MAX_COUT)) return false;
-  if (!pow2(op.Hout) || !pow2(op.Wout) || op.Wout > 128 || op.Hout > 128) return false;
+  const int Hg = op.ups ? op.Hin : op.Hout, Wg = op.ups ? op.Win : op.Wout;      // grid the M tiles walk
+  if (!pow2(Hg) || !pow2(Wg) || Wg > 128 || Hg > 128 || Wg < 4) return false;   // epilogue groups 4 consecutive pixels of a row
   if (op.stride == 2 && (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout || 2 * std::min(op.Wout, 128) > 256)) return false;
   auto chan_ok = [&](int id) { return id < 0 || e.tensors[id].C % TC_BLOCK_K == 0; };
   if (op.src1 >= 0) return false;                            // main operand is always a single (GN-output) tensor
@@ -510,21 +572,47 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   // a 256-row tile (two UMMAs per B tile) restores the 2:1 ratio of the N = 256 case.
   pl->mh = (pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;
   const int rows = 128 * pl->mh;
-  pl->bw = std::min(op.Wout, rows);
-  pl->bh = std::min(op.Hout, rows / pl->bw);
+  // sub-pixel decomposition of (nearest x2 upsample -> 3x3 conv): the M tiles walk the SOURCE grid, four phases,
+  // each a 2x2 conv whose taps are sums of the 3x3 taps that land on the same source pixel (4/9 of the MACs,
+  // and the upsampled tensor is never materialised)
+  pl->n_phase = op.ups ? 4 : 1;
+  const int Hg = op.ups ? op.Hin : op.Hout, Wg = op.ups ? op.Win : op.Wout;
+  pl->Hg = Hg; pl->Wg = Wg;
+  pl->bw = std::min(Wg, rows);
+  pl->bh = std::min(Hg, rows / pl->bw);
   pl->bn = rows / (pl->bw * pl->bh);
   pl->pair = !op.out_is_output && pl->block_n >= 192 && !env_off("CFM_DISABLE_TC_2CTA");   // N = 128 tiles are A-traffic bound: 256-row single-CTA tiles win there
-  pl->pbw = std::min(op.Wout, 128);
-  pl->pbh = std::min(op.Hout, 128 / pl->pbw);
+  pl->pbw = std::min(Wg, 128);
+  pl->pbh = std::min(Hg, 128 / pl->pbw);
   pl->pbn = 128 / (pl->pbw * pl->pbh);
-  pl->seg[0] = {0, Cin / TC_BLOCK_K, ks, op.stride}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
+  const int eks = op.ups ? 2 : ks;          // taps per axis the kernel walks
+  pl->seg[0] = {0, Cin / TC_BLOCK_K, eks, op.stride}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
   if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
   if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
-  pl->total_k = ks * ks * (Cin / TC_BLOCK_K) + op.Cskip / TC_BLOCK_K;
-  // pack: kiter-major, [Cout][64] per kiter, same iteration order as the producer warp
-  std::vector<bf16> packed((size_t)pl->total_k * Cout * TC_BLOCK_K);
+  pl->total_k = eks * eks * (Cin / TC_BLOCK_K) + op.Cskip / TC_BLOCK_K;
+  // pack: [phase] kiter-major, [Cout][64] per kiter, same iteration order as the producer warp
+  std::vector<bf16> packed((size_t)pl->n_phase * pl->total_k * Cout * TC_BLOCK_K);
   size_t kiter = 0;
-  for (int tap = 0; tap < ks * ks; ++tap)
+  if (op.ups) {
+    // phase (py, px), tap (a, b): source offset (a - 1 + py, b - 1 + px); the 3x3 taps folding onto it are
+    // ky in {0} | {1,2} for py = 0 and {0,1} | {2} for py = 1 (same along x); summed in fp32, rounded once
+    auto lo = [](int p, int a) { return p == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2); };
+    auto hi = [](int p, int a) { return p == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2); };
+    for (int ph = 0; ph < 4; ++ph)
+      for (int tap = 0; tap < 4; ++tap) {
+        const int py = ph >> 1, px = ph & 1, a = tap >> 1, b = tap & 1;
+        for (int ch = 0; ch < Cin / TC_BLOCK_K; ++ch, ++kiter)
+          for (int o = 0; o < Cout; ++o)
+            for (int j = 0; j < TC_BLOCK_K; ++j) {
+              float acc = 0.f;
+              for (int ky = lo(py, a); ky <= hi(py, a); ++ky)
+                for (int kx = lo(px, b); kx <= hi(px, b); ++kx)
+                  acc += w[((size_t)o * Cin + ch * TC_BLOCK_K + j) * 9 + ky * 3 + kx];
+              packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(acc);
+            }
+      }
+  }
+  for (int tap = 0; !op.ups && tap < ks * ks; ++tap)
     for (int ch = 0; ch < Cin / TC_BLOCK_K; ++ch, ++kiter)
       for (int o = 0; o < Cout; ++o)
         for (int j = 0; j < TC_BLOCK_K; ++j)
@@ -590,7 +678,7 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
       if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A pair) failed for " + op.name; return CFM_ERR_CUDA; }
     }
     for (int s = pl->n_seg; s < 3; ++s) m->a2[s] = m->a2[0];
-    cuuint64_t dims2[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->total_k * pl->cout_pad};
+    cuuint64_t dims2[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->n_phase * pl->total_k * pl->cout_pad};
     cuuint64_t strides2[1] = {(cuuint64_t)TC_BLOCK_K * 2};
     cuuint32_t box2[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->block_n / 2)};
     cuuint32_t estr2[2] = {1, 1};
@@ -599,7 +687,7 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r2 != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(B pair) failed for " + op.name; return CFM_ERR_CUDA; }
   }
-  cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->total_k * pl->cout_pad};
+  cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->n_phase * pl->total_k * pl->cout_pad};
   cuuint64_t strides[1] = {(cuuint64_t)TC_BLOCK_K * 2};
   cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)pl->block_n};
   cuuint32_t estr[2] = {1, 1};
@@ -623,11 +711,11 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.n_seg = pl->n_seg;
   for (int s = 0; s < 3; ++s) p.seg[s] = pl->seg[s];
   p.total_k = pl->total_k;
-  p.B = B; p.H = op.Hout; p.W = op.Wout;
+  p.B = B; p.H = pl->Hg; p.W = pl->Wg; p.n_phase = pl->n_phase;
   p.bw = pl->bw; p.bh = pl->bh; p.bn = pl->bn; p.mh = pl->mh;
-  p.tiles_w = op.Wout / pl->bw; p.tiles_h = op.Hout / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
+  p.tiles_w = pl->Wg / pl->bw; p.tiles_h = pl->Hg / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
   p.tiles_n = pl->cout_pad / pl->block_n;
-  p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+  p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n * p.n_phase;
   p.block_n = pl->block_n; p.Cout = pl->cout_pad;
   p.bias = pl->bias_pad ? pl->bias_pad : op.bias;
   if (op.emb_off >= 0) { p.emb = e.emb_out + op.emb_off; p.emb_stride = e.emb_total; p.emb_row = e.row_of_sample; }
@@ -637,9 +725,9 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   if (op.out_is_output) { p.out_nchw = out_nchw; p.cout_real = op.Cout; }
   if (pl->pair) {
     p.bw = pl->pbw; p.bh = pl->pbh; p.bn = pl->pbn; p.mh = 1;
-    p.tiles_w = op.Wout / p.bw; p.tiles_h = op.Hout / p.bh; p.tiles_b = (B + p.bn - 1) / p.bn;
+    p.tiles_w = pl->Wg / p.bw; p.tiles_h = pl->Hg / p.bh; p.tiles_b = (B + p.bn - 1) / p.bn;
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
-    const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n;
+    const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
     const int stage_bytes = TC_A_BYTES + (pl->block_n / 2) * TC_BLOCK_K * 2;
     const int n_stages = std::min(TC2_MAX_STAGES, TC2_RING_BYTES / stage_bytes);
     cudaLaunchConfig_t cfg{};

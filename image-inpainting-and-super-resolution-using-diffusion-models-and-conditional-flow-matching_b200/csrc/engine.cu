@@ -310,8 +310,10 @@ static int build_plan(Engine& e) {
           if ((rc = add_resblock(e, pu, h, Cur{-1, 0, 0, 0}, h.C, true, false, emb_pieces, &h))) return rc;
         } else if (c.conv_resample) {
           const int t = new_tensor(e, h.C, h.H * 2, h.W * 2);
-          if (e.bf16) {
-            // tensor-core path: materialise the nearest-neighbour upsample once, then a plain 3x3 conv
+          Op probe; probe.kind = OP_CONV; probe.ks = 3; probe.stride = 1; probe.ups = 1; probe.src0 = h.id; probe.Cin = probe.Cout = h.C;
+          probe.Hin = h.H; probe.Win = h.W; probe.Hout = 2 * h.H; probe.Wout = 2 * h.W;
+          if (e.bf16 && !tc_conv_supported(e, probe)) {
+            // bf16 shapes the tensor-core kernel cannot fold: materialise the nearest-neighbour upsample, then a plain 3x3 conv
             const int u = new_tensor(e, h.C, h.H * 2, h.W * 2);
             add_resample(e, pu + ".interpolate", h.id, u, 1);
             if ((rc = add_conv(e, pu + ".conv", pu + ".conv", 3, 1, 0, u, -1, false, h.C, h.H * 2, h.W * 2, h.C, "", -1, -1, 0, -1, -1, -1, t, false))) return rc;
