@@ -10,76 +10,86 @@ namespace cfm {
 void* tensor_ptr(const Engine& e, int id, int B);
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm32 over NHWC bf16, register-resident.
+// GroupNorm32 over NHWC bf16, staged through shared memory.
 // An "item" is one (sample, channel slab); a slab is a whole number of groups and of 8-channel
-// 16-byte vectors (>= 64 B per pixel: 32 or 48 channels).  TPI threads own an item: each thread
-// loads up to GN_VPT vectors straight into registers (all loads in flight at once - the kernel is
-// HBM-bound, so bytes in flight are what matters), statistics are reduced deterministically
-// through shared memory (no atomics -> bit-reproducible), and the normalised / FiLM-modulated /
-// SiLU-activated values are stored from the same registers: one global read, one global write.
-// Small feature maps pack several items into one CTA.
+// 16-byte vectors.  One CTA (or a cluster of `cs` CTAs that split the item's pixels) owns an item:
+//   1. every thread copies its vectors global -> shared with cp.async (no register staging, so a
+//      CTA costs ~40 registers/thread and several CTAs per SM keep their loads in flight while others
+//      reduce or store - the kernel is HBM-bound and bytes in flight are what matters);
+//   2. each thread reduces the vectors it copied itself (no barrier needed to read them back); the
+//      per-channel sums are combined in a fixed order - shuffles + one smem pass, DSMEM across the
+//      cluster - so the result is bit-reproducible (no atomics);
+//   3. the same vectors are read back from shared memory, normalised / FiLM-modulated / SiLU-activated
+//      and stored with 16-byte coalesced stores: one global read, one global write.
 // ------------------------------------------------------------------------------------------------
 struct GnFastArgs {
   const bf16* src0; const bf16* src1; int C0, C1;
   int HW, cpg, slab;                 // slab channels per item (multiple of 8 and of cpg)
-  int tpi, ipc, n_items;             // threads per item, items per CTA, total items
+  int n_items;
   int cs;                            // CTAs (of one cluster) sharing an item's pixels; 1 = no cluster
+  int shfl;                          // 1: vectors-per-pixel is a power of two <= 32 -> warp-shuffle pre-reduction
+  int data_bytes;                    // staged bytes per CTA
   const float* gamma; const float* beta; float eps; int silu;
   const float* film; int film_stride; const int* film_row;
   bf16* out;
 };
 
-constexpr int GN_VPT = 16;
-constexpr int GN_MAX_SLAB = 64;
+constexpr int GN_MAX_SLAB = 128;
 constexpr int GN_MAX_THREADS = 256;
 
-__global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFastArgs a) {
-  extern __shared__ float gn_smem[];
-  // layout: part_sum[threads][8] | part_sq[threads][8] | ch_scale[ipc][64] | ch_shift[ipc][64] | ch_sum[ipc][64] | ch_sq[ipc][64]
-  float* part_sum = gn_smem;
-  float* part_sq = part_sum + blockDim.x * 8;
-  float* ch_scale = part_sq + blockDim.x * 8;
-  float* ch_shift = ch_scale + a.ipc * GN_MAX_SLAB;
-  float* ch_sum = ch_shift + a.ipc * GN_MAX_SLAB;
-  float* ch_sq = ch_sum + a.ipc * GN_MAX_SLAB;
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
+__global__ void __launch_bounds__(GN_MAX_THREADS) groupnorm_bf16_kernel(GnFastArgs a) {
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  // layout: data[data_bytes] | red[rows][17] | ch_sum[64] | ch_sq[64] | ch_scale[64] | ch_shift[64]
+  const int T = blockDim.x;
+  const int vpp = a.slab >> 3;
+  const int n_warps = T >> 5;
+  const int red_rows = a.shfl ? n_warps * vpp : T;
+  float* red = (float*)(gn_smem + a.data_bytes);      // rows of 16 partials, stride 17 (bank-conflict-free per-thread rows)
+  float* ch_sum = red + red_rows * 17;
+  float* ch_sq = ch_sum + GN_MAX_SLAB;
+  float* ch_scale = ch_sq + GN_MAX_SLAB;
+  float* ch_shift = ch_scale + GN_MAX_SLAB;
 
   const int C = a.C0 + a.C1;
   const int slabs = C / a.slab;
-  const int vpp = a.slab / 8;
-  const int nvec = a.HW * vpp;
-  const int il = threadIdx.x / a.tpi;                    // item within the CTA
-  const int ti = threadIdx.x - il * a.tpi;               // thread within the item
-  // cs > 1: the CTAs of a cluster split one item's pixels (large feature maps); then ipc == 1
+  const int t = threadIdx.x;
   const int crank = a.cs > 1 ? (int)cluster_ctarank() : 0;
-  const int item = a.cs > 1 ? (int)(blockIdx.x / a.cs) : blockIdx.x * a.ipc + il;
+  const int item = (int)(blockIdx.x / a.cs);
   const int HWl = a.HW / a.cs;                           // pixels owned by this CTA
-  const int pbase = crank * HWl;
-  const bool active = item < a.n_items;
-  const int b = active ? item / slabs : 0, sl = active ? item % slabs : 0;
+  const int b = item / slabs, sl = item - b * slabs;
   const int c_base = sl * a.slab;
-  const int q = ti % vpp;                                // tpi % vpp == 0 -> fixed vector slot per thread
+  const int q = t % vpp;                                 // T % vpp == 0 -> fixed vector slot (8 channels) per thread
   const int cq = c_base + q * 8;
   const bf16* sp; int sC, sc;
   if (cq < a.C0) { sp = a.src0; sC = a.C0; sc = cq; } else { sp = a.src1; sC = a.C1; sc = cq - a.C0; }
-  const long long pix0 = (long long)b * a.HW + pbase;
-  const int p0 = ti / vpp, pstep = a.tpi / vpp;          // this thread's pixels: p0 + k*pstep (within the CTA's range)
+  const long long pix0 = (long long)b * a.HW + (long long)crank * HWl;
+  const int p0 = t / vpp, pstep = T / vpp;               // this thread's pixels: p0 + k * pstep
+  const int nvec = HWl * vpp;
+  const uint32_t data_addr = smem_u32(gn_smem);
 
-  uint4 regs[GN_VPT];
   {
     const bf16* lp = sp + (pix0 + p0) * sC + sc;
     const long long lstep = (long long)pstep * sC;
-#pragma unroll
-    for (int k = 0; k < GN_VPT; ++k) {
-      regs[k] = (active && p0 + k * pstep < HWl) ? __ldg((const uint4*)lp) : make_uint4(0, 0, 0, 0);
-      lp += lstep;
-    }
+    for (int v = t; v < nvec; v += T, lp += lstep) cp_async16(data_addr + (uint32_t)v * 16u, lp);
   }
+  cp_async_wait_all();
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
-#pragma unroll
-  for (int k = 0; k < GN_VPT; ++k) {
-    const __nv_bfloat162* h2 = (const __nv_bfloat162*)&regs[k];
+#pragma unroll 4
+  for (int v = t; v < nvec; v += T) {
+    const uint4 r = lds_u4(data_addr + (uint32_t)v * 16u);
+    const __nv_bfloat162* h2 = (const __nv_bfloat162*)&r;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __bfloat1622float2(h2[j]);
@@ -87,124 +97,122 @@ __global__ void __launch_bounds__(GN_MAX_THREADS, 2) groupnorm_bf16_kernel(GnFas
       s[2 * j + 1] += f.y; ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
     }
   }
-  // keep only the packed bf16 words live across the reduction (stops the compiler from parking 128 unpacked floats)
+  if (a.shfl) {
+    // lanes that share a vector slot are vpp apart: butterfly over the lane bits above log2(vpp)
+    for (int m = vpp; m < 32; m <<= 1) {
 #pragma unroll
-  for (int k = 0; k < GN_VPT; ++k) asm volatile("" : "+r"(regs[k].x), "+r"(regs[k].y), "+r"(regs[k].z), "+r"(regs[k].w));
+      for (int j = 0; j < 8; ++j) { s[j] += __shfl_xor_sync(0xffffffffu, s[j], m); ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], m); }
+    }
+    const int lane = t & 31, w = t >> 5;
+    if (lane < vpp) {
+      float* rp = red + (w * vpp + lane) * 17;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { part_sum[threadIdx.x * 8 + j] = s[j]; part_sq[threadIdx.x * 8 + j] = ss[j]; }
+      for (int j = 0; j < 8; ++j) { rp[j] = s[j]; rp[8 + j] = ss[j]; }
+    }
+  } else {
+    float* rp = red + t * 17;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { rp[j] = s[j]; rp[8 + j] = ss[j]; }
+  }
   __syncthreads();
-  // one thread per (item, channel): fixed-order sum over the item's threads that share the vector slot
-  for (int w = threadIdx.x; w < a.ipc * a.slab; w += blockDim.x) {
-    const int wi = w / a.slab, c = w - wi * a.slab;
+  for (int c = t; c < a.slab; c += T) {
+    // fixed-order sum of the partials that belong to channel c of the slab
     const int qq = c >> 3, j = c & 7;
     float ts = 0.f, tq = 0.f;
-    for (int t = wi * a.tpi + qq; t < (wi + 1) * a.tpi; t += vpp) { ts += part_sum[t * 8 + j]; tq += part_sq[t * 8 + j]; }
-    ch_sum[wi * GN_MAX_SLAB + c] = ts; ch_sq[wi * GN_MAX_SLAB + c] = tq;
+    if (a.shfl) { for (int w = 0; w < n_warps; ++w) { const float* rp = red + (w * vpp + qq) * 17; ts += rp[j]; tq += rp[8 + j]; } }
+    else { for (int u = qq; u < T; u += vpp) { ts += red[u * 17 + j]; tq += red[u * 17 + 8 + j]; } }
+    ch_sum[c] = ts; ch_sq[c] = tq;
   }
   __syncthreads();
   if (a.cs > 1) {
     // combine the per-CTA channel sums across the cluster through distributed shared memory, in rank order
+    // (cluster CTAs always have >= 64 threads: one channel per thread)
     cluster_sync_all();
     float ts = 0.f, tq = 0.f;
-    if (threadIdx.x < a.slab) {
+    if (t < a.slab) {
       for (int r = 0; r < a.cs; ++r) {
-        ts += ld_dsmem_f32(mapa_u32(smem_u32(&ch_sum[threadIdx.x]), r));
-        tq += ld_dsmem_f32(mapa_u32(smem_u32(&ch_sq[threadIdx.x]), r));
+        ts += ld_dsmem_f32(mapa_u32(smem_u32(&ch_sum[t]), r));
+        tq += ld_dsmem_f32(mapa_u32(smem_u32(&ch_sq[t]), r));
       }
     }
     cluster_sync_all();              // everyone has read the partials before they are overwritten
-    if (threadIdx.x < a.slab) { ch_sum[threadIdx.x] = ts; ch_sq[threadIdx.x] = tq; }
+    if (t < a.slab) { ch_sum[t] = ts; ch_sq[t] = tq; }
     __syncthreads();
   }
-  for (int w = threadIdx.x; w < a.ipc * a.slab; w += blockDim.x) {
-    const int wi = w / a.slab, c = w - wi * a.slab;
-    const int it = a.cs > 1 ? (int)(blockIdx.x / a.cs) : blockIdx.x * a.ipc + wi;
-    if (it >= a.n_items) continue;
-    const int bb = it / slabs, cb = (it % slabs) * a.slab;
+  for (int c = t; c < a.slab; c += T) {
     const int g0 = (c / a.cpg) * a.cpg;
     float gs = 0.f, gq = 0.f;
-    for (int j = 0; j < a.cpg; ++j) { gs += ch_sum[wi * GN_MAX_SLAB + g0 + j]; gq += ch_sq[wi * GN_MAX_SLAB + g0 + j]; }
+    for (int j = 0; j < a.cpg; ++j) { gs += ch_sum[g0 + j]; gq += ch_sq[g0 + j]; }
     const float inv_n = 1.0f / (float)(a.cpg * a.HW);
     const float mean = gs * inv_n;
     const float var = fmaxf(gq * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + a.eps);
-    float sc_ = rstd * a.gamma[cb + c];
-    float sh_ = a.beta[cb + c] - mean * sc_;
+    float sc_ = rstd * a.gamma[c_base + c];
+    float sh_ = a.beta[c_base + c] - mean * sc_;
     if (a.film) {
-      const float* f = a.film + (long long)a.film_row[bb] * a.film_stride;
-      const float m = 1.0f + f[cb + c];
-      sc_ *= m; sh_ = sh_ * m + f[C + cb + c];
+      const float* f = a.film + (long long)a.film_row[b] * a.film_stride;
+      const float m = 1.0f + f[c_base + c];
+      sc_ *= m; sh_ = sh_ * m + f[C + c_base + c];
     }
     if (a.silu) { sc_ *= 0.5f; sh_ *= 0.5f; }          // the activation works on h = y/2: silu(y) = h*tanh(h) + h
-    ch_scale[wi * GN_MAX_SLAB + c] = sc_; ch_shift[wi * GN_MAX_SLAB + c] = sh_;
+    ch_scale[c] = sc_; ch_shift[c] = sh_;
   }
   __syncthreads();
-  if (!active) return;
   float sc8[8], sh8[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc8[j] = ch_scale[il * GN_MAX_SLAB + q * 8 + j]; sh8[j] = ch_shift[il * GN_MAX_SLAB + q * 8 + j]; }
+  for (int j = 0; j < 8; ++j) { sc8[j] = ch_scale[q * 8 + j]; sh8[j] = ch_shift[q * 8 + j]; }
   bf16* op = a.out + (pix0 + p0) * C + cq;
   const long long ostep = (long long)pstep * C;
+#pragma unroll 4
+  for (int v = t; v < nvec; v += T, op += ostep) {
+    const uint4 r = lds_u4(data_addr + (uint32_t)v * 16u);
+    const __nv_bfloat162* h2 = (const __nv_bfloat162*)&r;
+    uint4 o4;
+    __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
 #pragma unroll
-  for (int k = 0; k < GN_VPT; ++k, op += ostep) {
-    if (p0 + k * pstep < HWl) {
-      const __nv_bfloat162* h2 = (const __nv_bfloat162*)&regs[k];
-      uint4 o4;
-      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h2[j]);
-        float y0 = fmaf(f.x, sc8[2 * j], sh8[2 * j]), y1 = fmaf(f.y, sc8[2 * j + 1], sh8[2 * j + 1]);
-        if (a.silu) { y0 = silu_from_half(y0); y1 = silu_from_half(y1); }
-        o2[j] = __floats2bfloat162_rn(y0, y1);
-      }
-      *(uint4*)op = o4;
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h2[j]);
+      float y0 = fmaf(f.x, sc8[2 * j], sh8[2 * j]), y1 = fmaf(f.y, sc8[2 * j + 1], sh8[2 * j + 1]);
+      if (a.silu) { y0 = silu_from_half(y0); y1 = silu_from_half(y1); }
+      o2[j] = __floats2bfloat162_rn(y0, y1);
     }
+    *(uint4*)op = o4;
   }
 }
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-struct GnGeom { int cpg, slab, tpi, ipc, threads, cs; size_t smem; bool ok; };
+struct GnGeom { int cpg, slab, threads, cs, shfl, data_bytes; size_t smem; bool ok; };
 
 static GnGeom gn_geometry(const Op& op) {
   GnGeom g{};
   const int C = op.Cin, HW = op.Hin * op.Win;
   g.cpg = C / 32;
-  g.cs = 1;
   const int base = g.cpg / gcd_i(g.cpg, 8) * 8;        // lcm(cpg, 8): smallest legal slab
-  // widest slab (<= 64 channels, dividing C) whose item still fits GN_VPT vectors/thread in <= 256 threads
-  static const int max_slab = [] { const char* v = getenv("CFM_GN_MAXSLAB"); return v ? atoi(v) : GN_MAX_SLAB; }();
-  static const int cta_threads = [] { const char* v = getenv("CFM_GN_CTA"); return v ? atoi(v) : GN_MAX_THREADS; }();
-  for (int sl = base; sl <= std::max(max_slab, base) && sl <= GN_MAX_SLAB && C % sl == 0; sl *= 2) {
-    const int vpp = sl / 8;
-    const int unit = 32 / gcd_i(32, vpp) * vpp;        // lcm(32, vpp): whole warps, multiple of vpp
-    const int nvec = HW * vpp;
-    int tpi = ((nvec + GN_VPT - 1) / GN_VPT + unit - 1) / unit * unit;
-    tpi = std::max(tpi, unit);
-    if (tpi > GN_MAX_THREADS) break;
-    g.slab = sl; g.tpi = tpi; g.ok = true;
-  }
-  static const bool wide = [] { const char* v = getenv("CFM_GN_WIDE"); return v && v[0] == '1'; }();
-  int wbase = base;
-  if (wide && g.ok && g.slab < 64 && C % 64 == 0 && 64 % g.cpg == 0 && HW >= 256) { g.ok = false; wbase = 64; }   // experiment: full 128 B lines per CTA
-  if (!g.ok && wbase <= GN_MAX_SLAB && C % wbase == 0) {
-    // large feature map: split the item's pixels over a cluster of 2..8 CTAs (partials combined through DSMEM)
-    const int base = wbase;
-    const int vpp = base / 8;
-    const int unit = 32 / gcd_i(32, vpp) * vpp;
-    for (int cs = 2; cs <= 8; cs *= 2) {
-      if (HW % cs) break;
-      const int nvec = (HW / cs) * vpp;
-      int tpi = ((nvec + GN_VPT - 1) / GN_VPT + unit - 1) / unit * unit;
-      tpi = std::max(tpi, unit);
-      if (tpi <= GN_MAX_THREADS) { g.slab = base; g.tpi = tpi; g.cs = cs; g.ok = true; break; }
-    }
-  }
-  if (!g.ok) return g;
-  g.ipc = g.cs > 1 ? 1 : std::max(1, cta_threads / g.tpi);
-  g.threads = g.tpi * g.ipc;
-  g.smem = sizeof(float) * ((size_t)g.threads * 16 + (size_t)g.ipc * GN_MAX_SLAB * 4);
+  if (base > GN_MAX_SLAB || C % base) return g;
+  static const int target = [] { const char* v = getenv("CFM_GN_ITEM_BYTES"); return v ? atoi(v) : 64 * 1024; }();
+  // slab: a multiple of `base` dividing C, preferably a whole number of 64-byte DRAM bursts per pixel (32 channels;
+  // e.g. 96 for C = 384, where 48-channel slabs would straddle bursts) and at most 64 channels when that works
+  int slab = 0;
+  for (int sl = base; sl <= GN_MAX_SLAB; sl += base)
+    if (C % sl == 0 && sl % 32 == 0) { if (slab == 0 || sl <= 64) slab = sl; }
+  if (slab == 0) { slab = base; while (slab * 2 <= 64 && C % (slab * 2) == 0) slab *= 2; }
+  // bring the per-CTA bytes to the target: split the pixels over a cluster first, then narrow the slab (>= 64 B per pixel)
+  int cs = 1;
+  while ((long long)HW * slab * 2 / cs > target && cs < 8 && HW % (cs * 2) == 0 && HW / (cs * 2) >= 8) cs *= 2;
+  while ((long long)HW * slab * 2 / cs > target && slab % 64 == 0 && (slab / 2) % base == 0) slab /= 2;
+  const long long bytes = (long long)HW * slab * 2 / cs;
+  if (bytes > 160 * 1024) return g;
+  const int vpp = slab / 8;
+  const int unit = 32 / gcd_i(32, vpp) * vpp;          // lcm(32, vpp): whole warps, multiple of vpp
+  const int nvec = (int)(bytes / 16);
+  int threads = ((nvec + 7) / 8 + unit - 1) / unit * unit;   // ~8 vectors per thread
+  threads = std::min(std::max(threads, cs > 1 ? std::max(unit, (GN_MAX_SLAB + unit - 1) / unit * unit) : unit), GN_MAX_THREADS / unit * unit);
+  g.slab = slab; g.cs = cs; g.threads = threads; g.data_bytes = (int)bytes;
+  g.shfl = (vpp & (vpp - 1)) == 0 && vpp <= 32;
+  const int red_rows = g.shfl ? (threads / 32) * vpp : threads;
+  g.smem = (size_t)bytes + sizeof(float) * ((size_t)red_rows * 17 + 4 * GN_MAX_SLAB);
+  g.ok = true;
   return g;
 }
 
@@ -213,7 +221,7 @@ bool gn_bf16_supported(const Engine& e, const Op& op) {
   const char* off = getenv("CFM_DISABLE_FAST_GN");
   if (off && off[0] == '1') return false;
   const GnGeom g = gn_geometry(op);
-  if (!g.ok || g.smem > 96 * 1024) return false;
+  if (!g.ok || g.smem > 200 * 1024) return false;
   if (e.tensors[op.src0].C % 8) return false;
   return true;
 }
@@ -221,14 +229,14 @@ bool gn_bf16_supported(const Engine& e, const Op& op) {
 int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(groupnorm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(groupnorm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(groupnorm_bf16_kernel) failed"; return CFM_ERR_CUDA;
     }
     attr = true;
   }
   const GnGeom g = gn_geometry(op);
   GnFastArgs a{};
-  a.cpg = g.cpg; a.slab = g.slab; a.tpi = g.tpi; a.ipc = g.ipc; a.cs = g.cs;
+  a.cpg = g.cpg; a.slab = g.slab; a.cs = g.cs; a.shfl = g.shfl; a.data_bytes = g.data_bytes;
   a.src0 = (const bf16*)tensor_ptr(e, op.src0, B); a.C0 = e.tensors[op.src0].C;
   a.src1 = (const bf16*)tensor_ptr(e, op.src1, B); a.C1 = op.src1 >= 0 ? e.tensors[op.src1].C : 0;
   a.HW = op.Hin * op.Win;
@@ -236,21 +244,16 @@ int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   a.gamma = op.gamma; a.beta = op.beta; a.eps = 1e-5f; a.silu = op.silu;
   if (op.film) { a.film = e.emb_out + op.emb_off; a.film_stride = e.emb_total; a.film_row = e.row_of_sample; }
   a.out = (bf16*)tensor_ptr(e, op.out, B);
-  if (g.cs > 1) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(a.n_items * g.cs));
-    cfg.blockDim = dim3(g.threads);
-    cfg.dynamicSmemBytes = g.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = g.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, groupnorm_bf16_kernel, a) != cudaSuccess) { e.err = "groupnorm cluster launch failed"; return CFM_ERR_CUDA; }
-    return 0;
-  }
-  const int blocks = (a.n_items + g.ipc - 1) / g.ipc;
-  groupnorm_bf16_kernel<<<blocks, g.threads, g.smem, st>>>(a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(a.n_items * g.cs));
+  cfg.blockDim = dim3(g.threads);
+  cfg.dynamicSmemBytes = g.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = g.cs; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
+  cfg.attrs = lattr; cfg.numAttrs = g.cs > 1 ? 1 : 0;
+  if (cudaLaunchKernelEx(&cfg, groupnorm_bf16_kernel, a) != cudaSuccess) { e.err = "groupnorm launch failed"; return CFM_ERR_CUDA; }
   return 0;
 }
 
@@ -436,43 +439,70 @@ int stem_conv_launch(Engine& e, const Op& op, int B, const float* x, const float
 //   rest              0
 // so the 3x3 stem conv becomes a K_pad-deep 1x1 GEMM on the tensor cores (weights duplicated for hi/lo).
 // ------------------------------------------------------------------------------------------------
-__global__ void stem_im2col_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0, int C1,
-                                   bf16* __restrict__ out, int B, int H, int W, int Kpad) {
+// One CTA per strip of IM2COL_ROWS image rows: the (rows + 2) x (W + 2) x Cin input patch is staged in shared
+// memory with coalesced NCHW reads (zero halo), then every thread assembles 16-byte vectors of 8 consecutive K
+// values - consecutive threads write consecutive vectors, so the [B,H,W,K_pad] tensor (what bounds this kernel)
+// is written in full 128-byte lines.
+constexpr int IM2COL_ROWS = 4;
+
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0, int C1,
+                                                          bf16* __restrict__ out, int B, int H, int W, int Kpad) {
+  extern __shared__ float im_smem[];     // patch[Cin][rows + 2][W + 2] | koff[Kpad] (int)
   const int Cin = C0 + C1, K9 = 9 * Cin;
+  const int strips = (H + IM2COL_ROWS - 1) / IM2COL_ROWS;
+  const int b = blockIdx.x / strips, y0 = (blockIdx.x % strips) * IM2COL_ROWS;
+  const int rows = min(IM2COL_ROWS, H - y0);
+  const int PW = W + 2, PH = IM2COL_ROWS + 2;
+  float* patch = im_smem;
+  int* koff = (int*)(im_smem + Cin * PH * PW);
+  for (int i = threadIdx.x; i < Cin * PH * PW; i += blockDim.x) {
+    const int px = i % PW, py = (i / PW) % PH, c = i / (PW * PH);
+    const int ix = px - 1, iy = y0 + py - 1;
+    float v = 0.f;
+    if (ix >= 0 && ix < W && iy >= 0 && iy < H && py < rows + 2)
+      v = (c < C0) ? __ldg(x0 + (((long long)b * C0 + c) * H + iy) * W + ix)
+                   : __ldg(x1 + (((long long)b * C1 + (c - C0)) * H + iy) * W + ix);
+    patch[i] = v;
+  }
+  // K index -> offset of the tap inside the patch relative to the pixel's top-left halo corner; bit 30 = "lo" term, -1 = zero
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int kk = k, lo = 0;
+    if (kk >= K9) { kk -= K9; lo = 1; }
+    int off = -1;
+    if (kk < K9) { const int tap = kk / Cin, c = kk - tap * Cin; off = (c * PH + tap / 3) * PW + tap % 3; if (lo) off |= 1 << 30; }
+    koff[k] = off;
+  }
+  __syncthreads();
   const int cv = Kpad >> 3;
-  const long long total = (long long)B * H * W * cv;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int k0 = (int)(i % cv) << 3;
-    const long long m = i / cv;
-    const int x = (int)(m % W), y = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+  const int total = rows * W * cv;
+  bf16* obase = out + (((long long)b * H + y0) * W) * Kpad;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int k0 = (i % cv) << 3;
+    const int m = i / cv;                  // pixel within the strip
+    const int x = m % W, ry = m / W;
+    const int pbase = ry * PW + x;
     uint4 o4;
     bf16* ob = (bf16*)&o4;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int k = k0 + j;
-      const bool lo = k >= K9;
-      if (lo) k -= K9;
+      const int off = koff[k0 + j];
       float v = 0.f;
-      if (k < K9) {
-        const int tap = k / Cin, c = k - tap * Cin;
-        const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-          v = (c < C0) ? __ldg(x0 + (((long long)b * C0 + c) * H + iy) * W + ix)
-                       : __ldg(x1 + (((long long)b * C1 + (c - C0)) * H + iy) * W + ix);
-        if (lo) v = v - __bfloat162float(__float2bfloat16_rn(v));
+      if (off >= 0) {
+        v = patch[pbase + (off & 0x3fffffff)];
+        if (off >> 30) v = v - __bfloat162float(__float2bfloat16_rn(v));
       }
       ob[j] = __float2bfloat16_rn(v);
     }
-    *(uint4*)(out + i * 8) = o4;
+    *(uint4*)(obase + (long long)i * 8) = o4;
   }
 }
 
 int stem_im2col_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st) {
   const int cx = cond ? e.x_channels() : e.cfg.in_channels;
-  const long long total = (long long)B * op.Hin * op.Win * (op.Cout / 8);
-  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.sm_count * 16);
-  stem_im2col_kernel<<<blocks, 256, 0, st>>>(x, cond, cx, e.cfg.in_channels - cx, (bf16*)tensor_ptr(e, op.out, B), B, op.Hin, op.Win, op.Cout);
+  const int strips = (op.Hin + IM2COL_ROWS - 1) / IM2COL_ROWS;
+  const size_t smem = sizeof(float) * ((size_t)op.Cin * (IM2COL_ROWS + 2) * (op.Win + 2) + op.Cout);
+  if (smem > 48 * 1024) { e.err = "stem im2col patch does not fit shared memory"; return CFM_ERR_INVALID; }
+  stem_im2col_kernel<<<B * strips, 256, smem, st>>>(x, cond, cx, e.cfg.in_channels - cx, (bf16*)tensor_ptr(e, op.out, B), B, op.Hin, op.Win, op.Cout);
   return 0;
 }
 
