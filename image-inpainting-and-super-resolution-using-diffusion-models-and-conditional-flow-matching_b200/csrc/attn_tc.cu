@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_qk, 3 * 16384);
       tma_load_2d(smem + AT_Q_OFF, &map, bar_qk, qcol, row0 + mt * AT_M);
       tma_load_2d(smem + AT_K_OFF, &map, bar_qk, kcol, row0);
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
     }
     mbar_wait(bar_qk, 0);
     tc_fence_after();
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(AT_M, AT_T);
       const uint64_t ad = make_desc_sw128(smem_u32(smem + AT_Q_OFF)), bd = make_desc_sw128(smem_u32(smem + AT_K_OFF));
 #pragma unroll
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   if (warp == 0) {
     mbar_wait(bar_v, 0);
     tc_fence_after();
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_major(AT_M, AT_D, 0, 1);
       const uint32_t pbase = smem_u32(smem + AT_P_OFF), vbase = smem_u32(smem + AT_V_OFF);
 #pragma unroll
@@ -139,21 +139,24 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   mbar_wait(bar_o, 0);
   tc_fence_after();
   const float inv = 1.0f / sum;
-  bf16* op = p.out + ((long long)(row0 + mt * AT_M + r)) * p.C + h * AT_D;
+  // 4 lanes write one row's 64 B run per instruction (quad transpose) instead of 32 half-sector stores
+  bf16* op = p.out + ((long long)(row0 + mt * AT_M + (r & ~3))) * p.C + h * AT_D + 8 * (lane & 3);
 #pragma unroll
   for (int c0 = 0; c0 < AT_D; c0 += 32) {
     uint32_t v[32];
     tmem_ld32(t_row + (uint32_t)c0, v);
     tmem_ld_wait();
+    uint4 o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      uint4 o4;
-      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+      __nv_bfloat162* o2 = (__nv_bfloat162*)&o[i];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         o2[q] = __floats2bfloat162_rn(__uint_as_float(v[i * 8 + 2 * q]) * inv, __uint_as_float(v[i * 8 + 2 * q + 1]) * inv);
-      *(uint4*)(op + c0 + i * 8) = o4;
     }
+    quad_transpose(o, lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *(uint4*)(op + (long long)k * p.C + c0) = o[k];
   }
   tc_fence_before();
   __syncthreads();

@@ -26,35 +26,43 @@ void* tensor_ptr(const Engine& e, int id, int B);
 
 constexpr int TC_BLOCK_M = 128;         // rows of one UMMA; a CTA tile is 128 * mh rows (mh = 1 or 2 M-halves)
 constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB per M-half
-constexpr int TC_STAGE_BYTES = 48 * 1024;                 // A (16 KB * mh) + B (block_n * 128 B) <= 48 KB
 #ifndef CFM_TC_EPI_WARPS
 #define CFM_TC_EPI_WARPS 8
 #endif
 constexpr int TC_EPI_WARPS = CFM_TC_EPI_WARPS;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;        // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr int TC_MAX_COUT = 2048;                         // bias staged in smem
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_MAX_COUT * 4 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_MAX_A = 8, TC_MAX_B = 16;                // ring depths (A slots, B slots)
+constexpr int TC_RING_BYTES = 216 * 1024;                 // A ring + B ring
+constexpr int TC_BAR_BYTES = 512;
+constexpr int TC_SMEM_BYTES = TC_RING_BYTES + TC_MAX_COUT * 4 + TC_BAR_BYTES + 1024 /*align*/;
 
-struct TcSeg { int map; int n_chunks; int ks; int stride; };
+// One K segment: the main 3x3 / 1x1 operand or a 1x1 skip operand.
+//   halo = 0: one A tile per (tap, 64-channel chunk), shifted by the tap offset.
+//   halo = 1: one A tile per (chunk, dx): a box of (tile rows + 2) image rows; the taps along y are row-shifted
+//             views of that box (descriptor start + dy * bw * 128 B - a multiple of the 1024 B swizzle atom), so
+//             a 3x3 conv pulls its activations from L2 three times instead of nine.  The operand stream from L2
+//             (not the tensor pipe) is what bounds the N <= 128 layers: 96 B/clk/SM without this, ~57 with.
+struct TcSeg { int map; int n_chunks; int ks; int stride; int halo; };
 
 struct TcParams {
   int n_seg; TcSeg seg[3];
   int total_k;
-  int B, H, W;                 // output spatial size
-  int bw, bh, bn;              // tile box, bw*bh*bn == 128 * mh
+  int B, H, W;                 // spatial size of the grid the M tiles walk (output size; source size for the folded upsample)
+  int bw, bh, bn;              // tile box, bw*bh*bn == 128 * mh  (128 per CTA in the pair kernel)
   int mh;                      // M-halves per CTA tile (2: two UMMAs share one B tile)
   int tiles_w, tiles_h, tiles_b, tiles_n, n_tiles;
   int n_phase;                 // 4: nearest-x2 upsample folded into the conv as four 2x2 sub-pixel convs (H, W = source size)
   int block_n, Cout;
+  int a_slot_bytes, b_slot_bytes, n_a, n_b;   // operand rings
+  int a_tile_bytes, a_halo_bytes;             // bytes of a plain / halo A load
   const float* bias;
   const float* emb; int emb_stride; const int* emb_row;
   const bf16* res0; const bf16* res1; int R0, R1;
   bf16* out;
   float* out_nchw; int cout_real;   // network head: fp32 NCHW output of the first cout_real channels
 };
-
 
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers (shared by the single-CTA and the CTA-pair kernel)
@@ -102,26 +110,6 @@ __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCo
     r.pix = ((long long)r.n * p.H + r.h) * p.W + r.w;
   }
   return r;
-}
-// 4x4 transpose of 16-byte chunks inside each aligned group of 4 lanes: in  c[k] = chunk k of this lane's row,
-// out c[k] = chunk (lane & 3) of the row owned by lane (lane & ~3) + k.  An involution: the same call maps back.
-// It turns "one lane = one 64 B row segment" (32 half-sector accesses per instruction) into "4 lanes = one row
-// segment" (8 fully written 64 B runs per instruction) for the epilogue's global loads and stores.
-__device__ __forceinline__ void quad_transpose(uint4 (&c)[4], int lane) {
-#pragma unroll
-  for (int m = 1; m <= 2; m <<= 1) {
-    const bool up = (lane & m) != 0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      if (a & m) continue;
-      const int b = a | m;
-      const uint4 send = up ? c[a] : c[b];
-      uint4 recv;
-      recv.x = __shfl_xor_sync(0xffffffffu, send.x, m); recv.y = __shfl_xor_sync(0xffffffffu, send.y, m);
-      recv.z = __shfl_xor_sync(0xffffffffu, send.z, m); recv.w = __shfl_xor_sync(0xffffffffu, send.w, m);
-      if (up) c[a] = recv; else c[b] = recv;
-    }
-  }
 }
 // pixel index of row (lane & ~3) + k of this lane's group: the 4 rows of a group are consecutive output pixels
 // (box width % 4 == 0), two apart in the interleaved map of a sub-pixel phase
@@ -201,6 +189,11 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// K-loop walk shared by the producer and the MMA issuer
+// ------------------------------------------------------------------------------------------------
+struct Ring { int slot; uint32_t phase; int n; __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1; } } };
+
+// ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -209,15 +202,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int a_bytes = TC_A_BYTES * p.mh;
-  const int b_bytes = p.block_n * TC_BLOCK_K * 2;
-  float* s_bias = (float*)(smem + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES + TC_MAX_COUT * 4);
-  uint64_t* full_bar = bars;                 // [stages]
-  uint64_t* empty_bar = bars + TC_STAGES;    // [stages]
-  uint64_t* tfull_bar = bars + 2 * TC_STAGES;      // [2]
-  uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2; // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+  uint8_t* ring_a = smem;
+  uint8_t* ring_b = smem + p.n_a * p.a_slot_bytes;
+  float* s_bias = (float*)(smem + TC_RING_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + TC_RING_BYTES + TC_MAX_COUT * 4);
+  uint64_t* fullA = bars;                              // [TC_MAX_A]
+  uint64_t* emptyA = bars + TC_MAX_A;                  // [TC_MAX_A]
+  uint64_t* fullB = bars + 2 * TC_MAX_A;               // [TC_MAX_B]
+  uint64_t* emptyB = bars + 2 * TC_MAX_A + TC_MAX_B;   // [TC_MAX_B]
+  uint64_t* tfull_bar = bars + 2 * TC_MAX_A + 2 * TC_MAX_B;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                          // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -225,7 +220,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     if (p.n_seg > 1) prefetch_tmap(&mapA1);
     if (p.n_seg > 2) prefetch_tmap(&mapA2);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TC_MAX_A; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < TC_MAX_B; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], TC_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -239,26 +235,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+    if (elect_one()) {
+      Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
-        const int nt = tc.nt;
         const int w0 = tc.tw * p.bw, h0 = tc.th * p.bh, n0 = tc.tb * p.bn;
-        int kiter = tc.ph * p.total_k;
+        int brow = tc.ph * p.total_k * p.Cout + tc.nt * p.block_n;      // row of the packed weights of the next K-iteration
         for (int s = 0; s < p.n_seg; ++s) {
           const TcSeg sg = p.seg[s];
           const CUtensorMap* map = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-          const int taps = sg.ks * sg.ks;
-          for (int tap = 0; tap < taps; ++tap) {
-            int dy, dx; tap_offset(sg.ks, tap, tc.ph, &dy, &dx);
-            for (int ch = 0; ch < sg.n_chunks; ++ch, ++kiter) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-              uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-              tma_load_4d(sa, map, &full_bar[stage], ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
-              tma_load_2d(sa + a_bytes, &mapB, &full_bar[stage], 0, kiter * p.Cout + nt * p.block_n);
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (sg.halo) {
+            const int yorg = h0 - 1 + (sg.ks == 2 ? (tc.ph >> 1) : 0);
+            for (int ch = 0; ch < sg.n_chunks; ++ch)
+              for (int xi = 0; xi < sg.ks; ++xi) {
+                const int dx = xi - 1 + (sg.ks == 2 ? (tc.ph & 1) : 0);
+                mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
+                mbar_expect_tx(&fullA[ra.slot], p.a_halo_bytes);
+                tma_load_4d(ring_a + ra.slot * p.a_slot_bytes, map, &fullA[ra.slot], ch * TC_BLOCK_K, w0 + dx, yorg, n0);
+                ra.next();
+                for (int yi = 0; yi < sg.ks; ++yi, brow += p.Cout) {
+                  mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
+                  mbar_expect_tx(&fullB[rb.slot], p.b_slot_bytes);
+                  tma_load_2d(ring_b + rb.slot * p.b_slot_bytes, &mapB, &fullB[rb.slot], 0, brow);
+                  rb.next();
+                }
+              }
+          } else {
+            const int taps = sg.ks * sg.ks;
+            for (int tap = 0; tap < taps; ++tap) {
+              int dy, dx; tap_offset(sg.ks, tap, tc.ph, &dy, &dx);
+              for (int ch = 0; ch < sg.n_chunks; ++ch, brow += p.Cout) {
+                mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
+                mbar_expect_tx(&fullA[ra.slot], p.a_tile_bytes);
+                tma_load_4d(ring_a + ra.slot * p.a_slot_bytes, map, &fullA[ra.slot], ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+                ra.next();
+                mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
+                mbar_expect_tx(&fullB[rb.slot], p.b_slot_bytes);
+                tma_load_2d(ring_b + rb.slot * p.b_slot_bytes, &mapB, &fullB[rb.slot], 0, brow);
+                rb.next();
+              }
             }
           }
         }
@@ -267,31 +282,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc(TC_BLOCK_M, p.block_n);
-    int stage = 0; uint32_t phase = 0;
+    const uint32_t row_step = (uint32_t)(p.bw * 128) >> 4;        // one image row of a halo slot, in descriptor units
+    Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
-      for (int k = 0; k < p.total_k; ++k) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
-          const uint64_t adesc = make_desc_sw128(sa);
-          const uint64_t bdesc = make_desc_sw128(sa + a_bytes);
+      int kdone = 0;
+      for (int s = 0; s < p.n_seg; ++s) {
+        const TcSeg sg = p.seg[s];
+        const int G = sg.halo ? sg.ks : 1;
+        const int n_groups = sg.halo ? sg.n_chunks * sg.ks : sg.ks * sg.ks * sg.n_chunks;
+        for (int g = 0; g < n_groups; ++g) {
+          mbar_wait(&fullA[ra.slot], ra.phase);
+          const uint32_t sa = smem_u32(ring_a + ra.slot * p.a_slot_bytes);
+          for (int j = 0; j < G; ++j, ++kdone) {
+            mbar_wait(&fullB[rb.slot], rb.phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t adesc = make_desc_sw128(sa) + (uint64_t)(sg.halo ? (uint32_t)j * row_step : 0u);
+              const uint64_t bdesc = make_desc_sw128(smem_u32(ring_b + rb.slot * p.b_slot_bytes));
 #pragma unroll
-          for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk) {
-            const uint32_t accum = (k > 0 || kk > 0) ? 1u : 0u;
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
-            if (p.mh == 2)   // second M-half re-uses the same B tile: halves the B traffic per FLOP
-              umma_bf16(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)(TC_A_BYTES >> 4) + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+              for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk) {
+                const uint32_t accum = (kdone > 0 || kk > 0) ? 1u : 0u;
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+                if (p.mh == 2)   // second M-half re-uses the same B tile: halves the B traffic per FLOP
+                  umma_bf16(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)(TC_A_BYTES >> 4) + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+              }
+              umma_commit(&emptyB[rb.slot]);                      // B slot reusable once these MMAs retire
+              if (j == G - 1) umma_commit(&emptyA[ra.slot]);      // last view of this A slot
+              if (kdone == p.total_k - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+            }
+            __syncwarp();
+            rb.next();
           }
-          umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
-          if (k == p.total_k - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          ra.next();
         }
-        __syncwarp();
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -351,32 +378,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): two SMs of a cluster cooperate on a 256-row x N tile.  Each CTA loads
 // its own 128-row A half and HALF of the weight tile (N/2 rows) - so the bytes pulled from L2 and
-// written to / read from shared memory per FLOP drop by a third versus the single-CTA 128 x N tile,
-// and the freed shared memory buys a deeper ring (6 stages at N = 256).  The leader CTA's MMA warp
-// issues one 256 x N x 16 UMMA per K step; tcgen05.commit multicasts stage-free / accumulator-ready
-// signals to both CTAs; both CTAs' epilogues drain their own 128 TMEM lanes and report back to the
-// leader's accumulator-empty barrier.
+// written to / read from shared memory per FLOP drop by a third versus the single-CTA 128 x N tile.
+// The leader CTA's MMA warp issues one 256 x N x 16 UMMA per K step; tcgen05.commit multicasts
+// slot-free / accumulator-ready signals to both CTAs; both CTAs' epilogues drain their own 128 TMEM
+// lanes and report back to the leader's accumulator-empty barrier.
 // ------------------------------------------------------------------------------------------------
-constexpr int TC2_MAX_STAGES = 8;
-constexpr int TC2_RING_BYTES = 192 * 1024;
-constexpr int TC2_SMEM_BYTES = TC2_RING_BYTES + TC_MAX_COUT * 4 + 1024 + 256;
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
-                const TcParams p, const int n_stages) {
+                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int a_bytes = TC_A_BYTES;                              // 128 rows per CTA
-  const int b_bytes = (p.block_n >> 1) * TC_BLOCK_K * 2;       // half of the weight tile per CTA
-  const int stage_bytes = a_bytes + b_bytes;
-  float* s_bias = (float*)(smem + TC2_RING_BYTES);
-  uint64_t* bars = (uint64_t*)(smem + TC2_RING_BYTES + TC_MAX_COUT * 4);
-  uint64_t* full_bar = bars;                          // [8]  (leader's are used)
-  uint64_t* empty_bar = bars + TC2_MAX_STAGES;        // [8]  per CTA, signalled by the leader's commit multicast
-  uint64_t* tfull_bar = bars + 2 * TC2_MAX_STAGES;    // [2]  per CTA, commit multicast
-  uint64_t* tempty_bar = bars + 2 * TC2_MAX_STAGES + 2;   // [2]  leader's are used: 2 * TC_EPI_WARPS arrivals
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC2_MAX_STAGES + 4);
+  uint8_t* ring_a = smem;
+  uint8_t* ring_b = smem + p.n_a * p.a_slot_bytes;
+  float* s_bias = (float*)(smem + TC_RING_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + TC_RING_BYTES + TC_MAX_COUT * 4);
+  uint64_t* fullA = bars;                              // leader's are used
+  uint64_t* emptyA = bars + TC_MAX_A;                  // per CTA, signalled by the leader's commit multicast
+  uint64_t* fullB = bars + 2 * TC_MAX_A;               // leader's are used
+  uint64_t* emptyB = bars + 2 * TC_MAX_A + TC_MAX_B;   // per CTA
+  uint64_t* tfull_bar = bars + 2 * TC_MAX_A + 2 * TC_MAX_B;      // [2] per CTA, commit multicast
+  uint64_t* tempty_bar = tfull_bar + 2;                          // [2] leader's are used: 2 * TC_EPI_WARPS arrivals
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -389,7 +412,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     if (p.n_seg > 1) prefetch_tmap(&mapA1);
     if (p.n_seg > 2) prefetch_tmap(&mapA2);
-    for (int s = 0; s < TC2_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TC_MAX_A; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < TC_MAX_B; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * TC_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -403,27 +427,45 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+    if (elect_one()) {
+      Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
         const TileCoord tc = decode_pair_tile(p, pt, (int)rank);   // tb may equal tiles_b for the odd tail: all-OOB loads
-        const int nt = tc.nt;
         const int w0 = tc.tw * p.bw, h0 = tc.th * p.bh, n0 = tc.tb * p.bn;
-        int kiter = tc.ph * p.total_k;
+        int brow = tc.ph * p.total_k * p.Cout + tc.nt * p.block_n + (int)rank * (p.block_n >> 1);
         for (int s = 0; s < p.n_seg; ++s) {
           const TcSeg sg = p.seg[s];
           const CUtensorMap* map = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-          const int taps = sg.ks * sg.ks;
-          for (int tap = 0; tap < taps; ++tap) {
-            int dy, dx; tap_offset(sg.ks, tap, tc.ph, &dy, &dx);
-            for (int ch = 0; ch < sg.n_chunks; ++ch, ++kiter) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);       // leader's full barrier
-              if (leader) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);      // bytes of BOTH CTAs
-              uint8_t* sa = smem + stage * stage_bytes;
-              tma_load_4d_2sm(sa, map, bar, ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
-              tma_load_2d_2sm(sa + a_bytes, &mapB, bar, 0, kiter * p.Cout + nt * p.block_n + (int)rank * (p.block_n >> 1));
-              if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          if (sg.halo) {
+            const int yorg = h0 - 1 + (sg.ks == 2 ? (tc.ph >> 1) : 0);
+            for (int ch = 0; ch < sg.n_chunks; ++ch)
+              for (int xi = 0; xi < sg.ks; ++xi) {
+                const int dx = xi - 1 + (sg.ks == 2 ? (tc.ph & 1) : 0);
+                mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
+                if (leader) mbar_expect_tx(&fullA[ra.slot], 2 * p.a_halo_bytes);      // bytes of BOTH CTAs
+                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * TC_BLOCK_K, w0 + dx, yorg, n0);
+                ra.next();
+                for (int yi = 0; yi < sg.ks; ++yi, brow += p.Cout) {
+                  mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
+                  if (leader) mbar_expect_tx(&fullB[rb.slot], 2 * p.b_slot_bytes);
+                  tma_load_2d_2sm(ring_b + rb.slot * p.b_slot_bytes, &mapB, mapa_u32(smem_u32(&fullB[rb.slot]), 0), 0, brow);
+                  rb.next();
+                }
+              }
+          } else {
+            const int taps = sg.ks * sg.ks;
+            for (int tap = 0; tap < taps; ++tap) {
+              int dy, dx; tap_offset(sg.ks, tap, tc.ph, &dy, &dx);
+              for (int ch = 0; ch < sg.n_chunks; ++ch, brow += p.Cout) {
+                mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
+                if (leader) mbar_expect_tx(&fullA[ra.slot], 2 * p.a_tile_bytes);
+                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+                ra.next();
+                mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
+                if (leader) mbar_expect_tx(&fullB[rb.slot], 2 * p.b_slot_bytes);
+                tma_load_2d_2sm(ring_b + rb.slot * p.b_slot_bytes, &mapB, mapa_u32(smem_u32(&fullB[rb.slot]), 0), 0, brow);
+                rb.next();
+              }
             }
           }
         }
@@ -433,27 +475,39 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       const uint32_t idesc = make_idesc(256, p.block_n);
-      int stage = 0; uint32_t phase = 0;
+      const uint32_t row_step = (uint32_t)(p.bw * 128) >> 4;
+      Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       int acc = 0; uint32_t acc_phase = 0;
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        for (int k = 0; k < p.total_k; ++k) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-            const uint64_t adesc = make_desc_sw128(sa);
-            const uint64_t bdesc = make_desc_sw128(sa + a_bytes);
+        int kdone = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const TcSeg sg = p.seg[s];
+          const int G = sg.halo ? sg.ks : 1;
+          const int n_groups = sg.halo ? sg.n_chunks * sg.ks : sg.ks * sg.ks * sg.n_chunks;
+          for (int g = 0; g < n_groups; ++g) {
+            mbar_wait(&fullA[ra.slot], ra.phase);
+            const uint32_t sa = smem_u32(ring_a + ra.slot * p.a_slot_bytes);
+            for (int j = 0; j < G; ++j, ++kdone) {
+              mbar_wait(&fullB[rb.slot], rb.phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t adesc = make_desc_sw128(sa) + (uint64_t)(sg.halo ? (uint32_t)j * row_step : 0u);
+                const uint64_t bdesc = make_desc_sw128(smem_u32(ring_b + rb.slot * p.b_slot_bytes));
 #pragma unroll
-            for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk)
-              umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
-            umma_commit_2sm(&empty_bar[stage], 3);                       // both CTAs may refill this stage
-            if (k == p.total_k - 1) umma_commit_2sm(&tfull_bar[acc], 3); // both CTAs' epilogues may drain
+                for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk)
+                  umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kdone > 0 || kk > 0) ? 1u : 0u);
+                umma_commit_2sm(&emptyB[rb.slot], 3);                         // both CTAs may refill this B slot
+                if (j == G - 1) umma_commit_2sm(&emptyA[ra.slot], 3);         // last view of this A slot
+                if (kdone == p.total_k - 1) umma_commit_2sm(&tfull_bar[acc], 3);   // both CTAs' epilogues may drain
+              }
+              __syncwarp();
+              rb.next();
+            }
+            ra.next();
           }
-          __syncwarp();
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -501,17 +555,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct TcMaps { CUtensorMap a[3]; CUtensorMap b; CUtensorMap a2[3]; CUtensorMap b2; };   // a2/b2: CTA-pair boxes (128 rows, N/2 rows)
+struct TcMaps { CUtensorMap a[3]; CUtensorMap b; };
 
 struct TcConvPlan {
-  bf16* w_packed = nullptr;     // [total_k * Cout][64]
+  bf16* w_packed = nullptr;     // [n_phase * total_k * Cout][64], K-iterations in the order the producer walks them
   int n_seg = 0; TcSeg seg[3];
   int seg_tensor[3] = {-1, -1, -1};
   int total_k = 0, block_n = 0;
-  int bw = 0, bh = 0, bn = 0, mh = 1;
-  int n_phase = 1, Hg = 0, Wg = 0;   // sub-pixel phases (4 for the folded upsample) and the grid the M tiles walk
-  bool pair = false;           // CTA-pair (cta_group::2) kernel
-  int pbw = 0, pbh = 0, pbn = 0;   // 128-row box of the pair kernel
+  int bw = 0, bh = 0, bn = 0, mh = 1;   // per-CTA tile box (128 * mh rows)
+  int n_phase = 1, Hg = 0, Wg = 0;      // sub-pixel phases (4 for the folded upsample) and the grid the M tiles walk
+  bool pair = false;                    // CTA-pair (cta_group::2) kernel
+  int a_slot_bytes = 0, b_slot_bytes = 0, n_a = 0, n_b = 0, a_tile_bytes = 0, a_halo_bytes = 0;
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
@@ -521,7 +575,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static std::vector<TcConvPlan*> g_plans_dummy;
 
 static int get_encode(Engine& e) {
   if (g_encode) return 0;
@@ -562,15 +615,29 @@ bool tc_conv_supported(const Engine& e, const Op& op) {
   return true;
 }
 
+// ring depths: D K-iterations of weights in flight and the A slots that feed them (G K-iterations per A slot)
+static bool size_rings(TcConvPlan* pl, int G) {
+  for (int D = 12; D >= G; --D) {
+    const int n_b = D, n_a = (D + G - 1) / G + (G > 1 ? 1 : 0);
+    if (n_a > TC_MAX_A || n_b > TC_MAX_B) continue;
+    if ((long long)n_a * pl->a_slot_bytes + (long long)n_b * pl->b_slot_bytes > TC_RING_BYTES) continue;
+    pl->n_a = n_a; pl->n_b = n_b;
+    return true;
+  }
+  return false;
+}
+
 int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::vector<float>& ws) {
   TcConvPlan* pl = new TcConvPlan();
   const int Cin = op.Cin, ks = op.ks;
   const int Cout = op.out_is_output ? 32 : op.Cout;      // padded rows of W are zero
   pl->cout_pad = Cout;
   pl->block_n = pick_block_n(Cout);
-  // N <= 128 tiles are shared-memory-bandwidth bound with a 128-row tile (A and B stream at 1:1);
-  // a 256-row tile (two UMMAs per B tile) restores the 2:1 ratio of the N = 256 case.
-  pl->mh = (pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;
+  static const int pair_min_n = [] { const char* v = getenv("CFM_TC_PAIR_MIN_N"); return v ? atoi(v) : 192; }();
+  // N >= 192: CTA pair (half the weight tile per SM).  N <= 128: a pair measured slower than one CTA with a 256-row tile
+  // (two UMMAs per B tile), which restores the 2:1 A:B ratio of the N = 256 case.
+  pl->pair = !op.out_is_output && pl->block_n >= pair_min_n && !env_off("CFM_DISABLE_TC_2CTA");
+  pl->mh = (!pl->pair && pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;
   const int rows = 128 * pl->mh;
   // sub-pixel decomposition of (nearest x2 upsample -> 3x3 conv): the M tiles walk the SOURCE grid, four phases,
   // each a 2x2 conv whose taps are sums of the 3x3 taps that land on the same source pixel (4/9 of the MACs,
@@ -581,46 +648,58 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   pl->bw = std::min(Wg, rows);
   pl->bh = std::min(Hg, rows / pl->bw);
   pl->bn = rows / (pl->bw * pl->bh);
-  pl->pair = !op.out_is_output && pl->block_n >= 192 && !env_off("CFM_DISABLE_TC_2CTA");   // N = 128 tiles are A-traffic bound: 256-row single-CTA tiles win there
-  pl->pbw = std::min(Wg, 128);
-  pl->pbh = std::min(Hg, 128 / pl->pbw);
-  pl->pbn = 128 / (pl->pbw * pl->pbh);
   const int eks = op.ups ? 2 : ks;          // taps per axis the kernel walks
-  pl->seg[0] = {0, Cin / TC_BLOCK_K, eks, op.stride}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
-  if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
-  if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / TC_BLOCK_K, 1, 1}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
-  pl->total_k = eks * eks * (Cin / TC_BLOCK_K) + op.Cskip / TC_BLOCK_K;
-  // pack: [phase] kiter-major, [Cout][64] per kiter, same iteration order as the producer warp
+  // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous) and be 8-row aligned per image row
+  bool halo = eks > 1 && op.stride == 1 && pl->bn == 1 && pl->bw >= 8 && !env_off("CFM_DISABLE_TC_HALO");
+  pl->a_tile_bytes = rows * 128;
+  pl->a_halo_bytes = (rows + 2 * pl->bw) * 128;
+  pl->b_slot_bytes = (pl->pair ? pl->block_n / 2 : pl->block_n) * 128;
+  pl->a_slot_bytes = halo ? pl->a_halo_bytes : pl->a_tile_bytes;
+  if (halo && !size_rings(pl, eks)) { halo = false; pl->a_slot_bytes = pl->a_tile_bytes; }
+  if (!halo && !size_rings(pl, 1)) { e.err = "conv tile does not fit the shared-memory rings: " + op.name; delete pl; return CFM_ERR_INVALID; }
+  pl->seg[0] = {0, Cin / TC_BLOCK_K, eks, op.stride, halo ? 1 : 0}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
+  if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / TC_BLOCK_K, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
+  if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / TC_BLOCK_K, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
+  const int n_chunks = Cin / TC_BLOCK_K;
+  pl->total_k = eks * eks * n_chunks + op.Cskip / TC_BLOCK_K;
+  // pack: [phase] K-iteration-major, [Cout][64] per K-iteration, in the producer's order:
+  //   halo:  chunk -> x tap -> y tap        plain:  tap (y-major) -> chunk        then the 1x1 skip chunks
   std::vector<bf16> packed((size_t)pl->n_phase * pl->total_k * Cout * TC_BLOCK_K);
-  size_t kiter = 0;
-  if (op.ups) {
+  // weight of main-operand channel c, output o, for walked tap (yi, xi) of phase ph
+  auto tap_weight = [&](int ph, int yi, int xi, int c, int o) -> float {
+    if (o >= op.Cout) return 0.f;
+    if (!op.ups) return w[((size_t)o * Cin + c) * ks * ks + yi * ks + xi];
     // phase (py, px), tap (a, b): source offset (a - 1 + py, b - 1 + px); the 3x3 taps folding onto it are
     // ky in {0} | {1,2} for py = 0 and {0,1} | {2} for py = 1 (same along x); summed in fp32, rounded once
     auto lo = [](int p, int a) { return p == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2); };
     auto hi = [](int p, int a) { return p == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2); };
-    for (int ph = 0; ph < 4; ++ph)
-      for (int tap = 0; tap < 4; ++tap) {
-        const int py = ph >> 1, px = ph & 1, a = tap >> 1, b = tap & 1;
-        for (int ch = 0; ch < Cin / TC_BLOCK_K; ++ch, ++kiter)
-          for (int o = 0; o < Cout; ++o)
-            for (int j = 0; j < TC_BLOCK_K; ++j) {
-              float acc = 0.f;
-              for (int ky = lo(py, a); ky <= hi(py, a); ++ky)
-                for (int kx = lo(px, b); kx <= hi(px, b); ++kx)
-                  acc += w[((size_t)o * Cin + ch * TC_BLOCK_K + j) * 9 + ky * 3 + kx];
-              packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(acc);
-            }
-      }
-  }
-  for (int tap = 0; !op.ups && tap < ks * ks; ++tap)
-    for (int ch = 0; ch < Cin / TC_BLOCK_K; ++ch, ++kiter)
-      for (int o = 0; o < Cout; ++o)
-        for (int j = 0; j < TC_BLOCK_K; ++j)
-          packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(o < op.Cout ? w[((size_t)o * Cin + ch * TC_BLOCK_K + j) * ks * ks + tap] : 0.f);
-  for (int ch = 0; ch < op.Cskip / TC_BLOCK_K; ++ch, ++kiter)
+    const int py = ph >> 1, px = ph & 1;
+    float acc = 0.f;
+    for (int ky = lo(py, yi); ky <= hi(py, yi); ++ky)
+      for (int kx = lo(px, xi); kx <= hi(px, xi); ++kx) acc += w[((size_t)o * Cin + c) * 9 + ky * 3 + kx];
+    return acc;
+  };
+  size_t kiter = 0;
+  auto put = [&](int ph, int yi, int xi, int ch) {
     for (int o = 0; o < Cout; ++o)
       for (int j = 0; j < TC_BLOCK_K; ++j)
-        packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(ws[(size_t)o * op.Cskip + ch * TC_BLOCK_K + j]);
+        packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(tap_weight(ph, yi, xi, ch * TC_BLOCK_K + j, o));
+    ++kiter;
+  };
+  for (int ph = 0; ph < pl->n_phase; ++ph) {
+    if (halo) {
+      for (int ch = 0; ch < n_chunks; ++ch)
+        for (int xi = 0; xi < eks; ++xi)
+          for (int yi = 0; yi < eks; ++yi) put(ph, yi, xi, ch);
+    } else {
+      for (int tap = 0; tap < eks * eks; ++tap)
+        for (int ch = 0; ch < n_chunks; ++ch) put(ph, tap / eks, tap % eks, ch);
+    }
+    for (int ch = 0; ch < op.Cskip / TC_BLOCK_K; ++ch, ++kiter)
+      for (int o = 0; o < Cout; ++o)
+        for (int j = 0; j < TC_BLOCK_K; ++j)
+          packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(ws[(size_t)o * op.Cskip + ch * TC_BLOCK_K + j]);
+  }
   void* d = nullptr;
   if (cudaMalloc(&d, packed.size() * sizeof(bf16)) != cudaSuccess) { e.err = "cudaMalloc(packed conv weights) failed"; delete pl; return CFM_ERR_OOM; }
   e.owned.push_back(d);
@@ -640,7 +719,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES) != cudaSuccess) {
+        cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(conv_tc_kernel, smem) failed"; return CFM_ERR_CUDA;
     }
     attr_set = true;
@@ -654,9 +733,10 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
   for (int s = 0; s < pl->n_seg; ++s) {
     const TensorDesc& t = e.tensors[pl->seg_tensor[s]];
     const int st = pl->seg[s].stride;
+    const int box_h = pl->seg[s].halo ? pl->bh + 2 : pl->bh * st;
     cuuint64_t dims[4] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)t.C * 2, (cuuint64_t)t.W * t.C * 2, (cuuint64_t)t.H * t.W * t.C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->bw * st), (cuuint32_t)(pl->bh * st), (cuuint32_t)pl->bn};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->bw * st), (cuuint32_t)box_h, (cuuint32_t)pl->bn};
     cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
     CUresult r = g_encode(&m->a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, tensor_ptr(e, pl->seg_tensor[s], B), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -664,32 +744,9 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
     if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
   }
   for (int s = pl->n_seg; s < 3; ++s) m->a[s] = m->a[0];
-  if (pl->pair) {
-    for (int s = 0; s < pl->n_seg; ++s) {
-      const TensorDesc& t = e.tensors[pl->seg_tensor[s]];
-      const int st = pl->seg[s].stride;
-      cuuint64_t dims[4] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)B};
-      cuuint64_t strides[3] = {(cuuint64_t)t.C * 2, (cuuint64_t)t.W * t.C * 2, (cuuint64_t)t.H * t.W * t.C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->pbw * st), (cuuint32_t)(pl->pbh * st), (cuuint32_t)pl->pbn};
-      cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
-      CUresult r = g_encode(&m->a2[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, tensor_ptr(e, pl->seg_tensor[s], B), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A pair) failed for " + op.name; return CFM_ERR_CUDA; }
-    }
-    for (int s = pl->n_seg; s < 3; ++s) m->a2[s] = m->a2[0];
-    cuuint64_t dims2[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->n_phase * pl->total_k * pl->cout_pad};
-    cuuint64_t strides2[1] = {(cuuint64_t)TC_BLOCK_K * 2};
-    cuuint32_t box2[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->block_n / 2)};
-    cuuint32_t estr2[2] = {1, 1};
-    CUresult r2 = g_encode(&m->b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->w_packed, dims2, strides2, box2, estr2,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r2 != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(B pair) failed for " + op.name; return CFM_ERR_CUDA; }
-  }
   cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->n_phase * pl->total_k * pl->cout_pad};
   cuuint64_t strides[1] = {(cuuint64_t)TC_BLOCK_K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)pl->block_n};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->b_slot_bytes / 128)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(&m->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->w_packed, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -717,6 +774,8 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.tiles_n = pl->cout_pad / pl->block_n;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n * p.n_phase;
   p.block_n = pl->block_n; p.Cout = pl->cout_pad;
+  p.a_slot_bytes = pl->a_slot_bytes; p.b_slot_bytes = pl->b_slot_bytes; p.n_a = pl->n_a; p.n_b = pl->n_b;
+  p.a_tile_bytes = pl->a_tile_bytes; p.a_halo_bytes = pl->a_halo_bytes;
   p.bias = pl->bias_pad ? pl->bias_pad : op.bias;
   if (op.emb_off >= 0) { p.emb = e.emb_out + op.emb_off; p.emb_stride = e.emb_total; p.emb_row = e.row_of_sample; }
   p.res0 = (const bf16*)tensor_ptr(e, op.res0, B); p.R0 = op.res0 >= 0 ? e.tensors[op.res0].C : 0;
@@ -724,22 +783,18 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.out = (bf16*)tensor_ptr(e, op.out, B);
   if (op.out_is_output) { p.out_nchw = out_nchw; p.cout_real = op.Cout; }
   if (pl->pair) {
-    p.bw = pl->pbw; p.bh = pl->pbh; p.bn = pl->pbn; p.mh = 1;
-    p.tiles_w = pl->Wg / p.bw; p.tiles_h = pl->Hg / p.bh; p.tiles_b = (B + p.bn - 1) / p.bn;
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
-    const int stage_bytes = TC_A_BYTES + (pl->block_n / 2) * TC_BLOCK_K * 2;
-    const int n_stages = std::min(TC2_MAX_STAGES, TC2_RING_BYTES / stage_bytes);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * std::min(pair_tiles, e.sm_count / 2));
     cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC2_SMEM_BYTES;
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, it->second.a2[0], it->second.a2[1], it->second.a2[2], it->second.b2, p, n_stages);
+    cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
     if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
     return 0;
   }

@@ -58,6 +58,18 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// true in exactly one (converged) lane of the warp.  Unlike `lane == 0`, the compiler knows a single thread runs the
+// guarded code, so tcgen05 / TMA operands move to uniform registers without a per-lane ELECT/R2UR loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -116,6 +128,27 @@ __host__ __device__ constexpr uint32_t make_idesc_major(int M, int N, int a_mn, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
+// 4x4 transpose of 16-byte chunks inside each aligned group of 4 lanes: in  c[k] = chunk k of this lane's row,
+// out c[k] = chunk (lane & 3) of the row owned by lane (lane & ~3) + k.  An involution: the same call maps back.
+// It turns "one lane = one 64 B row segment" (32 half-sector accesses per instruction) into "4 lanes = one row
+// segment" (8 fully written 64 B runs per instruction) for the epilogue's global loads and stores.
+__device__ __forceinline__ void quad_transpose(uint4 (&c)[4], int lane) {
+#pragma unroll
+  for (int m = 1; m <= 2; m <<= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (a & m) continue;
+      const int b = a | m;
+      const uint4 send = up ? c[a] : c[b];
+      uint4 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, m); recv.y = __shfl_xor_sync(0xffffffffu, send.y, m);
+      recv.z = __shfl_xor_sync(0xffffffffu, send.z, m); recv.w = __shfl_xor_sync(0xffffffffu, send.w, m);
+      if (up) c[a] = recv; else c[b] = recv;
+    }
+  }
+}
 
 // ---- thread-block clusters / CTA pairs (cta_group::2) ---------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }

@@ -35,6 +35,6 @@ for r in sorted(rows, key=lambda r:-r['ms'])[:25]:
 
 import os
 os.makedirs('gpurun_out', exist_ok=True)
-with open('gpurun_out/profile_ops.txt','w') as f:
+with open('gpurun_out/' + (sys.argv[2] if len(sys.argv) > 2 else 'profile_ops.txt'),'w') as f:
     for r in rows:
         f.write(f"{r['name']:36s} {r['kind']:13s} {r['ms']:8.4f} ms {r['flops']/r['ms']/1e9 if r['ms'] else 0:8.1f} TF/s\n")
