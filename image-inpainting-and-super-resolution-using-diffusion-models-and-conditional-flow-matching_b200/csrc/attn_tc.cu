@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   const int vcol = p.new_order ? 2 * p.C + h * AT_D : h * 3 * AT_D + 2 * AT_D;
   const int row0 = b * AT_T;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     prefetch_tmap(&map);
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
@@ -205,7 +207,8 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.heads = op.heads; p.C = op.Cin; p.new_order = e.cfg.use_new_attention_order;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
-  attn_tc_kernel<<<dim3(AT_T / AT_M, B * op.heads), 128, AT_SMEM, st>>>(it->second, p);
+  LaunchCfg lc(dim3(AT_T / AT_M, B * op.heads), dim3(128), AT_SMEM, st, 1, pdl_enabled());
+  if (cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel, it->second, p) != cudaSuccess) { e.err = "attn_tc_kernel launch failed"; return CFM_ERR_CUDA; }
   return 0;
 }
 

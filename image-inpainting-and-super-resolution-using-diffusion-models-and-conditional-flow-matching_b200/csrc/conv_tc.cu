@@ -216,6 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();      // the next kernel's CTAs may take over SMs as ours retire and run their prologue
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     if (p.n_seg > 1) prefetch_tmap(&mapA1);
@@ -226,10 +227,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];   // weights: not produced by a predecessor
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                   // activations of the predecessor are complete and visible from here on
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = p.block_n * p.mh;     // TMEM columns per accumulator stage
 
@@ -408,6 +410,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
   const int pair_tiles = ((tiles128 + 1) >> 1) * p.tiles_n * p.n_phase;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     if (p.n_seg > 1) prefetch_tmap(&mapA1);
@@ -423,6 +426,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   __syncthreads();
   cluster_sync_all();                 // peer barriers initialised before any remote arrive / multicast commit
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -785,21 +789,15 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   if (pl->pair) {
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * std::min(pair_tiles, e.sm_count / 2));
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t ce = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+    LaunchCfg lc(dim3(2 * std::min(pair_tiles, e.sm_count / 2)), dim3(TC_THREADS), TC_SMEM_BYTES, st, 2, pdl_enabled());
+    cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc2_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
     if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
     return 0;
   }
   const int grid = std::min(p.n_tiles, e.sm_count);
-  conv_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+  LaunchCfg lc(dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, 1, pdl_enabled());
+  cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+  if (ce != cudaSuccess) { e.err = std::string("conv_tc_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
   return 0;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -84,6 +85,33 @@ struct Engine {
   std::vector<double> prof_ms;
   int x_channels() const { return cfg.out_channels; }
 };
+
+// Launch configuration with an optional cluster dimension and programmatic dependent launch (PDL).  A kernel launched
+// with pdl = true may start while its predecessor in the stream is still draining; it must execute pdl_wait()
+// (griddepcontrol.wait) before its first access to global memory that a predecessor writes or reads.
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, bool pdl) {
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    int n = 0;
+    if (cluster > 1) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (pdl) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+  }
+};
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("CFM_DISABLE_PDL"); return !(v && v[0] == '1'); }();
+  return on;
+}
 
 // conv_tc.cu
 bool tc_conv_supported(const Engine& e, const Op& op);

@@ -26,6 +26,7 @@ struct GnFastArgs {
   const bf16* src0; const bf16* src1; int C0, C1;
   int HW, cpg, slab;                 // slab channels per item (multiple of 8 and of cpg)
   int n_items;
+  int tpi, ipc;                      // threads per item, items per CTA (ipc > 1 only without a cluster)
   int cs;                            // CTAs (of one cluster) sharing an item's pixels; 1 = no cluster
   int shfl;                          // 1: vectors-per-pixel is a power of two <= 32 -> warp-shuffle pre-reduction
   int data_bytes;                    // staged bytes per CTA
@@ -49,45 +50,51 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
 
 __global__ void __launch_bounds__(GN_MAX_THREADS) groupnorm_bf16_kernel(GnFastArgs a) {
   extern __shared__ __align__(16) uint8_t gn_smem[];
-  // layout: data[data_bytes] | red[rows][17] | ch_sum[64] | ch_sq[64] | ch_scale[64] | ch_shift[64]
+  // layout: data[ipc][data_bytes] | red[rows][17] | ch_sum[ipc][128] | ch_sq | ch_scale | ch_shift
+  // Small feature maps pack `ipc` items into one CTA (tpi threads each) so a CTA still moves >= 16 KB.
   const int T = blockDim.x;
   const int vpp = a.slab >> 3;
-  const int n_warps = T >> 5;
-  const int red_rows = a.shfl ? n_warps * vpp : T;
-  float* red = (float*)(gn_smem + a.data_bytes);      // rows of 16 partials, stride 17 (bank-conflict-free per-thread rows)
+  const int tpi = a.tpi, ipc = a.ipc;
+  const int wpi = tpi >> 5;                                // warps per item
+  const int red_rows = a.shfl ? (T >> 5) * vpp : T;
+  float* red = (float*)(gn_smem + ipc * a.data_bytes);     // rows of 16 partials, stride 17 (bank-conflict-free per-thread rows)
   float* ch_sum = red + red_rows * 17;
-  float* ch_sq = ch_sum + GN_MAX_SLAB;
-  float* ch_scale = ch_sq + GN_MAX_SLAB;
-  float* ch_shift = ch_scale + GN_MAX_SLAB;
+  float* ch_sq = ch_sum + ipc * GN_MAX_SLAB;
+  float* ch_scale = ch_sq + ipc * GN_MAX_SLAB;
+  float* ch_shift = ch_scale + ipc * GN_MAX_SLAB;
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = a.C0 + a.C1;
   const int slabs = C / a.slab;
-  const int t = threadIdx.x;
+  const int il = threadIdx.x / tpi;                        // item within the CTA
+  const int t = threadIdx.x - il * tpi;                    // thread within the item
   const int crank = a.cs > 1 ? (int)cluster_ctarank() : 0;
-  const int item = (int)(blockIdx.x / a.cs);
+  const int item = a.cs > 1 ? (int)(blockIdx.x / a.cs) : (int)blockIdx.x * ipc + il;
+  const bool active = item < a.n_items;
   const int HWl = a.HW / a.cs;                           // pixels owned by this CTA
-  const int b = item / slabs, sl = item - b * slabs;
+  const int b = active ? item / slabs : 0, sl = active ? item - b * slabs : 0;
   const int c_base = sl * a.slab;
-  const int q = t % vpp;                                 // T % vpp == 0 -> fixed vector slot (8 channels) per thread
+  const int q = t % vpp;                                 // tpi % vpp == 0 -> fixed vector slot (8 channels) per thread
   const int cq = c_base + q * 8;
   const bf16* sp; int sC, sc;
   if (cq < a.C0) { sp = a.src0; sC = a.C0; sc = cq; } else { sp = a.src1; sC = a.C1; sc = cq - a.C0; }
   const long long pix0 = (long long)b * a.HW + (long long)crank * HWl;
-  const int p0 = t / vpp, pstep = T / vpp;               // this thread's pixels: p0 + k * pstep
-  const int nvec = HWl * vpp;
-  const uint32_t data_addr = smem_u32(gn_smem);
+  const int p0 = t / vpp, pstep = tpi / vpp;             // this thread's pixels: p0 + k * pstep
+  const int nvec = active ? HWl * vpp : 0;
+  const uint32_t data_addr = smem_u32(gn_smem) + (uint32_t)(il * a.data_bytes);
 
   {
     const bf16* lp = sp + (pix0 + p0) * sC + sc;
     const long long lstep = (long long)pstep * sC;
-    for (int v = t; v < nvec; v += T, lp += lstep) cp_async16(data_addr + (uint32_t)v * 16u, lp);
+    for (int v = t; v < nvec; v += tpi, lp += lstep) cp_async16(data_addr + (uint32_t)v * 16u, lp);
   }
   cp_async_wait_all();
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
 #pragma unroll 4
-  for (int v = t; v < nvec; v += T) {
+  for (int v = t; v < nvec; v += tpi) {
     const uint4 r = lds_u4(data_addr + (uint32_t)v * 16u);
     const __nv_bfloat162* h2 = (const __nv_bfloat162*)&r;
 #pragma unroll
@@ -103,30 +110,30 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) groupnorm_bf16_kernel(GnFastAr
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += __shfl_xor_sync(0xffffffffu, s[j], m); ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], m); }
     }
-    const int lane = t & 31, w = t >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane < vpp) {
       float* rp = red + (w * vpp + lane) * 17;
 #pragma unroll
       for (int j = 0; j < 8; ++j) { rp[j] = s[j]; rp[8 + j] = ss[j]; }
     }
   } else {
-    float* rp = red + t * 17;
+    float* rp = red + threadIdx.x * 17;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { rp[j] = s[j]; rp[8 + j] = ss[j]; }
   }
   __syncthreads();
-  for (int c = t; c < a.slab; c += T) {
-    // fixed-order sum of the partials that belong to channel c of the slab
+  for (int c = t; c < a.slab; c += tpi) {
+    // fixed-order sum of the partials that belong to channel c of this item's slab
     const int qq = c >> 3, j = c & 7;
     float ts = 0.f, tq = 0.f;
-    if (a.shfl) { for (int w = 0; w < n_warps; ++w) { const float* rp = red + (w * vpp + qq) * 17; ts += rp[j]; tq += rp[8 + j]; } }
-    else { for (int u = qq; u < T; u += vpp) { ts += red[u * 17 + j]; tq += red[u * 17 + 8 + j]; } }
-    ch_sum[c] = ts; ch_sq[c] = tq;
+    if (a.shfl) { for (int w = il * wpi; w < (il + 1) * wpi; ++w) { const float* rp = red + (w * vpp + qq) * 17; ts += rp[j]; tq += rp[8 + j]; } }
+    else { for (int u = il * tpi + qq; u < (il + 1) * tpi; u += vpp) { ts += red[u * 17 + j]; tq += red[u * 17 + 8 + j]; } }
+    ch_sum[il * GN_MAX_SLAB + c] = ts; ch_sq[il * GN_MAX_SLAB + c] = tq;
   }
   __syncthreads();
   if (a.cs > 1) {
     // combine the per-CTA channel sums across the cluster through distributed shared memory, in rank order
-    // (cluster CTAs always have >= 64 threads: one channel per thread)
+    // (cluster CTAs hold one item and have >= slab threads: one channel per thread)
     cluster_sync_all();
     float ts = 0.f, tq = 0.f;
     if (t < a.slab) {
@@ -139,10 +146,10 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) groupnorm_bf16_kernel(GnFastAr
     if (t < a.slab) { ch_sum[t] = ts; ch_sq[t] = tq; }
     __syncthreads();
   }
-  for (int c = t; c < a.slab; c += T) {
+  for (int c = t; c < a.slab; c += tpi) {
     const int g0 = (c / a.cpg) * a.cpg;
     float gs = 0.f, gq = 0.f;
-    for (int j = 0; j < a.cpg; ++j) { gs += ch_sum[g0 + j]; gq += ch_sq[g0 + j]; }
+    for (int j = 0; j < a.cpg; ++j) { gs += ch_sum[il * GN_MAX_SLAB + g0 + j]; gq += ch_sq[il * GN_MAX_SLAB + g0 + j]; }
     const float inv_n = 1.0f / (float)(a.cpg * a.HW);
     const float mean = gs * inv_n;
     const float var = fmaxf(gq * inv_n - mean * mean, 0.f);
@@ -155,16 +162,16 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) groupnorm_bf16_kernel(GnFastAr
       sc_ *= m; sh_ = sh_ * m + f[C + c_base + c];
     }
     if (a.silu) { sc_ *= 0.5f; sh_ *= 0.5f; }          // the activation works on h = y/2: silu(y) = h*tanh(h) + h
-    ch_scale[c] = sc_; ch_shift[c] = sh_;
+    ch_scale[il * GN_MAX_SLAB + c] = sc_; ch_shift[il * GN_MAX_SLAB + c] = sh_;
   }
   __syncthreads();
   float sc8[8], sh8[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc8[j] = ch_scale[q * 8 + j]; sh8[j] = ch_shift[q * 8 + j]; }
+  for (int j = 0; j < 8; ++j) { sc8[j] = ch_scale[il * GN_MAX_SLAB + q * 8 + j]; sh8[j] = ch_shift[il * GN_MAX_SLAB + q * 8 + j]; }
   bf16* op = a.out + (pix0 + p0) * C + cq;
   const long long ostep = (long long)pstep * C;
 #pragma unroll 4
-  for (int v = t; v < nvec; v += T, op += ostep) {
+  for (int v = t; v < nvec; v += tpi, op += ostep) {
     const uint4 r = lds_u4(data_addr + (uint32_t)v * 16u);
     const __nv_bfloat162* h2 = (const __nv_bfloat162*)&r;
     uint4 o4;
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(GN_MAX_THREADS) groupnorm_bf16_kernel(GnFastAr
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-struct GnGeom { int cpg, slab, threads, cs, shfl, data_bytes; size_t smem; bool ok; };
+struct GnGeom { int cpg, slab, threads, tpi, ipc, cs, shfl, data_bytes; size_t smem; bool ok; };
 
 static GnGeom gn_geometry(const Op& op) {
   GnGeom g{};
@@ -208,10 +215,13 @@ static GnGeom gn_geometry(const Op& op) {
   const int nvec = (int)(bytes / 16);
   int threads = ((nvec + 7) / 8 + unit - 1) / unit * unit;   // ~8 vectors per thread
   threads = std::min(std::max(threads, cs > 1 ? std::max(unit, (GN_MAX_SLAB + unit - 1) / unit * unit) : unit), GN_MAX_THREADS / unit * unit);
-  g.slab = slab; g.cs = cs; g.threads = threads; g.data_bytes = (int)bytes;
+  // small maps: several items per CTA so that a CTA still moves ~16 KB
+  int ipc = 1;
+  if (cs == 1) ipc = (int)std::max<long long>(1, std::min<long long>(GN_MAX_THREADS / threads, 16384 / std::max<long long>(bytes, 1)));
+  g.slab = slab; g.cs = cs; g.tpi = threads; g.ipc = ipc; g.threads = threads * ipc; g.data_bytes = (int)bytes;
   g.shfl = (vpp & (vpp - 1)) == 0 && vpp <= 32;
-  const int red_rows = g.shfl ? (threads / 32) * vpp : threads;
-  g.smem = (size_t)bytes + sizeof(float) * ((size_t)red_rows * 17 + 4 * GN_MAX_SLAB);
+  const int red_rows = g.shfl ? (g.threads / 32) * vpp : g.threads;
+  g.smem = (size_t)bytes * ipc + sizeof(float) * ((size_t)red_rows * 17 + 4 * (size_t)ipc * GN_MAX_SLAB);
   g.ok = true;
   return g;
 }
@@ -236,7 +246,7 @@ int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   }
   const GnGeom g = gn_geometry(op);
   GnFastArgs a{};
-  a.cpg = g.cpg; a.slab = g.slab; a.cs = g.cs; a.shfl = g.shfl; a.data_bytes = g.data_bytes;
+  a.cpg = g.cpg; a.slab = g.slab; a.cs = g.cs; a.shfl = g.shfl; a.data_bytes = g.data_bytes; a.tpi = g.tpi; a.ipc = g.ipc;
   a.src0 = (const bf16*)tensor_ptr(e, op.src0, B); a.C0 = e.tensors[op.src0].C;
   a.src1 = (const bf16*)tensor_ptr(e, op.src1, B); a.C1 = op.src1 >= 0 ? e.tensors[op.src1].C : 0;
   a.HW = op.Hin * op.Win;
@@ -244,16 +254,8 @@ int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   a.gamma = op.gamma; a.beta = op.beta; a.eps = 1e-5f; a.silu = op.silu;
   if (op.film) { a.film = e.emb_out + op.emb_off; a.film_stride = e.emb_total; a.film_row = e.row_of_sample; }
   a.out = (bf16*)tensor_ptr(e, op.out, B);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(a.n_items * g.cs));
-  cfg.blockDim = dim3(g.threads);
-  cfg.dynamicSmemBytes = g.smem;
-  cfg.stream = st;
-  cudaLaunchAttribute lattr[1];
-  lattr[0].id = cudaLaunchAttributeClusterDimension;
-  lattr[0].val.clusterDim.x = g.cs; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
-  cfg.attrs = lattr; cfg.numAttrs = g.cs > 1 ? 1 : 0;
-  if (cudaLaunchKernelEx(&cfg, groupnorm_bf16_kernel, a) != cudaSuccess) { e.err = "groupnorm launch failed"; return CFM_ERR_CUDA; }
+  LaunchCfg lc(dim3((unsigned)(g.cs > 1 ? a.n_items * g.cs : (a.n_items + g.ipc - 1) / g.ipc)), dim3(g.threads), g.smem, st, g.cs, pdl_enabled());
+  if (cudaLaunchKernelEx(&lc.cfg, groupnorm_bf16_kernel, a) != cudaSuccess) { e.err = "groupnorm launch failed"; return CFM_ERR_CUDA; }
   return 0;
 }
 

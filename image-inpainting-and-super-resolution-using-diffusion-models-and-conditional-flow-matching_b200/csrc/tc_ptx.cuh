@@ -58,6 +58,11 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// Programmatic dependent launch: let the next kernel of the stream start its prologue / wait until every
+// predecessor grid has completed and its memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // true in exactly one (converged) lane of the warp.  Unlike `lane == 0`, the compiler knows a single thread runs the
 // guarded code, so tcgen05 / TMA operands move to uniform registers without a per-lane ELECT/R2UR loop.
 __device__ __forceinline__ bool elect_one() {
