@@ -25,7 +25,7 @@ namespace cfm {
 void* tensor_ptr(const Engine& e, int id, int B);
 
 constexpr int TC_BLOCK_M = 128;         // rows of one UMMA; a CTA tile is 128 * mh rows (mh = 1 or 2 M-halves)
-constexpr int TC_BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_BLOCK_K = 64;          // widest K-iteration: 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB per M-half
 #ifndef CFM_TC_EPI_WARPS
 #define CFM_TC_EPI_WARPS 8
@@ -57,6 +57,8 @@ struct TcParams {
   int block_n, Cout;
   int a_slot_bytes, b_slot_bytes, n_a, n_b;   // operand rings
   int a_tile_bytes, a_halo_bytes;             // bytes of a plain / halo A load
+  int kc;                      // channels per K-iteration: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
+  int valid_rows;              // bw*bh*bn: rows of the tile that carry pixels (< 128*mh for maps such as 28x28)
   const float* bias;
   const float* emb; int emb_stride; const int* emb_row;
   const bf16* res0; const bf16* res1; int R0, R1;
@@ -67,7 +69,9 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers (shared by the single-CTA and the CTA-pair kernel)
 // ------------------------------------------------------------------------------------------------
-struct EpiRow { bool valid; int n, h, w; long long pix; };
+// One accumulator row (= output pixel) as the epilogue sees it.  gpix / gvalid describe the 4 rows of this lane's
+// aligned lane group (rows (lane & ~3) + k), which the transposed loads / stores touch.
+struct EpiRow { bool valid; int n, h, w; long long pix; long long gpix[4]; uint32_t gvalid; };
 
 struct TileCoord { int nt, ph, tw, th, tb; };
 // tile index -> (N tile, sub-pixel phase, spatial tile).  N tile and phase vary fastest, so the CTAs that share an
@@ -102,31 +106,33 @@ __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCo
   EpiRow r;
   const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
   r.n = c.tb * p.bn + ni; r.h = c.th * p.bh + hi; r.w = c.tw * p.bw + wi;
-  r.valid = r.n < p.B;
+  r.valid = row < p.valid_rows && r.n < p.B && r.h < p.H;
   if (p.n_phase == 4) {   // rows index the source grid; this phase's outputs interleave into the 2H x 2W map
     r.h = 2 * r.h + (c.ph >> 1); r.w = 2 * r.w + (c.ph & 1);
     r.pix = ((long long)r.n * (2 * p.H) + r.h) * (2 * p.W) + r.w;
   } else {
     r.pix = ((long long)r.n * p.H + r.h) * p.W + r.w;
   }
+  // pixel index / validity of the 4 rows of this lane's group (any box shape: rows of a group need not be neighbours)
+  const int lane = threadIdx.x & 31, g0 = lane & ~3;
+  r.gvalid = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    r.gpix[k] = __shfl_sync(0xffffffffu, r.pix, g0 + k);
+    r.gvalid |= (uint32_t)__shfl_sync(0xffffffffu, (int)r.valid, g0 + k) << k;
+  }
   return r;
-}
-// pixel index of row (lane & ~3) + k of this lane's group: the 4 rows of a group are consecutive output pixels
-// (box width % 4 == 0), two apart in the interleaved map of a sub-pixel phase
-__device__ __forceinline__ long long epi_group_pix(const TcParams& p, const EpiRow& r, int lane, int k) {
-  const int step = p.n_phase == 4 ? 2 : 1;
-  return r.pix + (long long)((k - (lane & 3)) * step);
 }
 // issue the residual loads of one 32-channel chunk early (they are the only DRAM-latency operand of the epilogue),
 // in the transposed (coalesced) pattern: res[k] = 8 channels (lane & 3) of row (lane & ~3) + k
 __device__ __forceinline__ void epi_load_res(const TcParams& p, const EpiRow& r, int lane, int cg, uint4 (&res)[4]) {
-  if (p.res0 && r.valid) {
+  if (p.res0) {
     const int cj = cg + 8 * (lane & 3);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const long long pix = epi_group_pix(p, r, lane, k);
+      const long long pix = r.gpix[k];
       const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cj : p.res1 + pix * p.R1 + (cj - p.R0);
-      res[k] = __ldg((const uint4*)rp);
+      res[k] = ((r.gvalid >> k) & 1u) ? __ldg((const uint4*)rp) : make_uint4(0, 0, 0, 0);
     }
   }
 }
@@ -181,11 +187,10 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
     for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
   }
   quad_transpose(o, lane);
-  if (r.valid) {
-    const int cj = cg + 8 * (lane & 3);
+  const int cj = cg + 8 * (lane & 3);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) *(uint4*)(p.out + epi_group_pix(p, r, lane, k) * p.Cout + cj) = o[k];
-  }
+  for (int k = 0; k < 4; ++k)
+    if ((r.gvalid >> k) & 1u) *(uint4*)(p.out + r.gpix[k] * p.Cout + cj) = o[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -253,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int dx = xi - 1 + (sg.ks == 2 ? (tc.ph & 1) : 0);
                 mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
                 mbar_expect_tx(&fullA[ra.slot], p.a_halo_bytes);
-                tma_load_4d(ring_a + ra.slot * p.a_slot_bytes, map, &fullA[ra.slot], ch * TC_BLOCK_K, w0 + dx, yorg, n0);
+                tma_load_4d(ring_a + ra.slot * p.a_slot_bytes, map, &fullA[ra.slot], ch * p.kc, w0 + dx, yorg, n0);
                 ra.next();
                 for (int yi = 0; yi < sg.ks; ++yi, brow += p.Cout) {
                   mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
@@ -269,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               for (int ch = 0; ch < sg.n_chunks; ++ch, brow += p.Cout) {
                 mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
                 mbar_expect_tx(&fullA[ra.slot], p.a_tile_bytes);
-                tma_load_4d(ring_a + ra.slot * p.a_slot_bytes, map, &fullA[ra.slot], ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+                tma_load_4d(ring_a + ra.slot * p.a_slot_bytes, map, &fullA[ra.slot], ch * p.kc, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
                 ra.next();
                 mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
                 mbar_expect_tx(&fullB[rb.slot], p.b_slot_bytes);
@@ -284,7 +289,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc(TC_BLOCK_M, p.block_n);
-    const uint32_t row_step = (uint32_t)(p.bw * 128) >> 4;        // one image row of a halo slot, in descriptor units
+    const uint32_t row_step = (uint32_t)(p.bw * p.kc * 2) >> 4;   // one image row of a halo slot, in descriptor units
+    const uint32_t half_step = (uint32_t)(TC_BLOCK_M * p.kc * 2) >> 4;   // second M-half of an A slot
+    const int n_kk = p.kc >> 4;
     Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -303,14 +310,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(&fullB[rb.slot], rb.phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t adesc = make_desc_sw128(sa) + (uint64_t)(sg.halo ? (uint32_t)j * row_step : 0u);
-              const uint64_t bdesc = make_desc_sw128(smem_u32(ring_b + rb.slot * p.b_slot_bytes));
+              const uint64_t adesc = make_desc_k(sa, p.kc) + (uint64_t)(sg.halo ? (uint32_t)j * row_step : 0u);
+              const uint64_t bdesc = make_desc_k(smem_u32(ring_b + rb.slot * p.b_slot_bytes), p.kc);
 #pragma unroll
               for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk) {
-                const uint32_t accum = (kdone > 0 || kk > 0) ? 1u : 0u;
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
-                if (p.mh == 2)   // second M-half re-uses the same B tile: halves the B traffic per FLOP
-                  umma_bf16(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)(TC_A_BYTES >> 4) + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+                if (kk < n_kk) {
+                  const uint32_t accum = (kdone > 0 || kk > 0) ? 1u : 0u;
+                  umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+                  if (p.mh == 2)   // second M-half re-uses the same B tile: halves the B traffic per FLOP
+                    umma_bf16(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)half_step + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+                }
               }
               umma_commit(&emptyB[rb.slot]);                      // B slot reusable once these MMAs retire
               if (j == G - 1) umma_commit(&emptyA[ra.slot]);      // last view of this A slot
@@ -447,7 +456,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const int dx = xi - 1 + (sg.ks == 2 ? (tc.ph & 1) : 0);
                 mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
                 if (leader) mbar_expect_tx(&fullA[ra.slot], 2 * p.a_halo_bytes);      // bytes of BOTH CTAs
-                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * TC_BLOCK_K, w0 + dx, yorg, n0);
+                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * p.kc, w0 + dx, yorg, n0);
                 ra.next();
                 for (int yi = 0; yi < sg.ks; ++yi, brow += p.Cout) {
                   mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
@@ -463,7 +472,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               for (int ch = 0; ch < sg.n_chunks; ++ch, brow += p.Cout) {
                 mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
                 if (leader) mbar_expect_tx(&fullA[ra.slot], 2 * p.a_tile_bytes);
-                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * TC_BLOCK_K, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * p.kc, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
                 ra.next();
                 mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
                 if (leader) mbar_expect_tx(&fullB[rb.slot], 2 * p.b_slot_bytes);
@@ -479,7 +488,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       const uint32_t idesc = make_idesc(256, p.block_n);
-      const uint32_t row_step = (uint32_t)(p.bw * 128) >> 4;
+      const uint32_t row_step = (uint32_t)(p.bw * p.kc * 2) >> 4;
+      const int n_kk = p.kc >> 4;
       Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       int acc = 0; uint32_t acc_phase = 0;
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
@@ -498,11 +508,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               mbar_wait(&fullB[rb.slot], rb.phase);
               tc_fence_after();
               if (elect_one()) {
-                const uint64_t adesc = make_desc_sw128(sa) + (uint64_t)(sg.halo ? (uint32_t)j * row_step : 0u);
-                const uint64_t bdesc = make_desc_sw128(smem_u32(ring_b + rb.slot * p.b_slot_bytes));
+                const uint64_t adesc = make_desc_k(sa, p.kc) + (uint64_t)(sg.halo ? (uint32_t)j * row_step : 0u);
+                const uint64_t bdesc = make_desc_k(smem_u32(ring_b + rb.slot * p.b_slot_bytes), p.kc);
 #pragma unroll
                 for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk)
-                  umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kdone > 0 || kk > 0) ? 1u : 0u);
+                  if (kk < n_kk) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kdone > 0 || kk > 0) ? 1u : 0u);
                 umma_commit_2sm(&emptyB[rb.slot], 3);                         // both CTAs may refill this B slot
                 if (j == G - 1) umma_commit_2sm(&emptyA[ra.slot], 3);         // last view of this A slot
                 if (kdone == p.total_k - 1) umma_commit_2sm(&tfull_bar[acc], 3);   // both CTAs' epilogues may drain
@@ -570,6 +580,7 @@ struct TcConvPlan {
   int n_phase = 1, Hg = 0, Wg = 0;      // sub-pixel phases (4 for the folded upsample) and the grid the M tiles walk
   bool pair = false;                    // CTA-pair (cta_group::2) kernel
   int a_slot_bytes = 0, b_slot_bytes = 0, n_a = 0, n_b = 0, a_tile_bytes = 0, a_halo_bytes = 0;
+  int kc = 64, valid_rows = 0;
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
@@ -609,9 +620,9 @@ bool tc_conv_supported(const Engine& e, const Op& op) {
   if (op.ks != 1 && op.ks != 3) return false;
   if (!op.out_is_output && (pick_block_n(op.Cout) == 0 || op.Cout > TC_MAX_COUT)) return false;
   const int Hg = op.ups ? op.Hin : op.Hout, Wg = op.ups ? op.Win : op.Wout;      // grid the M tiles walk
-  if (!pow2(Hg) || !pow2(Wg) || Wg > 128 || Hg > 128 || Wg < 4) return false;   // epilogue groups 4 consecutive pixels of a row
+  if (Wg > 128 || Hg < 1 || Wg < 1) return false;            // a tile row-block spans the full width when W is not a power of two
   if (op.stride == 2 && (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout || 2 * std::min(op.Wout, 128) > 256)) return false;
-  auto chan_ok = [&](int id) { return id < 0 || e.tensors[id].C % TC_BLOCK_K == 0; };
+  auto chan_ok = [&](int id) { return id < 0 || e.tensors[id].C % 32 == 0; };   // K-iterations of 64 or 32 channels
   if (op.src1 >= 0) return false;                            // main operand is always a single (GN-output) tensor
   if (!chan_ok(op.src0) || !chan_ok(op.skip0) || !chan_ok(op.skip1)) return false;
   auto res_ok = [&](int id) { return id < 0 || e.tensors[id].C % 32 == 0; };
@@ -643,32 +654,40 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   pl->pair = !op.out_is_output && pl->block_n >= pair_min_n && !env_off("CFM_DISABLE_TC_2CTA");
   pl->mh = (!pl->pair && pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;
   const int rows = 128 * pl->mh;
+  // K-iteration width: 64 channels (SWIZZLE_128B rows) when every operand allows it, else 32 (SWIZZLE_64B)
+  pl->kc = 64;
+  for (int id : {op.src0, op.skip0, op.skip1}) if (id >= 0 && e.tensors[id].C % 64) pl->kc = 32;
+  const int kc = pl->kc, row_bytes = kc * 2;
   // sub-pixel decomposition of (nearest x2 upsample -> 3x3 conv): the M tiles walk the SOURCE grid, four phases,
   // each a 2x2 conv whose taps are sums of the 3x3 taps that land on the same source pixel (4/9 of the MACs,
   // and the upsampled tensor is never materialised)
   pl->n_phase = op.ups ? 4 : 1;
   const int Hg = op.ups ? op.Hin : op.Hout, Wg = op.ups ? op.Win : op.Wout;
   pl->Hg = Hg; pl->Wg = Wg;
-  pl->bw = std::min(Wg, rows);
+  // tile box: full image rows (bw = W; any W <= 128), bh rows of them, and bn whole images when an image is
+  // smaller than the tile.  bw*bh*bn <= rows; the unused accumulator rows (e.g. 16 of 128 at 28x28) are ignored.
+  pl->bw = Wg;
   pl->bh = std::min(Hg, rows / pl->bw);
-  pl->bn = rows / (pl->bw * pl->bh);
+  pl->bn = pl->bh == Hg ? std::max(1, rows / (pl->bw * pl->bh)) : 1;
+  pl->valid_rows = pl->bw * pl->bh * pl->bn;
   const int eks = op.ups ? 2 : ks;          // taps per axis the kernel walks
-  // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous) and be 8-row aligned per image row
-  bool halo = eks > 1 && op.stride == 1 && pl->bn == 1 && pl->bw >= 8 && !env_off("CFM_DISABLE_TC_HALO");
-  pl->a_tile_bytes = rows * 128;
-  pl->a_halo_bytes = (rows + 2 * pl->bw) * 128;
-  pl->b_slot_bytes = (pl->pair ? pl->block_n / 2 : pl->block_n) * 128;
-  pl->a_slot_bytes = halo ? pl->a_halo_bytes : pl->a_tile_bytes;
-  if (halo && !size_rings(pl, eks)) { halo = false; pl->a_slot_bytes = pl->a_tile_bytes; }
+  // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous), fill its rows exactly and
+  // an image row must be a whole number of 8-row swizzle atoms
+  bool halo = eks > 1 && op.stride == 1 && pl->bn == 1 && pl->bw % 8 == 0 && pl->valid_rows == rows && !env_off("CFM_DISABLE_TC_HALO");
+  pl->a_tile_bytes = pl->valid_rows * row_bytes;
+  pl->a_halo_bytes = (rows + 2 * pl->bw) * row_bytes;
+  pl->b_slot_bytes = (pl->pair ? pl->block_n / 2 : pl->block_n) * row_bytes;
+  pl->a_slot_bytes = halo ? pl->a_halo_bytes : rows * row_bytes;
+  if (halo && !size_rings(pl, eks)) { halo = false; pl->a_slot_bytes = rows * row_bytes; }
   if (!halo && !size_rings(pl, 1)) { e.err = "conv tile does not fit the shared-memory rings: " + op.name; delete pl; return CFM_ERR_INVALID; }
-  pl->seg[0] = {0, Cin / TC_BLOCK_K, eks, op.stride, halo ? 1 : 0}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
-  if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / TC_BLOCK_K, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
-  if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / TC_BLOCK_K, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
-  const int n_chunks = Cin / TC_BLOCK_K;
-  pl->total_k = eks * eks * n_chunks + op.Cskip / TC_BLOCK_K;
+  pl->seg[0] = {0, Cin / kc, eks, op.stride, halo ? 1 : 0}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
+  if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / kc, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
+  if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / kc, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
+  const int n_chunks = Cin / kc;
+  pl->total_k = eks * eks * n_chunks + op.Cskip / kc;
   // pack: [phase] K-iteration-major, [Cout][64] per K-iteration, in the producer's order:
   //   halo:  chunk -> x tap -> y tap        plain:  tap (y-major) -> chunk        then the 1x1 skip chunks
-  std::vector<bf16> packed((size_t)pl->n_phase * pl->total_k * Cout * TC_BLOCK_K);
+  std::vector<bf16> packed((size_t)pl->n_phase * pl->total_k * Cout * kc);
   // weight of main-operand channel c, output o, for walked tap (yi, xi) of phase ph
   auto tap_weight = [&](int ph, int yi, int xi, int c, int o) -> float {
     if (o >= op.Cout) return 0.f;
@@ -686,8 +705,8 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   size_t kiter = 0;
   auto put = [&](int ph, int yi, int xi, int ch) {
     for (int o = 0; o < Cout; ++o)
-      for (int j = 0; j < TC_BLOCK_K; ++j)
-        packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(tap_weight(ph, yi, xi, ch * TC_BLOCK_K + j, o));
+      for (int j = 0; j < kc; ++j)
+        packed[(kiter * Cout + o) * kc + j] = __float2bfloat16(tap_weight(ph, yi, xi, ch * kc + j, o));
     ++kiter;
   };
   for (int ph = 0; ph < pl->n_phase; ++ph) {
@@ -699,10 +718,10 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
       for (int tap = 0; tap < eks * eks; ++tap)
         for (int ch = 0; ch < n_chunks; ++ch) put(ph, tap / eks, tap % eks, ch);
     }
-    for (int ch = 0; ch < op.Cskip / TC_BLOCK_K; ++ch, ++kiter)
+    for (int ch = 0; ch < op.Cskip / kc; ++ch, ++kiter)
       for (int o = 0; o < Cout; ++o)
-        for (int j = 0; j < TC_BLOCK_K; ++j)
-          packed[(kiter * Cout + o) * TC_BLOCK_K + j] = __float2bfloat16(ws[(size_t)o * op.Cskip + ch * TC_BLOCK_K + j]);
+        for (int j = 0; j < kc; ++j)
+          packed[(kiter * Cout + o) * kc + j] = __float2bfloat16(ws[(size_t)o * op.Cskip + ch * kc + j]);
   }
   void* d = nullptr;
   if (cudaMalloc(&d, packed.size() * sizeof(bf16)) != cudaSuccess) { e.err = "cudaMalloc(packed conv weights) failed"; delete pl; return CFM_ERR_OOM; }
@@ -734,26 +753,27 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
 static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
   TcConvPlan* pl = op.tc;
   std::memset(m, 0, sizeof(*m));
+  const CUtensorMapSwizzle swz = pl->kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < pl->n_seg; ++s) {
     const TensorDesc& t = e.tensors[pl->seg_tensor[s]];
     const int st = pl->seg[s].stride;
     const int box_h = pl->seg[s].halo ? pl->bh + 2 : pl->bh * st;
     cuuint64_t dims[4] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)t.C * 2, (cuuint64_t)t.W * t.C * 2, (cuuint64_t)t.H * t.W * t.C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->bw * st), (cuuint32_t)box_h, (cuuint32_t)pl->bn};
+    cuuint32_t box[4] = {(cuuint32_t)pl->kc, (cuuint32_t)(pl->bw * st), (cuuint32_t)box_h, (cuuint32_t)pl->bn};
     cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
     CUresult r = g_encode(&m->a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, tensor_ptr(e, pl->seg_tensor[s], B), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(A) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
   }
   for (int s = pl->n_seg; s < 3; ++s) m->a[s] = m->a[0];
-  cuuint64_t dims[2] = {(cuuint64_t)TC_BLOCK_K, (cuuint64_t)pl->n_phase * pl->total_k * pl->cout_pad};
-  cuuint64_t strides[1] = {(cuuint64_t)TC_BLOCK_K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(pl->b_slot_bytes / 128)};
+  cuuint64_t dims[2] = {(cuuint64_t)pl->kc, (cuuint64_t)pl->n_phase * pl->total_k * pl->cout_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)pl->kc * 2};
+  cuuint32_t box[2] = {(cuuint32_t)pl->kc, (cuuint32_t)(pl->b_slot_bytes / (pl->kc * 2))};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(&m->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->w_packed, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(B) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
   return 0;
@@ -774,7 +794,8 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.total_k = pl->total_k;
   p.B = B; p.H = pl->Hg; p.W = pl->Wg; p.n_phase = pl->n_phase;
   p.bw = pl->bw; p.bh = pl->bh; p.bn = pl->bn; p.mh = pl->mh;
-  p.tiles_w = pl->Wg / pl->bw; p.tiles_h = pl->Hg / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
+  p.tiles_w = pl->Wg / pl->bw; p.tiles_h = (pl->Hg + pl->bh - 1) / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
+  p.kc = pl->kc; p.valid_rows = pl->valid_rows;
   p.tiles_n = pl->cout_pad / pl->block_n;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n * p.n_phase;
   p.block_n = pl->block_n; p.Cout = pl->cout_pad;

@@ -116,6 +116,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major descriptor for rows of `kc` bf16: kc = 64 -> 128-byte rows, SWIZZLE_128B (layout 2, 1024 B atoms);
+// kc = 32 -> 64-byte rows, SWIZZLE_64B (layout 4, 512 B atoms).  SBO = 8 rows.
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, int kc) {
+  const uint64_t sbo = (uint64_t)((kc * 16) >> 4), layout = kc == 64 ? 2ull : 4ull;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
