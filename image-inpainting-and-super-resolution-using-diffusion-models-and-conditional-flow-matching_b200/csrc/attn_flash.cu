@@ -1,0 +1,279 @@
+// Attention core for any sequence length on tcgen05/TMEM (AttentionBlock of unet.py:424-483 at shapes the
+// fixed T = 256 kernel of attn_tc.cu does not take: MNIST 28x28 -> T = 784 with one 32-wide head, 7x7 -> T = 49, ...).
+//
+//   a = softmax((q s)^T (k s)) v,  s = ch^-1/4, per (sample, head); head width D = 32 or 64.
+//
+// One CTA per (sample, head, 128-query tile); the keys are walked in blocks of 128 with an online softmax:
+//   S_j = Q K_j^T          one UMMA chain (128 x 128 x D) into TMEM
+//   thread r owns query row r: block max / running max, p = 2^(s - m), running sum; P_j (bf16) goes to shared
+//   memory in the swizzled K-major layout                                   (two tcgen05.ld passes over S_j)
+//   O_j = P_j V_j          second UMMA chain (V consumed as an MN-major operand straight from its NHWC rows)
+//   o = o * 2^(m_old - m_new) + O_j   in registers (D fp32 per thread)
+// K_{j+1} / V_{j+1} arrive by TMA (3-D map {3C, T, B}: rows past T are zero-filled, and masked) while block j is
+// processed; S_{j+1} is issued together with O_j so the tensor pipe overlaps the softmax.  No atomics; a sample's
+// result does not depend on its batch.
+#include <cstring>
+#include <map>
+#include "engine.h"
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace cfm {
+
+void* tensor_ptr(const Engine& e, int id, int B);
+
+constexpr int AF_M = 128, AF_BK = 128;
+constexpr int AF_Q_OFF = 0, AF_K_OFF = 16384, AF_V_OFF = 49152, AF_P_OFF = 81920, AF_BAR_OFF = 114688;
+constexpr int AF_SMEM = AF_BAR_OFF + 128 + 1024;
+
+struct AttnFlashParams { int T, heads, C, new_order, n_kv; float scale_log2; bf16* out; };
+
+__device__ __forceinline__ float af_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constant__ CUtensorMap map, const AttnFlashParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar_q = (uint64_t*)(smem + AF_BAR_OFF);
+  uint64_t* bar_k = bar_q + 1;      // [2]
+  uint64_t* bar_v = bar_q + 3;      // [2]
+  uint64_t* bar_s = bar_q + 5;
+  uint64_t* bar_o = bar_q + 6;
+  uint32_t* tmem_slot = (uint32_t*)(bar_q + 7);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
+  const int qcol = p.new_order ? h * D : h * 3 * D;
+  const int kcol = p.new_order ? p.C + h * D : h * 3 * D + D;
+  const int vcol = p.new_order ? 2 * p.C + h * D : h * 3 * D + 2 * D;
+  constexpr int ROWB = D * 2;                 // bytes of one q / k / v row
+  constexpr int TILE_B = 128 * ROWB;          // one 128-row operand tile
+
+  pdl_launch_dependents();
+  if (tid == 0) {
+    prefetch_tmap(&map);
+    for (int i = 0; i < 7; ++i) mbar_init(bar_q + i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+
+  const uint32_t idesc_s = make_idesc(AF_M, AF_BK);
+  const uint32_t idesc_o = make_idesc_major(AF_M, D, 0, 1);
+  const uint32_t q_addr = smem_u32(smem + AF_Q_OFF), p_addr = smem_u32(smem + AF_P_OFF);
+
+  // S_j = Q K_j^T (one elected thread)
+  auto issue_s = [&](int j) {
+    const uint64_t ad = make_desc_k(q_addr, D), bd = make_desc_k(smem_u32(smem + AF_K_OFF + (j & 1) * 16384), D);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k) umma_bf16(tmem_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_s, k > 0);
+    umma_commit(bar_s);
+  };
+  auto load_kv = [&](int j) {
+    const int buf = j & 1;
+    mbar_expect_tx(&bar_k[buf], TILE_B);
+    tma_load_3d(smem + AF_K_OFF + buf * 16384, &map, &bar_k[buf], kcol, j * AF_BK, b);
+    mbar_expect_tx(&bar_v[buf], TILE_B);
+    tma_load_3d(smem + AF_V_OFF + buf * 16384, &map, &bar_v[buf], vcol, j * AF_BK, b);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, TILE_B);
+      tma_load_3d(smem + AF_Q_OFF, &map, bar_q, qcol, mt * AF_M, b);
+      load_kv(0);
+      if (p.n_kv > 1) load_kv(1);
+    }
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_k[0], 0);
+    tc_fence_after();
+    if (elect_one()) issue_s(0);
+    __syncwarp();
+  }
+
+  const int r = tid;                           // query row of this thread = TMEM lane
+  const uint32_t t_row = ((uint32_t)(warp * 32) << 16);
+  float m_run = -INFINITY, l_run = 0.f;        // running max (scaled to log2 units) and sum
+  float o[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) o[i] = 0.f;
+  uint8_t* prow = smem + AF_P_OFF + r * 128;
+
+  for (int j = 0; j < p.n_kv; ++j) {
+    const int kv0 = j * AF_BK;
+    const int n_valid = min(AF_BK, p.T - kv0);           // keys of this block that exist
+    // ---- pass 1: block max ----
+    mbar_wait(bar_s, j & 1);
+    tc_fence_after();
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < AF_BK; c0 += 32) {
+      if (c0 >= n_valid) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_s + t_row + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+    const float m_new = fmaxf(m_run, mx * p.scale_log2);
+    const float alpha = af_ex2(m_run - m_new);           // 0 for the first block (m_run = -inf)
+    m_run = m_new;
+    // ---- pass 2: p = 2^(s*scale - m), row sum, P -> shared (bf16, K-major SWIZZLE_128B, 64-key sub-tiles) ----
+    float sum = 0.f;
+    for (int c0 = 0; c0 < AF_BK; c0 += 32) {
+      uint32_t v[32];
+      if (c0 < n_valid) { tmem_ld32(tmem_s + t_row + (uint32_t)c0, v); tmem_ld_wait(); }
+      uint8_t* pchunk = prow + (c0 >> 6) * 16384;
+      const int c16 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o4;
+        __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = c0 + i * 8 + 2 * q;
+          const float e0 = c < n_valid ? af_ex2(fmaf(__uint_as_float(v[i * 8 + 2 * q]), p.scale_log2, -m_new)) : 0.f;
+          const float e1 = c + 1 < n_valid ? af_ex2(fmaf(__uint_as_float(v[i * 8 + 2 * q + 1]), p.scale_log2, -m_new)) : 0.f;
+          sum += e0 + e1;
+          o2[q] = __floats2bfloat162_rn(e0, e1);
+        }
+        *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+      }
+    }
+    l_run = l_run * alpha + sum;
+    fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();              // every row of P written, every thread done reading S_j
+    if (warp == 0) {
+      mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
+      if (j + 1 < p.n_kv) mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t vbase = smem_u32(smem + AF_V_OFF + (j & 1) * 16384);
+#pragma unroll
+        for (int k = 0; k < AF_BK / 16; ++k) {
+          const uint64_t ad = make_desc_k(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 64);
+          const uint64_t bd = make_desc_mn(vbase + k * 16 * ROWB, 1024, D);
+          umma_bf16(tmem_o, ad, bd, idesc_o, k > 0);
+        }
+        umma_commit(bar_o);
+        if (j + 1 < p.n_kv) issue_s(j + 1);   // overlaps the o-update below and the next block's TMA wait
+      }
+      __syncwarp();
+    }
+    // ---- o = o * alpha + O_j ----
+    mbar_wait(bar_o, j & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + t_row + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, __uint_as_float(v[i]));
+    }
+    // K_j / V_j buffers are free (S_j and O_j have completed): fetch block j + 2 into them
+    if (warp == 0 && j + 2 < p.n_kv) {
+      if (elect_one()) load_kv(j + 2);
+      __syncwarp();
+    }
+    tc_fence_before();            // order this thread's TMEM reads before the next block's MMAs (issued after the next sync)
+  }
+
+  // ---- normalise, store (4 lanes write one row's 64 B run per instruction) ----
+  const float inv = 1.0f / l_run;
+  const int row_in_tile = (r & ~3);
+  bf16* op = p.out + ((long long)b * p.T + mt * AF_M + row_in_tile) * p.C + h * D + 8 * (lane & 3);
+#pragma unroll
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    uint4 ov[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162* o2 = (__nv_bfloat162*)&ov[i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(o[c0 + i * 8 + 2 * q] * inv, o[c0 + i * 8 + 2 * q + 1] * inv);
+    }
+    quad_transpose(ov, lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (mt * AF_M + row_in_tile + k < p.T) *(uint4*)(op + (long long)k * p.C + c0) = ov[k];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct AttnFlashPlan { std::map<int, CUtensorMap> maps; };
+static std::map<const Op*, AttnFlashPlan> g_flash_plans;   // keyed by op address (ops vector is stable after build)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_flash_encode = nullptr;
+
+bool attn_flash_supported(const Engine& e, const Op& op) {
+  if (!e.bf16 || op.kind != OP_ATTN) return false;
+  const char* off = getenv("CFM_DISABLE_FLASH_ATTN");
+  if (off && off[0] == '1') return false;
+  return (op.ch == 32 || op.ch == 64) && op.Cin % 8 == 0;
+}
+
+int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
+  if (!g_flash_encode) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
+    g_flash_encode = (EncodeTiledFn)fn;
+    if (cudaFuncSetAttribute(attn_flash_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess) {
+      e.err = "cudaFuncSetAttribute(attn_flash_kernel) failed"; return CFM_ERR_CUDA;
+    }
+  }
+  const int T = op.Hin * op.Win;
+  AttnFlashPlan& pl = g_flash_plans[&op];
+  const void* qkv = tensor_ptr(e, op.src0, B);
+  auto it = pl.maps.find(B);
+  if (it == pl.maps.end()) {
+    CUtensorMap m;
+    const int C3 = 3 * op.Cin;
+    cuuint64_t dims[3] = {(cuuint64_t)C3, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C3 * 2, (cuuint64_t)T * C3 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)op.ch, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_flash_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                op.ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(qkv, flash) failed"; return CFM_ERR_CUDA; }
+    it = pl.maps.emplace(B, m).first;
+  }
+  AttnFlashParams p{};
+  p.T = T; p.heads = op.heads; p.C = op.Cin; p.new_order = e.cfg.use_new_attention_order;
+  p.n_kv = (T + AF_BK - 1) / AF_BK;
+  p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
+  p.out = (bf16*)tensor_ptr(e, op.out, B);
+  LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, B * op.heads), dim3(128), AF_SMEM, st, 1, pdl_enabled());
+  cudaError_t ce = op.ch == 64 ? cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<64>, it->second, p)
+                               : cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<32>, it->second, p);
+  if (ce != cudaSuccess) { e.err = std::string("attn_flash_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
+  return 0;
+}
+
+void attn_flash_release(Engine& e) {
+  for (const Op& op : e.ops) {
+    auto it = g_flash_plans.find(&op);
+    if (it != g_flash_plans.end()) it->second.maps.clear();
+  }
+}
+
+void attn_flash_forget(Engine& e) {
+  for (const Op& op : e.ops) g_flash_plans.erase(&op);
+}
+
+}  // namespace cfm

@@ -415,6 +415,7 @@ static int ensure_batch(Engine& e, int B) {
     if (e.arena) { cudaFree(e.arena); e.arena = nullptr; }
     tc_conv_release(e);   // tensor maps hold arena addresses
     attn_tc_release(e);
+    attn_flash_release(e);
     drop_graphs(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
     CU_CHECK(e, cudaMalloc(&e.arena, bytes));
@@ -553,6 +554,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
       case OP_ATTN: {
         if (attn_tc_supported(e, op)) {
           int rc = attn_tc_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
+        if (attn_flash_supported(e, op)) {
+          int rc = attn_flash_launch(e, op, B, st);
           if (rc) return rc;
           e.launches++;
           break;
@@ -728,6 +735,7 @@ void cfm_engine_destroy(cfm_engine* h) {
   cudaSetDevice(e.device);
   tc_conv_release(e);
   attn_tc_forget(e);
+  attn_flash_forget(e);
   drop_graphs(e);
   for (void* p : {(void*)e.x_work, (void*)e.cond_work, (void*)e.img_work, (void*)e.y_work, (void*)e.t_table, (void*)e.dt_table,
                   (void*)e.ddpm_table, (void*)e.step_counter})

@@ -54,6 +54,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -132,6 +137,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // 8 rows form the 1024 B swizzle atom; SBO = stride between 8-row K groups, LBO = stride between 64-wide MN blocks.
 __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major descriptor for rows (K indices) of `d` contiguous bf16 MN elements: d = 64 -> SWIZZLE_128B, d = 32 -> SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, int d) {
+  const uint64_t sbo = (uint64_t)((d * 16) >> 4), layout = d == 64 ? 2ull : 4ull;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 // instruction descriptor with explicit majors (0 = K-major, 1 = MN-major)
 __host__ __device__ constexpr uint32_t make_idesc_major(int M, int N, int a_mn, int b_mn) {
