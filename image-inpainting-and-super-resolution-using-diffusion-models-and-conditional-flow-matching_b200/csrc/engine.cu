@@ -793,13 +793,18 @@ int cfm_engine_profile_forward(cfm_engine* h, int32_t batch, const float* x_dev,
 
 int32_t cfm_engine_profile_count(const cfm_engine* h) { return h ? (int32_t)h->impl.prof_ms.size() : 0; }
 
-// kind: 0 generic conv, 1 groupnorm, 2 resample, 3 attention, 4 tcgen05 conv
+// kind: 0 generic conv, 1 groupnorm, 2 resample, 3 generic attention, 4 tcgen05 conv, 5 tcgen05 attention
 int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t name_cap, int32_t* kind, double* ms,
                            double* flops_per_sample) {
   if (!h || i < 0 || i >= (int32_t)h->impl.prof_ms.size()) return CFM_ERR_INVALID;
   const Op& op = h->impl.ops[i];
   if (name && name_cap > 0) { std::strncpy(name, op.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
-  if (kind) *kind = op.kind == OP_CONV ? (op.tc ? 4 : 0) : (op.kind == OP_IM2COL ? 2 : (int)op.kind);
+  if (kind) {
+    if (op.kind == OP_CONV) *kind = op.tc ? 4 : 0;
+    else if (op.kind == OP_IM2COL) *kind = 2;
+    else if (op.kind == OP_ATTN) *kind = (attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op)) ? 5 : 3;
+    else *kind = (int)op.kind;
+  }
   if (ms) *ms = h->impl.prof_ms[i];
   if (flops_per_sample) *flops_per_sample = op.flops;
   return 0;

@@ -175,7 +175,7 @@ class Engine:
             rc = self.lib.cfm_engine_profile_forward(self._h, B, _ptr(xd), _ptr(cd), float(t), _ptr(yd), _ptr(out),
                                                      repeats, _stream_ptr(self.device))
         _lib.check(rc, self._h)
-        kinds = {0: "conv_generic", 1: "groupnorm", 2: "resample", 3: "attention", 4: "conv_tcgen05"}
+        kinds = {0: "conv_generic", 1: "groupnorm", 2: "resample", 3: "attention_generic", 4: "conv_tcgen05", 5: "attention"}
         rows = []
         for i in range(self.lib.cfm_engine_profile_count(self._h)):
             name = C.create_string_buffer(128)

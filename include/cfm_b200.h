@@ -116,7 +116,7 @@ int cfm_engine_forward(cfm_engine* e, int32_t batch, const float* x_dev, const f
 
 /* Per-op device timing of one NFE (CUDA events around every launch, averaged over `repeats`
  * evaluations after one warm-up).  Results are read back with cfm_engine_profile_count/_get;
- * kind: 0 generic conv, 1 groupnorm, 2 resample, 3 attention, 4 tcgen05 conv. */
+ * kind: 0 generic conv, 1 groupnorm, 2 resample, 3 generic attention, 4 tcgen05 conv, 5 tcgen05 attention. */
 int cfm_engine_profile_forward(cfm_engine* e, int32_t batch, const float* x_dev, const float* cond_dev,
                                float t_scalar, const int64_t* y_dev, float* out_dev, int32_t repeats,
                                void* stream);

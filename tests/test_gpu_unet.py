@@ -119,3 +119,41 @@ def test_engine_flops_and_param_accounting(pkg, cuda):
     assert abs(e.flops_per_sample / 1e9 - 12.444) < 0.01
     m(torch.randn(1, 3, 32, 32, device=cuda), torch.rand(1, device=cuda))
     assert e.last_launches > 0
+
+
+def _kinds(m, x, t):
+    return {r["kind"] for r in m.engine().profile_forward(x, float(t), repeats=1)}
+
+
+@pytest.mark.parametrize("name", ["mnist_cfm", "mnist_ddpm", "flowers_ddpm", "cifar"])
+def test_bf16_runs_on_tensor_core_kernels(pkg, cuda, name):
+    # every conv / attention of the BASELINE configs must take the tcgen05 kernels in bf16 mode - a silent fall
+    # back to the CUDA-core kernels would keep parity green and lose two orders of magnitude
+    cfg, _, _ = GOLDEN_CONFIGS[name]
+    m = build(pkg, cfg, O.seeded_params(cfg, 1), "bf16", cuda)
+    x = torch.randn(2, cfg.in_channels, cfg.image_size, cfg.image_size, device=cuda)
+    kinds = _kinds(m, x, 0.3)
+    assert "conv_generic" not in kinds and "attention_generic" not in kinds, kinds
+    assert "conv_tcgen05" in kinds and "attention" in kinds
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("size,mult,heads,hc,attn", [(20, (1, 2), -1, 32, "1,2"), (12, (1, 1, 2), 2, -1, "1"), (24, (2, 1), -1, 64, "2")])
+def test_odd_maps_and_head_widths_match_oracle(pkg, cuda, precision, size, mult, heads, hc, attn):
+    # maps that are not powers of two (20/10, 12/6/3, 24/12), sequence lengths 400/100/144, 32- and 64-wide heads,
+    # strided and folded-upsample convs on them: the flash attention and the generalised conv tiles against the oracle
+    kw = dict(channel_mult=list(mult), attention_resolutions=",".join(str(size // int(a)) for a in attn.split(",")))
+    if hc > 0: kw.update(num_head_channels=hc)
+    else: kw.update(num_heads=heads)
+    cfg = O.config_from_wrapper((3, size, size), 64, 1, **kw)
+    params = O.seeded_params(cfg, 31)
+    m = pkg.UNetModelWrapper(dim=(3, size, size), num_channels=64, num_res_blocks=1, precision=precision, **kw)
+    m.load_state_dict(params)
+    m = m.to(cuda).eval()
+    x = torch.randn(5, 3, size, size)
+    t = torch.tensor(0.61)
+    want = O.wrapper_forward(cfg, params, t, x)
+    got = m(t.to(cuda), x.to(cuda)).cpu()
+    r = rel_l2(got, want)
+    print(f"odd[{size},{mult},{precision}] rel-L2 = {r:.3e}")
+    assert r < TOL[precision], r
