@@ -489,13 +489,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     if (leader) {
       const uint32_t idesc = make_idesc(256, p.block_n);
       const uint32_t row_step = (uint32_t)(p.bw * p.kc * 2) >> 4;
+      const uint32_t half_step = (uint32_t)(TC_BLOCK_M * p.kc * 2) >> 4;   // second M-half of each CTA's A slot
       const int n_kk = p.kc >> 4;
+      const int acc_cols = p.block_n * p.mh;
       Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       int acc = 0; uint32_t acc_phase = 0;
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
         int kdone = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const TcSeg sg = p.seg[s];
@@ -512,7 +514,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const uint64_t bdesc = make_desc_k(smem_u32(ring_b + rb.slot * p.b_slot_bytes), p.kc);
 #pragma unroll
                 for (int kk = 0; kk < TC_BLOCK_K / 16; ++kk)
-                  if (kk < n_kk) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kdone > 0 || kk > 0) ? 1u : 0u);
+                  if (kk < n_kk) {
+                    const uint32_t accum = (kdone > 0 || kk > 0) ? 1u : 0u;
+                    umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+                    if (p.mh == 2)   // each CTA's second 128 rows against the same (shared) weight tile
+                      umma_bf16_2sm(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)half_step + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
+                  }
                 umma_commit_2sm(&emptyB[rb.slot], 3);                         // both CTAs may refill this B slot
                 if (j == G - 1) umma_commit_2sm(&emptyA[ra.slot], 3);         // last view of this A slot
                 if (kdone == p.total_k - 1) umma_commit_2sm(&tfull_bar[acc], 3);   // both CTAs' epilogues may drain
@@ -530,28 +537,39 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== epilogue (warps 2..9, both CTAs) =====================
     const int quad = warp & 3;
     const int sub = (warp - 2) >> 2;
-    const int n_items = p.block_n >> 5;
+    const int chunks_per_half = p.block_n >> 5;
+    const int n_items = chunks_per_half * p.mh;
+    const int acc_cols = p.block_n * p.mh;
     const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
-      const EpiRow row = epi_decode_row(p, tc, quad * 32 + lane);
+      EpiRow rows[2];
+      rows[0] = epi_decode_row(p, tc, quad * 32 + lane);
+      rows[1] = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : rows[0];
       uint4 res_cur[4], res_nxt[4];
-      if (sub < n_items) epi_load_res(p, row, lane, nt * p.block_n + (sub << 5), res_nxt);
+      if (sub < n_items) {
+        const int half = sub / chunks_per_half;
+        epi_load_res(p, rows[half], lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
-        const int c0 = item << 5;
+        const int half = item / chunks_per_half;
+        const int c0 = (item - half * chunks_per_half) << 5;
         uint32_t v[32];
-        tmem_ld32(t_addr + (uint32_t)c0, v);
+        tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
         const int nxt = item + TC_EPI_WARPS / 4;
-        if (nxt < n_items) epi_load_res(p, row, lane, nt * p.block_n + (nxt << 5), res_nxt);
+        if (nxt < n_items) {
+          const int nh = nxt / chunks_per_half;
+          epi_load_res(p, rows[nh], lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
+        }
         tmem_ld_wait();
-        epi_finish(p, row, lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
+        epi_finish(p, rows[half], lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();
@@ -648,11 +666,13 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   const int Cout = op.out_is_output ? 32 : op.Cout;      // padded rows of W are zero
   pl->cout_pad = Cout;
   pl->block_n = pick_block_n(Cout);
-  static const int pair_min_n = [] { const char* v = getenv("CFM_TC_PAIR_MIN_N"); return v ? atoi(v) : 192; }();
-  // N >= 192: CTA pair (half the weight tile per SM).  N <= 128: a pair measured slower than one CTA with a 256-row tile
-  // (two UMMAs per B tile), which restores the 2:1 A:B ratio of the N = 256 case.
+  static const int pair_min_n = [] { const char* v = getenv("CFM_TC_PAIR_MIN_N"); return v ? atoi(v) : 128; }();
+  // N >= 128: CTA pair (half the weight tile per SM).  At N = 128 each CTA of the pair also takes two 128-row M-halves
+  // per weight tile (a 512 x 128 pair tile): the K-iteration stays 512 cycles long (a 256-cycle K-iteration is
+  // shorter than the issue loop) and the shared-memory bytes per MMA cycle drop from 182 to ~135 of the 128 B/clk port.
+  // N <= 96: one CTA with a 256-row tile.
   pl->pair = !op.out_is_output && pl->block_n >= pair_min_n && !env_off("CFM_DISABLE_TC_2CTA");
-  pl->mh = (!pl->pair && pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;
+  pl->mh = (pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;      // 2 x 128 rows per CTA share one B tile
   const int rows = 128 * pl->mh;
   // K-iteration width: 64 channels (SWIZZLE_128B rows) when every operand allows it, else 32 (SWIZZLE_64B)
   pl->kc = 64;
