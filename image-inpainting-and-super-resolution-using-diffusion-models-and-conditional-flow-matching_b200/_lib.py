@@ -67,6 +67,9 @@ SIGNATURES = {
     "cfm_sample_euler": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_uint32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cfm_sample_euler_cfg": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "cfm_sample_ddpm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(DdpmTablesC),
                                   C.POINTER(DdpmOptionsC), C.c_void_p, C.c_uint64, C.c_void_p]),
     "cfm_rk_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_float),

@@ -588,12 +588,14 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
   return 0;
 }
 
+// drop_labels: evaluate a class-conditional model WITHOUT its label embedding (the unconditional branch of
+// classifier-free guidance; y must then be NULL).
 static int forward_impl(Engine& e, int B, const float* x, const float* cond, const float* t_dev, float t_scalar,
                         const int64_t* y, float* out, cudaStream_t st, const float* t_table = nullptr,
-                        const int* step_counter = nullptr) {
+                        const int* step_counter = nullptr, bool drop_labels = false) {
   if (B <= 0) return fail(e, CFM_ERR_INVALID, "batch must be positive");
   if (!x || !out) return fail(e, CFM_ERR_INVALID, "x_dev and out_dev must be non-NULL");
-  if ((y != nullptr) != (e.cfg.num_classes > 0))
+  if (drop_labels ? (y != nullptr) : ((y != nullptr) != (e.cfg.num_classes > 0)))
     return fail(e, CFM_ERR_INVALID, "must specify y if and only if the model is class-conditional");
   if (!cond && e.cfg.in_channels != e.x_channels() && false) return fail(e, CFM_ERR_INVALID, "cond required");
   int rc = ensure_batch(e, B);
@@ -603,7 +605,7 @@ static int forward_impl(Engine& e, int B, const float* x, const float* cond, con
   const int n = std::max(rows, B);
   setup_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, rows, uniform, t_scalar, t_dev, t_table, step_counter, (const long long*)y, e.t_rows, e.label_idx, e.row_of_sample);
   time_hidden_kernel<<<rows, 256, sizeof(float) * e.cfg.model_channels, st>>>(e.t_rows, e.cfg.model_channels, e.ted, e.w_t1, e.b_t1, e.hidden);
-  linear_rows_kernel<<<dim3((e.ted + 7) / 8, rows), 256, 0, st>>>(e.hidden, e.ted, e.w_t2, e.b_t2, e.ted, e.label_emb, e.label_idx, 1, e.semb);
+  linear_rows_kernel<<<dim3((e.ted + 7) / 8, rows), 256, 0, st>>>(e.hidden, e.ted, e.w_t2, e.b_t2, e.ted, drop_labels ? nullptr : e.label_emb, e.label_idx, 1, e.semb);
   linear_rows_kernel<<<dim3((e.emb_total + 7) / 8, rows), 256, 0, st>>>(e.semb, e.ted, e.w_emb_cat, e.b_emb_cat, e.emb_total, nullptr, nullptr, 0, e.emb_out);
   e.launches += 4;
   rc = e.bf16 ? run_ops<bf16>(e, B, x, cond, out, st) : run_ops<float>(e, B, x, cond, out, st);
@@ -742,7 +744,7 @@ void cfm_engine_destroy(cfm_engine* h) {
     if (p) cudaFree(p);
   for (void* p : e.owned) cudaFree(p);
   for (cudaEvent_t ev : e.prof_events) cudaEventDestroy(ev);
-  for (void* p : {(void*)e.arena, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf})
+  for (void* p : {(void*)e.arena, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf, (void*)e.v2_buf})
     if (p) cudaFree(p);
   delete h;
 }
@@ -810,11 +812,12 @@ int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t n
   return 0;
 }
 
-int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev, const int64_t* y_dev,
-                     const float* t_host, const float* dt_host, int32_t n_steps, uint32_t flags,
-                     float* traj_dev, uint8_t* img_u8_dev, void* stream) {
+static int sample_euler_impl(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev, const int64_t* y_dev,
+                             bool guided, float guidance_w, const float* t_host, const float* dt_host, int32_t n_steps,
+                             uint32_t flags, float* traj_dev, uint8_t* img_u8_dev, void* stream) {
   if (!h) return CFM_ERR_INVALID;
   Engine& e = h->impl;
+  if (guided && e.cfg.num_classes <= 0) return fail(e, CFM_ERR_INVALID, "classifier-free guidance needs a class-conditional model");
   if (!x_dev || (n_steps > 0 && (!t_host || !dt_host)) || n_steps < 0 || batch <= 0) return fail(e, CFM_ERR_INVALID, "bad argument to cfm_sample_euler");
   if ((y_dev != nullptr) != (e.cfg.num_classes > 0)) return fail(e, CFM_ERR_INVALID, "must specify y if and only if the model is class-conditional");
   cudaSetDevice(e.device);
@@ -840,9 +843,16 @@ int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev
   const bool drift = (flags & CFM_EULER_COND_DRIFT) && cond_dev;
   const float* cond_w = cond_dev ? e.cond_work : nullptr;
   const int64_t* y_w = y_dev ? (const int64_t*)e.y_work : nullptr;
+  if (guided) { int r2 = grow(e, &e.v2_buf, &e.v2_cap, n); if (r2) return r2; }
   auto body = [&](cudaStream_t s2) -> int {
     int r = forward_impl(e, batch, e.x_work, cond_w, nullptr, 0.f, y_w, e.v_buf, s2, e.t_table, e.step_counter);
     if (r) return r;
+    if (guided) {   // second evaluation without the label embedding, then v = v_c + w (v_c - v_u)
+      r = forward_impl(e, batch, e.x_work, cond_w, nullptr, 0.f, nullptr, e.v2_buf, s2, e.t_table, e.step_counter, true);
+      if (r) return r;
+      cfg_combine_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.v_buf, e.v2_buf, guidance_w, n);
+      e.launches++;
+    }
     euler_step_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.dt_table, e.step_counter, n_steps, n,
                                                       drift ? e.cond_work : nullptr, n_cond, traj_dev,
                                                       img_u8_dev ? e.img_work : nullptr);
@@ -851,8 +861,9 @@ int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev
     return 0;
   };
   char key[160];
-  snprintf(key, sizeof(key), "euler:%d:%d:%d:%d:%d:%p:%d", batch, n_steps, cond_dev != nullptr, y_dev != nullptr, (int)drift,
-           (void*)traj_dev, img_u8_dev != nullptr);
+  uint32_t w_bits; std::memcpy(&w_bits, &guidance_w, 4);
+  snprintf(key, sizeof(key), "euler:%d:%d:%d:%d:%d:%p:%d:%d:%08x", batch, n_steps, cond_dev != nullptr, y_dev != nullptr, (int)drift,
+           (void*)traj_dev, img_u8_dev != nullptr, (int)guided, guided ? w_bits : 0u);
   const bool use_graph = (flags & CFM_EULER_USE_GRAPH) != 0;
   if (use_graph && n_steps > 0 && !e.graphs.count(key)) {
     // un-captured dry run first: all lazy host-side setup (tensor maps, kernel attributes) happens outside capture
@@ -864,6 +875,18 @@ int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev
   if (img_u8_dev && n_steps > 0) CU_CHECK(e, cudaMemcpyAsync(img_u8_dev, e.img_work, (size_t)n, cudaMemcpyDeviceToDevice, st));
   CU_CHECK(e, cudaGetLastError());
   return 0;
+}
+
+int cfm_sample_euler(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev, const int64_t* y_dev,
+                     const float* t_host, const float* dt_host, int32_t n_steps, uint32_t flags,
+                     float* traj_dev, uint8_t* img_u8_dev, void* stream) {
+  return sample_euler_impl(h, batch, x_dev, cond_dev, y_dev, false, 0.f, t_host, dt_host, n_steps, flags, traj_dev, img_u8_dev, stream);
+}
+
+int cfm_sample_euler_cfg(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev, const int64_t* y_dev,
+                         float guidance_w, const float* t_host, const float* dt_host, int32_t n_steps, uint32_t flags,
+                         float* traj_dev, uint8_t* img_u8_dev, void* stream) {
+  return sample_euler_impl(h, batch, x_dev, cond_dev, y_dev, true, guidance_w, t_host, dt_host, n_steps, flags, traj_dev, img_u8_dev, stream);
 }
 
 int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* condition_dev,

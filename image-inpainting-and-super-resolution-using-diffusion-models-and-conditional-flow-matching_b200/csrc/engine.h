@@ -65,6 +65,7 @@ struct Engine {
   long long* label_idx = nullptr; int* row_of_sample = nullptr; int rows_cap = 0;
   // scratch for samplers
   float* v_buf = nullptr; long long v_cap = 0;
+  float* v2_buf = nullptr; long long v2_cap = 0;      // unconditional velocity of classifier-free guidance
   float* x_work = nullptr; long long x_cap = 0;
   float* cond_work = nullptr; long long cond_cap = 0;
   uint8_t* img_work = nullptr; long long img_cap = 0;

@@ -59,6 +59,13 @@ __global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict
       cond[i] = __fadd_rn(cond[i], __fmul_rn(dt, cond[i]));
 }
 
+// classifier-free guidance: v_c <- v_c + w (v_c - v_u)   (= (1 + w) v_c - w v_u), evaluated in this order
+__global__ void cfg_combine_kernel(float* __restrict__ vc, const float* __restrict__ vu, float w, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    vc[i] = __fadd_rn(vc[i], __fmul_rn(w, __fsub_rn(vc[i], vu[i])));
+}
+
 __global__ void quantize_u8_kernel(uint8_t* __restrict__ out, const float* __restrict__ x, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)

@@ -188,8 +188,11 @@ class Engine:
     def sample_euler(self, x0: torch.Tensor, t_grid: Sequence[float], dt_grid: Sequence[float],
                      y: Optional[torch.Tensor] = None, cond: Optional[torch.Tensor] = None,
                      cond_drift: bool = False, return_trajectory: bool = False, return_uint8: bool = False,
-                     use_graph: bool = False):
-        """Runs ``x += dt_k * model(t_k, x)`` for every k on the device.  Returns (x_final, traj|None, u8|None)."""
+                     use_graph: bool = False, guidance_weight: Optional[float] = None):
+        """Runs ``x += dt_k * model(t_k, x)`` for every k on the device.  Returns (x_final, traj|None, u8|None).
+
+        ``guidance_weight`` (class-conditional models): classifier-free guidance, two evaluations per step,
+        ``v = v_c + w (v_c - v_u)`` with ``v_u`` evaluated without the label embedding."""
         n_steps = len(t_grid)
         assert len(dt_grid) == n_steps
         B = x0.shape[0]
@@ -204,8 +207,12 @@ class Engine:
         dg = (C.c_float * max(n_steps, 1))(*[float(v) for v in dt_grid])
         flags = (_lib.EULER_COND_DRIFT if cond_drift else 0) | (_lib.EULER_USE_GRAPH if use_graph else 0)
         with torch.cuda.device(self.device):
-            rc = self.lib.cfm_sample_euler(self._h, B, _ptr(x), _ptr(cd), _ptr(yd), tg, dg, n_steps, flags,
-                                           _ptr(traj), _ptr(img), _stream_ptr(self.device))
+            if guidance_weight is None:
+                rc = self.lib.cfm_sample_euler(self._h, B, _ptr(x), _ptr(cd), _ptr(yd), tg, dg, n_steps, flags,
+                                               _ptr(traj), _ptr(img), _stream_ptr(self.device))
+            else:
+                rc = self.lib.cfm_sample_euler_cfg(self._h, B, _ptr(x), _ptr(cd), _ptr(yd), float(guidance_weight), tg, dg,
+                                                   n_steps, flags, _ptr(traj), _ptr(img), _stream_ptr(self.device))
         _lib.check(rc, self._h)
         return x, traj, img
 

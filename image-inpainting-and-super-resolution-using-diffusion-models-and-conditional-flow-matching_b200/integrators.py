@@ -126,14 +126,14 @@ class NeuralODE(torch.nn.Module):
 
 
 def sample_euler(model: UNetModel, x0: torch.Tensor, t_span: torch.Tensor, y=None, cond=None, cond_drift=False,
-                 return_uint8: bool = False, use_graph: bool = True):
+                 return_uint8: bool = False, use_graph: bool = True, guidance_weight: Optional[float] = None):
     """Final state only (no 101x trajectory): what cifar10/compute_fid.py:73-88 actually consumes.
 
     Returns x_final, or (x_final, uint8 image) with ``return_uint8``.
     """
     ts, dts = euler_time_grid(t_span)
     x, _, img = model.engine().sample_euler(x0, ts, dts, y=y, cond=cond, cond_drift=cond_drift,
-                                            return_uint8=return_uint8, use_graph=use_graph)
+                                            return_uint8=return_uint8, use_graph=use_graph, guidance_weight=guidance_weight)
     return (x, img) if return_uint8 else x
 
 

@@ -138,6 +138,15 @@ int cfm_sample_euler(cfm_engine* e, int32_t batch, float* x_dev, float* cond_dev
                      int32_t n_steps, uint32_t flags, float* traj_dev, uint8_t* img_u8_dev,
                      void* stream);
 
+/* Classifier-free guidance on the same loop (BASELINE config 3; an EXTENSION - the reference's conditional_mnist
+ * notebook evaluates model(t, x, y) only): two U-Net evaluations per step,
+ *   v_c = model(t, x, y),  v_u = model(t, x) with the label embedding left out,  x += dt * (v_c + w (v_c - v_u)).
+ * The model must be class-conditional; guidance_w = 0 reproduces cfm_sample_euler. */
+int cfm_sample_euler_cfg(cfm_engine* e, int32_t batch, float* x_dev, float* cond_dev,
+                         const int64_t* y_dev, float guidance_w, const float* t_host, const float* dt_host,
+                         int32_t n_steps, uint32_t flags, float* traj_dev, uint8_t* img_u8_dev,
+                         void* stream);
+
 typedef enum cfm_ddpm_mode {
   CFM_DDPM_PRIOR = 0,        /* sampling.py:50-75   */
   CFM_DDPM_REPLACEMENT = 1,  /* sampling.py:209-260 */

@@ -41,6 +41,20 @@ def euler_trajectory(f: Callable, x: torch.Tensor, t_span: torch.Tensor) -> torc
     return torch.stack(sol)
 
 
+def euler_cfg_trajectory(f_cond: Callable, f_uncond: Callable, w: float, x: torch.Tensor, t_span: torch.Tensor) -> torch.Tensor:
+    """Classifier-free guidance on the Euler driver above (EXTENSION, not in the reference: SURVEY F7).
+
+    Two evaluations per step, combined as ``v_c + w (v_c - v_u)`` in fp32, in that order of operations.
+    """
+    wt = torch.tensor(w, dtype=torch.float32)
+
+    def f(t, xx):
+        vc, vu = f_cond(t, xx), f_uncond(t, xx)
+        return vc + wt * (vc - vu)
+
+    return euler_trajectory(f, x, t_span)
+
+
 def euler_time_grid(t_span: torch.Tensor) -> Tuple[List[float], List[float]]:
     """The (t_k, dt_k) pairs the loop above feeds to f / uses in the update."""
     t = t_span[0]

@@ -1,0 +1,82 @@
+"""End-to-end sampling throughput of every BASELINE.json config through the public Python API (one GPU, bf16,
+CUDA graphs, synthetic data, seeded weights).  Prints one line per config and writes gpurun_out/sampler_sweep.json.
+usage: python profiles/sampler_sweep.py [config-prefix ...]"""
+import json, os, sys, time
+import torch
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import __graft_entry__ as g
+g.build(); pkg = g.load_package()
+from oracle import unet as O
+
+
+def timed(fn, reps=2):
+    fn(); torch.cuda.synchronize()          # warm-up (graph capture, tensor maps)
+    t0 = time.time()
+    for _ in range(reps): fn()
+    torch.cuda.synchronize()
+    return (time.time() - t0) / reps
+
+
+def wrapper(cls, cfg_kw, oracle_cfg, **kw):
+    m = cls(precision="bf16", **cfg_kw, **kw)
+    m.load_state_dict(O.seeded_params(oracle_cfg, 0))
+    return m.cuda().eval()
+
+
+out = {}
+only = sys.argv[1:]
+def want(name): return not only or any(name.startswith(o) for o in only)
+
+if want("0"):
+    B = 64
+    cfg = O.config_from_wrapper((1, 28, 28), 32, 1, extra_in_channels=1)
+    m = wrapper(pkg.InPaintModelWrapper, dict(dim=(1, 28, 28), num_channels=32, num_res_blocks=1), cfg, num_classes=None, class_cond=True)
+    x0 = torch.randn(B, 1, 28, 28, device='cuda'); con = torch.rand(B, 1, 28, 28, device='cuda') * 2 - 1; con[:, :, 6:20, 7:21] = -2
+    ts = torch.linspace(0, 1, 101)
+    dt = timed(lambda: pkg.sample_euler(m, x0, ts, cond=con, cond_drift=True, use_graph=True))
+    out["0 mnist_cfm_inpaint b64 100-step Euler"] = {"s": dt, "samples_per_s": B / dt, "evals": 100}
+if want("2"):
+    B = 4096
+    cfg = O.config_from_wrapper((1, 28, 28), 32, 1, class_cond=True, num_classes=10)
+    m = wrapper(pkg.UNetModelWrapper, dict(dim=(1, 28, 28), num_channels=32, num_res_blocks=1), cfg, num_classes=10, class_cond=True)
+    x0 = torch.randn(B, 1, 28, 28, device='cuda'); y = torch.arange(B, device='cuda') % 10
+    ts = torch.linspace(0, 1, 101)
+    dt = timed(lambda: pkg.sample_euler(m, x0, ts, y=y, guidance_weight=2.0, use_graph=True), reps=1)
+    out["2 mnist_classcond CFG b4096 100-step Euler x2 evals"] = {"s": dt, "samples_per_s": B / dt, "evals": 200}
+if want("3a"):
+    B = 256
+    cfg = O.config_from_create_model(image_size=28, in_channels=2, out_channels=1, num_channels=32, num_res_blocks=1, channel_mult="1, 2, 2", resblock_updown=True)
+    net = pkg.create_model(image_size=28, in_channels=2, out_channels=1, num_channels=32, num_res_blocks=1, channel_mult="1, 2, 2", resblock_updown=True, precision="bf16")
+    net.load_state_dict(O.seeded_params(cfg, 0)); net = net.cuda().eval()
+    ddpm = pkg.DDPM(1000)
+    lik = pkg.InPainting(14, -2.0)
+    fn = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(), lik, use_graph=True)
+    xT = torch.randn(B, 1, 28, 28, device='cuda'); cond = lik.sample(torch.rand(B, 1, 28, 28, device="cuda") * 2 - 1)
+    dt = timed(lambda: fn(xT, cond), reps=1)
+    out["3a ddpm_mnist amortized inpainting b256 1000 steps"] = {"s": dt, "samples_per_s": B / dt, "evals": 1000}
+if want("3b"):
+    B = 128
+    kw = dict(image_size=64, in_channels=3, out_channels=3, num_channels=128, num_res_blocks=1, resblock_updown=True, num_head_channels=64, use_scale_shift_norm=True, num_heads=4)
+    cfg = O.config_from_create_model(**kw)
+    net = pkg.create_model(precision="bf16", **kw)
+    net.load_state_dict(O.seeded_params(cfg, 0)); net = net.cuda().eval()
+    ddpm = pkg.DDPM(1000)
+    lik = pkg.InPainting(20, -2.0)
+    fn = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Replacement(), lik, use_graph=True)
+    xT = torch.randn(B, 3, 64, 64, device='cuda'); cond = lik.sample(torch.rand(B, 3, 64, 64, device="cuda") * 2 - 1)
+    dt = timed(lambda: fn(xT, cond), reps=1)
+    out["3b ddpm_flowers64 RePaint-style replacement b128 1000 steps"] = {"s": dt, "samples_per_s": B / dt, "evals": 1000}
+if want("4"):
+    B = 32
+    cfg = O.config_from_wrapper((3, 128, 128), 128, 1, extra_in_channels=3)
+    m = wrapper(pkg.SuperResModelWrapper, dict(dim=(3, 128, 128), num_channels=128, num_res_blocks=1), cfg, num_classes=None, class_cond=True)
+    x0 = torch.randn(B, 3, 128, 128, device='cuda'); lo = torch.rand(B, 3, 32, 32, device='cuda') * 2 - 1
+    up = torch.nn.functional.interpolate(lo, size=(128, 128), mode="bilinear")
+    ts = torch.linspace(0, 1, 51)
+    dt = timed(lambda: pkg.sample_euler(m, x0, ts, cond=up, use_graph=True))
+    out["4 superres 32->128 CFM b32 50-step Euler"] = {"s": dt, "samples_per_s": B / dt, "evals": 50}
+
+for k, v in out.items():
+    print(f"{k:62s} {v['s']:8.3f} s  {v['samples_per_s']:10.1f} samples/s  {v['s'] / v['evals'] * 1e3:8.3f} ms per U-Net eval batch")
+os.makedirs('gpurun_out', exist_ok=True)
+json.dump(out, open('gpurun_out/sampler_sweep.json', 'w'), indent=1)

@@ -205,3 +205,31 @@ def test_ddpm_device_rng_statistics(pkg, cuda):
     a, b, c = fn(1), fn(1), fn(2)
     assert torch.equal(a, b) and not torch.equal(a, c)
     assert torch.isfinite(a).all() and a.abs().max() <= 1.0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 4e-2)])
+def test_classifier_free_guidance_euler(pkg, cuda, precision, tol):
+    """BASELINE config 3 (extension): two evaluations per step, v = v_c + w (v_c - v_u), the unconditional
+    branch being the class-conditional model without its label embedding.  Checked against the oracle loop; w = 0
+    must reproduce the plain conditional sampler bit for bit; use_graph replays the same captured step."""
+    cfg, params, m = small_cfm(pkg, cuda, precision, class_cond=True, num_classes=10)
+    x0 = torch.randn(6, 3, 16, 16)
+    y = torch.tensor([0, 3, 9, 1, 1, 7])
+    t_span = torch.linspace(0, 1, 5)
+    w = 1.5
+    want = I.euler_cfg_trajectory(lambda t, x: O.wrapper_forward(cfg, params, t, x, y),
+                                  lambda t, x: O.wrapper_forward(cfg, params, t, x, None, drop_labels=True),
+                                  w, x0, t_span)[-1]
+    got = pkg.sample_euler(m, x0.to(cuda), t_span, y=y.to(cuda), guidance_weight=w, use_graph=False)
+    r = rel_l2(got.cpu(), want)
+    print(f"cfg[{precision}] rel-L2 = {r:.3e}")
+    assert r < tol, r
+    got_graph = pkg.sample_euler(m, x0.to(cuda), t_span, y=y.to(cuda), guidance_weight=w, use_graph=True)
+    assert torch.equal(got, got_graph)
+    plain = pkg.sample_euler(m, x0.to(cuda), t_span, y=y.to(cuda), use_graph=False)
+    zero_w = pkg.sample_euler(m, x0.to(cuda), t_span, y=y.to(cuda), guidance_weight=0.0, use_graph=False)
+    assert torch.equal(plain, zero_w)
+    assert rel_l2(got.cpu(), plain.cpu()) > 1e-3           # guidance does change the trajectory
+    _, _, unc = small_cfm(pkg, cuda, precision)
+    with pytest.raises(Exception):
+        pkg.sample_euler(unc, x0.to(cuda), t_span, guidance_weight=w)   # needs a class-conditional model
