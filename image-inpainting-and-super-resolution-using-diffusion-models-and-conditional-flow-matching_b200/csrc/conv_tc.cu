@@ -123,6 +123,15 @@ __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCo
   }
   return r;
 }
+// rows[half] without dynamic indexing (which would put the two EpiRows in local memory): field-wise selects
+__device__ __forceinline__ EpiRow epi_pick(const EpiRow& a, const EpiRow& b, bool second) {
+  EpiRow r;
+  r.valid = second ? b.valid : a.valid; r.n = second ? b.n : a.n; r.h = second ? b.h : a.h; r.w = second ? b.w : a.w;
+  r.pix = second ? b.pix : a.pix; r.gvalid = second ? b.gvalid : a.gvalid;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r.gpix[k] = second ? b.gpix[k] : a.gpix[k];
+  return r;
+}
 // issue the residual loads of one 32-channel chunk early (they are the only DRAM-latency operand of the epilogue),
 // in the transposed (coalesced) pattern: res[k] = 8 channels (lane & 3) of row (lane & ~3) + k
 __device__ __forceinline__ void epi_load_res(const TcParams& p, const EpiRow& r, int lane, int cg, uint4 (&res)[4]) {
@@ -348,13 +357,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int nt = tc.nt;
-      EpiRow rows[2];
-      rows[0] = epi_decode_row(p, tc, quad * 32 + lane);
-      rows[1] = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : rows[0];
+      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+      const EpiRow row1 = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
         const int half = sub / chunks_per_half;
-        epi_load_res(p, rows[half], lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
+        epi_load_res(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -369,10 +377,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int nxt = item + TC_EPI_WARPS / 4;
         if (nxt < n_items) {
           const int nh = nxt / chunks_per_half;
-          epi_load_res(p, rows[nh], lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
+          epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
-        epi_finish(p, rows[half], lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
+        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();
@@ -545,13 +553,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
-      EpiRow rows[2];
-      rows[0] = epi_decode_row(p, tc, quad * 32 + lane);
-      rows[1] = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : rows[0];
+      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+      const EpiRow row1 = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
         const int half = sub / chunks_per_half;
-        epi_load_res(p, rows[half], lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
+        epi_load_res(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -566,10 +573,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int nxt = item + TC_EPI_WARPS / 4;
         if (nxt < n_items) {
           const int nh = nxt / chunks_per_half;
-          epi_load_res(p, rows[nh], lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
+          epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
-        epi_finish(p, rows[half], lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
+        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();
