@@ -102,6 +102,9 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& p, int pt,
   c.tb = mt / p.tiles_h;
   return c;
 }
+// kUniform: every tile row carries a pixel and the 4 rows of a lane group are neighbouring pixels of one image row
+// (all power-of-two maps) - the group's pixel indices follow by arithmetic and no per-row state is kept.
+template <bool kUniform>
 __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCoord& c, int row) {
   EpiRow r;
   const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
@@ -116,10 +119,17 @@ __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCo
   // pixel index / validity of the 4 rows of this lane's group (any box shape: rows of a group need not be neighbours)
   const int lane = threadIdx.x & 31, g0 = lane & ~3;
   r.gvalid = 0;
+  if (kUniform) {
+    const int step = p.n_phase == 4 ? 2 : 1;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    r.gpix[k] = __shfl_sync(0xffffffffu, r.pix, g0 + k);
-    r.gvalid |= (uint32_t)__shfl_sync(0xffffffffu, (int)r.valid, g0 + k) << k;
+    for (int k = 0; k < 4; ++k) r.gpix[k] = r.pix + (long long)((k - (lane & 3)) * step);
+    r.gvalid = r.valid ? 15u : 0u;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      r.gpix[k] = __shfl_sync(0xffffffffu, r.pix, g0 + k);
+      r.gvalid |= (uint32_t)__shfl_sync(0xffffffffu, (int)r.valid, g0 + k) << k;
+    }
   }
   return r;
 }
@@ -210,6 +220,7 @@ struct Ring { int slot; uint32_t phase; int n; __device__ __forceinline__ void n
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
+template <bool kUniform>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -357,18 +368,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int nt = tc.nt;
-      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
-      const EpiRow row1 = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
+      const EpiRow row0 = epi_decode_row<kUniform>(p, tc, quad * 32 + lane);
+      const EpiRow row1 = p.mh == 2 ? epi_decode_row<kUniform>(p, tc, 128 + quad * 32 + lane) : row0;
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
-        const int half = sub / chunks_per_half;
+        const int half = sub >= chunks_per_half ? 1 : 0;          // mh <= 2
         epi_load_res(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
-        const int half = item / chunks_per_half;
+        const int half = item >= chunks_per_half ? 1 : 0;
         const int c0 = (item - half * chunks_per_half) << 5;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
@@ -376,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
         const int nxt = item + TC_EPI_WARPS / 4;
         if (nxt < n_items) {
-          const int nh = nxt / chunks_per_half;
+          const int nh = nxt >= chunks_per_half ? 1 : 0;
           epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
@@ -402,6 +413,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // slot-free / accumulator-ready signals to both CTAs; both CTAs' epilogues drain their own 128 TMEM
 // lanes and report back to the leader's accumulator-empty barrier.
 // ------------------------------------------------------------------------------------------------
+// kMH: 128-row M-halves per CTA, a compile-time constant so that the kMH = 1 instances (N >= 192 layers, most of
+// them short-K and epilogue-bound) carry none of the two-half bookkeeping
+template <bool kUniform, int kMH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -499,7 +513,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const uint32_t row_step = (uint32_t)(p.bw * p.kc * 2) >> 4;
       const uint32_t half_step = (uint32_t)(TC_BLOCK_M * p.kc * 2) >> 4;   // second M-half of each CTA's A slot
       const int n_kk = p.kc >> 4;
-      const int acc_cols = p.block_n * p.mh;
+      const int acc_cols = p.block_n * kMH;
       Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       int acc = 0; uint32_t acc_phase = 0;
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
@@ -525,7 +539,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                   if (kk < n_kk) {
                     const uint32_t accum = (kdone > 0 || kk > 0) ? 1u : 0u;
                     umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
-                    if (p.mh == 2)   // each CTA's second 128 rows against the same (shared) weight tile
+                    if (kMH == 2)   // each CTA's second 128 rows against the same (shared) weight tile
                       umma_bf16_2sm(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)half_step + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
                   }
                 umma_commit_2sm(&emptyB[rb.slot], 3);                         // both CTAs may refill this B slot
@@ -546,25 +560,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int quad = warp & 3;
     const int sub = (warp - 2) >> 2;
     const int chunks_per_half = p.block_n >> 5;
-    const int n_items = chunks_per_half * p.mh;
-    const int acc_cols = p.block_n * p.mh;
+    const int n_items = chunks_per_half * kMH;
+    const int acc_cols = p.block_n * kMH;
     const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
-      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
-      const EpiRow row1 = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
+      const EpiRow row0 = epi_decode_row<kUniform>(p, tc, quad * 32 + lane);
+      const EpiRow row1 = kMH == 2 ? epi_decode_row<kUniform>(p, tc, 128 + quad * 32 + lane) : row0;   // kMH = 1: never selected
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
-        const int half = sub / chunks_per_half;
+        const int half = (kMH == 2 && sub >= chunks_per_half) ? 1 : 0;
         epi_load_res(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
-        const int half = item / chunks_per_half;
+        const int half = (kMH == 2 && item >= chunks_per_half) ? 1 : 0;
         const int c0 = (item - half * chunks_per_half) << 5;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
@@ -572,7 +586,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
         const int nxt = item + TC_EPI_WARPS / 4;
         if (nxt < n_items) {
-          const int nh = nxt / chunks_per_half;
+          const int nh = (kMH == 2 && nxt >= chunks_per_half) ? 1 : 0;
           epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
@@ -606,6 +620,7 @@ struct TcConvPlan {
   bool pair = false;                    // CTA-pair (cta_group::2) kernel
   int a_slot_bytes = 0, b_slot_bytes = 0, n_a = 0, n_b = 0, a_tile_bytes = 0, a_halo_bytes = 0;
   int kc = 64, valid_rows = 0;
+  bool uniform = false;        // every tile row is a pixel, lane groups of 4 are neighbours in one image row
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
@@ -697,6 +712,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   pl->bh = std::min(Hg, rows / pl->bw);
   pl->bn = pl->bh == Hg ? std::max(1, rows / (pl->bw * pl->bh)) : 1;
   pl->valid_rows = pl->bw * pl->bh * pl->bn;
+  pl->uniform = pl->valid_rows == rows && pl->bw % 4 == 0 && Hg % pl->bh == 0 && !env_off("CFM_TC_GENERIC_ROWS");
   const int eks = op.ups ? 2 : ks;          // taps per axis the kernel walks
   // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous), fill its rows exactly and
   // an image row must be a whole number of 8-row swizzle atoms
@@ -768,8 +784,12 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   op.tc = pl;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(conv_tc_kernel, smem) failed"; return CFM_ERR_CUDA;
     }
     attr_set = true;
@@ -838,13 +858,15 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
     LaunchCfg lc(dim3(2 * std::min(pair_tiles, e.sm_count / 2)), dim3(TC_THREADS), TC_SMEM_BYTES, st, 2, pdl_enabled());
-    cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc2_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+    auto kern = pl->mh == 2 ? (pl->uniform ? conv_tc2_kernel<true, 2> : conv_tc2_kernel<false, 2>)
+                            : (pl->uniform ? conv_tc2_kernel<true, 1> : conv_tc2_kernel<false, 1>);
+    cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, kern, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
     if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
     return 0;
   }
   const int grid = std::min(p.n_tiles, e.sm_count);
   LaunchCfg lc(dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, 1, pdl_enabled());
-  cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+  cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, pl->uniform ? conv_tc_kernel<true> : conv_tc_kernel<false>, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
   if (ce != cudaSuccess) { e.err = std::string("conv_tc_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
   return 0;
 }
