@@ -46,6 +46,23 @@ constexpr int TC_SMEM_BYTES = TC_RING_BYTES + TC_MAX_COUT * 4 + TC_BAR_BYTES + 1
 //             (not the tensor pipe) is what bounds the N <= 128 layers: 96 B/clk/SM without this, ~57 with.
 struct TcSeg { int map; int n_chunks; int ks; int stride; int halo; };
 
+// n / d for n < 2^31 as one multiply-high and a shift (the divisors are tile counts and box extents known at launch;
+// the epilogue of a short-K tile is only a few hundred instructions, so a handful of runtime divisions per tile show)
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __host__ void init(int dd) {
+    d = (uint32_t)dd; mul = 0; shr = 0;
+    if (dd > 1) {
+      int lg = 0; while ((1u << lg) < d) ++lg;
+      const int pw = 31 + lg;
+      mul = (uint32_t)((((unsigned long long)1 << pw) + d - 1) / d);
+      shr = (uint32_t)(pw - 32);
+    }
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int* q, int* r) const { *q = div(n); *r = n - *q * (int)d; }
+};
+
 struct TcParams {
   int n_seg; TcSeg seg[3];
   int total_k;
@@ -53,6 +70,7 @@ struct TcParams {
   int bw, bh, bn;              // tile box, bw*bh*bn == 128 * mh  (128 per CTA in the pair kernel)
   int mh;                      // M-halves per CTA tile (2: two UMMAs share one B tile)
   int tiles_w, tiles_h, tiles_b, tiles_n, n_tiles;
+  FastDiv d_tiles_n, d_phase, d_tiles_w, d_tiles_h, d_bw, d_bh;
   int n_phase;                 // 4: nearest-x2 upsample folded into the conv as four 2x2 sub-pixel convs (H, W = source size)
   int block_n, Cout;
   int a_slot_bytes, b_slot_bytes, n_a, n_b;   // operand rings
@@ -78,11 +96,10 @@ struct TileCoord { int nt, ph, tw, th, tb; };
 // A tile run at the same time and the tile is fetched from DRAM once.
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   TileCoord c;
-  c.nt = tile % p.tiles_n; tile /= p.tiles_n;
-  c.ph = tile % p.n_phase; tile /= p.n_phase;
-  c.tw = tile % p.tiles_w; tile /= p.tiles_w;
-  c.th = tile % p.tiles_h;
-  c.tb = tile / p.tiles_h;
+  p.d_tiles_n.divmod(tile, &tile, &c.nt);
+  p.d_phase.divmod(tile, &tile, &c.ph);
+  p.d_tiles_w.divmod(tile, &tile, &c.tw);
+  p.d_tiles_h.divmod(tile, &c.tb, &c.th);
   return c;
 }
 // tap offset of K-iteration `tap` of a segment: plain ks x ks conv, or (ks == 2) phase `ph` of the sub-pixel
@@ -94,12 +111,11 @@ __device__ __forceinline__ void tap_offset(int ks, int tap, int ph, int* dy, int
 // CTA-pair kernel: a pair tile is two consecutive 128-row tiles; `rank` picks this CTA's half
 __device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& p, int pt, int rank) {
   TileCoord c;
-  c.nt = pt % p.tiles_n; pt /= p.tiles_n;
-  c.ph = pt % p.n_phase; pt /= p.n_phase;
+  p.d_tiles_n.divmod(pt, &pt, &c.nt);
+  p.d_phase.divmod(pt, &pt, &c.ph);
   int mt = pt * 2 + rank;
-  c.tw = mt % p.tiles_w; mt /= p.tiles_w;
-  c.th = mt % p.tiles_h;
-  c.tb = mt / p.tiles_h;
+  p.d_tiles_w.divmod(mt, &mt, &c.tw);
+  p.d_tiles_h.divmod(mt, &c.tb, &c.th);
   return c;
 }
 // kUniform: every tile row carries a pixel and the 4 rows of a lane group are neighbouring pixels of one image row
@@ -107,7 +123,9 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& p, int pt,
 template <bool kUniform>
 __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCoord& c, int row) {
   EpiRow r;
-  const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
+  int wi, hi, ni, t;
+  p.d_bw.divmod(row, &t, &wi);
+  p.d_bh.divmod(t, &ni, &hi);
   r.n = c.tb * p.bn + ni; r.h = c.th * p.bh + hi; r.w = c.tw * p.bw + wi;
   r.valid = row < p.valid_rows && r.n < p.B && r.h < p.H;
   if (p.n_phase == 4) {   // rows index the source grid; this phase's outputs interleave into the 2H x 2W map
@@ -844,6 +862,8 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.tiles_w = pl->Wg / pl->bw; p.tiles_h = (pl->Hg + pl->bh - 1) / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
   p.kc = pl->kc; p.valid_rows = pl->valid_rows;
   p.tiles_n = pl->cout_pad / pl->block_n;
+  p.d_tiles_n.init(p.tiles_n); p.d_phase.init(p.n_phase); p.d_tiles_w.init(p.tiles_w); p.d_tiles_h.init(p.tiles_h);
+  p.d_bw.init(p.bw); p.d_bh.init(p.bh);
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n * p.n_phase;
   p.block_n = pl->block_n; p.Cout = pl->cout_pad;
   p.a_slot_bytes = pl->a_slot_bytes; p.b_slot_bytes = pl->b_slot_bytes; p.n_a = pl->n_a; p.n_b = pl->n_b;
