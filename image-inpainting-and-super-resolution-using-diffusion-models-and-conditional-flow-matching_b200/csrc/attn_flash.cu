@@ -187,23 +187,22 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
     tc_fence_before();            // order this thread's TMEM reads before the next block's MMAs (issued after the next sync)
   }
 
-  // ---- normalise, store (4 lanes write one row's 64 B run per instruction) ----
+  // ---- normalise, store: this thread's row, 64 B per chunk as two 256-bit stores (whole sectors) ----
   const float inv = 1.0f / l_run;
-  const int row_in_tile = (r & ~3);
-  bf16* op = p.out + ((long long)b * p.T + mt * AF_M + row_in_tile) * p.C + h * D + 8 * (lane & 3);
+  if (mt * AF_M + r < p.T) {
+    bf16* op = p.out + ((long long)b * p.T + mt * AF_M + r) * p.C + h * D;
 #pragma unroll
-  for (int c0 = 0; c0 < D; c0 += 32) {
-    uint4 ov[4];
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint4 ov[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162* o2 = (__nv_bfloat162*)&ov[i];
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162* o2 = (__nv_bfloat162*)&ov[i];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(o[c0 + i * 8 + 2 * q] * inv, o[c0 + i * 8 + 2 * q + 1] * inv);
+        for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(o[c0 + i * 8 + 2 * q] * inv, o[c0 + i * 8 + 2 * q + 1] * inv);
+      }
+      stg256(op + c0, ov[0], ov[1]);
+      stg256(op + c0 + 16, ov[2], ov[3]);
     }
-    quad_transpose(ov, lane);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (mt * AF_M + row_in_tile + k < p.T) *(uint4*)(op + (long long)k * p.C + c0) = ov[k];
   }
   tc_fence_before();
   __syncthreads();

@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   mbar_wait(bar_o, 0);
   tc_fence_after();
   const float inv = 1.0f / sum;
-  // 4 lanes write one row's 64 B run per instruction (quad transpose) instead of 32 half-sector stores
-  bf16* op = p.out + ((long long)(row0 + mt * AT_M + (r & ~3))) * p.C + h * AT_D + 8 * (lane & 3);
+  // each thread owns one output row: 64 B per chunk as two 256-bit stores (whole sectors)
+  bf16* op = p.out + ((long long)(row0 + mt * AT_M + r)) * p.C + h * AT_D;
 #pragma unroll
   for (int c0 = 0; c0 < AT_D; c0 += 32) {
     uint32_t v[32];
@@ -156,9 +156,8 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
       for (int q = 0; q < 4; ++q)
         o2[q] = __floats2bfloat162_rn(__uint_as_float(v[i * 8 + 2 * q]) * inv, __uint_as_float(v[i * 8 + 2 * q + 1]) * inv);
     }
-    quad_transpose(o, lane);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) *(uint4*)(op + (long long)k * p.C + c0) = o[k];
+    stg256(op + c0, o[0], o[1]);
+    stg256(op + c0 + 16, o[2], o[3]);
   }
   tc_fence_before();
   __syncthreads();

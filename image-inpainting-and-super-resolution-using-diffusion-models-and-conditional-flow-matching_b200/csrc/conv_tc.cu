@@ -87,9 +87,8 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers (shared by the single-CTA and the CTA-pair kernel)
 // ------------------------------------------------------------------------------------------------
-// One accumulator row (= output pixel) as the epilogue sees it.  gpix / gvalid describe the 4 rows of this lane's
-// aligned lane group (rows (lane & ~3) + k), which the transposed loads / stores touch.
-struct EpiRow { bool valid; int n, h, w; long long pix; long long gpix[4]; uint32_t gvalid; };
+// One accumulator row (= output pixel) as the epilogue sees it.
+struct EpiRow { bool valid; int n, h, w; long long pix; };
 
 struct TileCoord { int nt, ph, tw, th, tb; };
 // tile index -> (N tile, sub-pixel phase, spatial tile).  N tile and phase vary fastest, so the CTAs that share an
@@ -118,9 +117,6 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& p, int pt,
   p.d_tiles_h.divmod(mt, &c.tb, &c.th);
   return c;
 }
-// kUniform: every tile row carries a pixel and the 4 rows of a lane group are neighbouring pixels of one image row
-// (all power-of-two maps) - the group's pixel indices follow by arithmetic and no per-row state is kept.
-template <bool kUniform>
 __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCoord& c, int row) {
   EpiRow r;
   int wi, hi, ni, t;
@@ -134,43 +130,22 @@ __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCo
   } else {
     r.pix = ((long long)r.n * p.H + r.h) * p.W + r.w;
   }
-  // pixel index / validity of the 4 rows of this lane's group (any box shape: rows of a group need not be neighbours)
-  const int lane = threadIdx.x & 31, g0 = lane & ~3;
-  r.gvalid = 0;
-  if (kUniform) {
-    const int step = p.n_phase == 4 ? 2 : 1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r.gpix[k] = r.pix + (long long)((k - (lane & 3)) * step);
-    r.gvalid = r.valid ? 15u : 0u;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      r.gpix[k] = __shfl_sync(0xffffffffu, r.pix, g0 + k);
-      r.gvalid |= (uint32_t)__shfl_sync(0xffffffffu, (int)r.valid, g0 + k) << k;
-    }
-  }
   return r;
 }
 // rows[half] without dynamic indexing (which would put the two EpiRows in local memory): field-wise selects
 __device__ __forceinline__ EpiRow epi_pick(const EpiRow& a, const EpiRow& b, bool second) {
   EpiRow r;
   r.valid = second ? b.valid : a.valid; r.n = second ? b.n : a.n; r.h = second ? b.h : a.h; r.w = second ? b.w : a.w;
-  r.pix = second ? b.pix : a.pix; r.gvalid = second ? b.gvalid : a.gvalid;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) r.gpix[k] = second ? b.gpix[k] : a.gpix[k];
+  r.pix = second ? b.pix : a.pix;
   return r;
 }
-// issue the residual loads of one 32-channel chunk early (they are the only DRAM-latency operand of the epilogue),
-// in the transposed (coalesced) pattern: res[k] = 8 channels (lane & 3) of row (lane & ~3) + k
+// issue the residual loads of one 32-channel chunk early (they are the only DRAM-latency operand of the epilogue):
+// this lane's row, 64 bytes as two 256-bit loads
 __device__ __forceinline__ void epi_load_res(const TcParams& p, const EpiRow& r, int lane, int cg, uint4 (&res)[4]) {
-  if (p.res0) {
-    const int cj = cg + 8 * (lane & 3);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long pix = r.gpix[k];
-      const bf16* rp = (cg < p.R0) ? p.res0 + pix * p.R0 + cj : p.res1 + pix * p.R1 + (cj - p.R0);
-      res[k] = ((r.gvalid >> k) & 1u) ? __ldg((const uint4*)rp) : make_uint4(0, 0, 0, 0);
-    }
+  if (p.res0 && r.valid) {
+    const bf16* rp = (cg < p.R0) ? p.res0 + r.pix * p.R0 + cg : p.res1 + r.pix * p.R1 + (cg - p.R0);
+    ldg256(rp, res[0], res[1]);
+    ldg256(rp + 16, res[2], res[3]);
   }
 }
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
@@ -179,7 +154,6 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   return v;
 }
 // accumulator chunk (32 fp32 from TMEM) + bias + embedding vector + residual -> bf16 NHWC (or fp32 NCHW for the head).
-// Called by all 32 lanes (it shuffles); `res` arrives in the transposed pattern of epi_load_res.
 __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, int lane, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
                                            uint32_t s_bias_addr) {
   float f[32];
@@ -207,8 +181,8 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
       if (cg + j < p.cout_real) op[(long long)(cg + j) * hw] = f[j];
     return;
   }
+  if (!r.valid) return;
   if (p.res0) {
-    quad_transpose(res, lane);          // back to "this lane's row": single rounding of acc + bias + emb + residual
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
@@ -223,11 +197,9 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
 #pragma unroll
     for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
   }
-  quad_transpose(o, lane);
-  const int cj = cg + 8 * (lane & 3);
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if ((r.gvalid >> k) & 1u) *(uint4*)(p.out + r.gpix[k] * p.Cout + cj) = o[k];
+  bf16* op = p.out + r.pix * p.Cout + cg;      // 64 B of this row: two full 32 B sectors per store instruction
+  stg256(op, o[0], o[1]);
+  stg256(op + 16, o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,7 +210,6 @@ struct Ring { int slot; uint32_t phase; int n; __device__ __forceinline__ void n
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-template <bool kUniform>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -386,8 +357,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int nt = tc.nt;
-      const EpiRow row0 = epi_decode_row<kUniform>(p, tc, quad * 32 + lane);
-      const EpiRow row1 = p.mh == 2 ? epi_decode_row<kUniform>(p, tc, 128 + quad * 32 + lane) : row0;
+      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+      const EpiRow row1 = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
         const int half = sub >= chunks_per_half ? 1 : 0;          // mh <= 2
@@ -433,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // kMH: 128-row M-halves per CTA, a compile-time constant so that the kMH = 1 instances (N >= 192 layers, most of
 // them short-K and epilogue-bound) carry none of the two-half bookkeeping
-template <bool kUniform, int kMH>
+template <int kMH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -585,8 +556,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
-      const EpiRow row0 = epi_decode_row<kUniform>(p, tc, quad * 32 + lane);
-      const EpiRow row1 = kMH == 2 ? epi_decode_row<kUniform>(p, tc, 128 + quad * 32 + lane) : row0;   // kMH = 1: never selected
+      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+      const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;   // kMH = 1: never selected
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
         const int half = (kMH == 2 && sub >= chunks_per_half) ? 1 : 0;
@@ -638,7 +609,6 @@ struct TcConvPlan {
   bool pair = false;                    // CTA-pair (cta_group::2) kernel
   int a_slot_bytes = 0, b_slot_bytes = 0, n_a = 0, n_b = 0, a_tile_bytes = 0, a_halo_bytes = 0;
   int kc = 64, valid_rows = 0;
-  bool uniform = false;        // every tile row is a pixel, lane groups of 4 are neighbours in one image row
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
@@ -730,7 +700,6 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   pl->bh = std::min(Hg, rows / pl->bw);
   pl->bn = pl->bh == Hg ? std::max(1, rows / (pl->bw * pl->bh)) : 1;
   pl->valid_rows = pl->bw * pl->bh * pl->bn;
-  pl->uniform = pl->valid_rows == rows && pl->bw % 4 == 0 && Hg % pl->bh == 0 && !env_off("CFM_TC_GENERIC_ROWS");
   const int eks = op.ups ? 2 : ks;          // taps per axis the kernel walks
   // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous), fill its rows exactly and
   // an image row must be a whole number of 8-row swizzle atoms
@@ -802,12 +771,9 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   op.tc = pl;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(conv_tc_kernel, smem) failed"; return CFM_ERR_CUDA;
     }
     attr_set = true;
@@ -878,15 +844,14 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
     LaunchCfg lc(dim3(2 * std::min(pair_tiles, e.sm_count / 2)), dim3(TC_THREADS), TC_SMEM_BYTES, st, 2, pdl_enabled());
-    auto kern = pl->mh == 2 ? (pl->uniform ? conv_tc2_kernel<true, 2> : conv_tc2_kernel<false, 2>)
-                            : (pl->uniform ? conv_tc2_kernel<true, 1> : conv_tc2_kernel<false, 1>);
+    auto kern = pl->mh == 2 ? conv_tc2_kernel<2> : conv_tc2_kernel<1>;
     cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, kern, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
     if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
     return 0;
   }
   const int grid = std::min(p.n_tiles, e.sm_count);
   LaunchCfg lc(dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, 1, pdl_enabled());
-  cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, pl->uniform ? conv_tc_kernel<true> : conv_tc_kernel<false>, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+  cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
   if (ce != cudaSuccess) { e.err = std::string("conv_tc_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
   return 0;
 }

@@ -150,25 +150,15 @@ __host__ __device__ constexpr uint32_t make_idesc_major(int M, int N, int a_mn, 
 }
 
 
-// 4x4 transpose of 16-byte chunks inside each aligned group of 4 lanes: in  c[k] = chunk k of this lane's row,
-// out c[k] = chunk (lane & 3) of the row owned by lane (lane & ~3) + k.  An involution: the same call maps back.
-// It turns "one lane = one 64 B row segment" (32 half-sector accesses per instruction) into "4 lanes = one row
-// segment" (8 fully written 64 B runs per instruction) for the epilogue's global loads and stores.
-__device__ __forceinline__ void quad_transpose(uint4 (&c)[4], int lane) {
-#pragma unroll
-  for (int m = 1; m <= 2; m <<= 1) {
-    const bool up = (lane & m) != 0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      if (a & m) continue;
-      const int b = a | m;
-      const uint4 send = up ? c[a] : c[b];
-      uint4 recv;
-      recv.x = __shfl_xor_sync(0xffffffffu, send.x, m); recv.y = __shfl_xor_sync(0xffffffffu, send.y, m);
-      recv.z = __shfl_xor_sync(0xffffffffu, send.z, m); recv.w = __shfl_xor_sync(0xffffffffu, send.w, m);
-      if (up) c[a] = recv; else c[b] = recv;
-    }
-  }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  A lane that owns a 64-byte run of a row moves it as two whole
+// 32-byte sectors per instruction - no partial-sector traffic and no cross-lane transpose to build wider runs.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
 // ---- thread-block clusters / CTA pairs (cta_group::2) ---------------------------------------------
