@@ -34,6 +34,47 @@ __device__ __forceinline__ float af_ex2(float x) {
   return y;
 }
 
+// One row's 128 scores of a key block (registers) -> running max update, p = 2^(s*scale - m), row sum, and P as bf16
+// in shared memory (K-major SWIZZLE_128B, two 64-key sub-tiles).  kMasked: keys >= n_valid do not exist (last block).
+// Four independent max / sum chains keep the dependent-issue latency of a 128-long reduction off the critical path.
+template <bool kMasked>
+__device__ __forceinline__ void af_softmax_block(const uint32_t (&sv)[4][32], int n_valid, float scale_log2, float& m_run,
+                                                 float& alpha, float& sum, uint8_t* prow, int r) {
+  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (!kMasked || c * 32 + i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+  const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+  const float m_new = fmaxf(m_run, mx * scale_log2);
+  alpha = af_ex2(m_run - m_new);           // 0 for the first block (m_run = -inf)
+  m_run = m_new;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = c * 32;
+    uint8_t* pchunk = prow + (c0 >> 6) * 16384;
+    const int c16 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o4;
+      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cc = c0 + i * 8 + 2 * q;
+        float e0 = af_ex2(fmaf(__uint_as_float(sv[c][i * 8 + 2 * q]), scale_log2, -m_new));
+        float e1 = af_ex2(fmaf(__uint_as_float(sv[c][i * 8 + 2 * q + 1]), scale_log2, -m_new));
+        if (kMasked) { if (cc >= n_valid) e0 = 0.f; if (cc + 1 >= n_valid) e1 = 0.f; }
+        s4[q] += e0 + e1;
+        o2[q] = __floats2bfloat162_rn(e0, e1);
+      }
+      *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+    }
+  }
+  sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+}
+
 template <int D>
 __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constant__ CUtensorMap map, const AttnFlashParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -110,43 +151,16 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
   for (int j = 0; j < p.n_kv; ++j) {
     const int kv0 = j * AF_BK;
     const int n_valid = min(AF_BK, p.T - kv0);           // keys of this block that exist
-    // ---- pass 1: block max ----
+    // ---- the block's 128 scores of this row go to registers once: all four TMEM loads are issued before one wait ----
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
-    float mx = -INFINITY;
-    for (int c0 = 0; c0 < AF_BK; c0 += 32) {
-      if (c0 >= n_valid) break;
-      uint32_t v[32];
-      tmem_ld32(tmem_s + t_row + (uint32_t)c0, v);
-      tmem_ld_wait();
+    uint32_t sv[4][32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-    }
-    const float m_new = fmaxf(m_run, mx * p.scale_log2);
-    const float alpha = af_ex2(m_run - m_new);           // 0 for the first block (m_run = -inf)
-    m_run = m_new;
-    // ---- pass 2: p = 2^(s*scale - m), row sum, P -> shared (bf16, K-major SWIZZLE_128B, 64-key sub-tiles) ----
-    float sum = 0.f;
-    for (int c0 = 0; c0 < AF_BK; c0 += 32) {
-      uint32_t v[32];
-      if (c0 < n_valid) { tmem_ld32(tmem_s + t_row + (uint32_t)c0, v); tmem_ld_wait(); }
-      uint8_t* pchunk = prow + (c0 >> 6) * 16384;
-      const int c16 = (c0 & 63) >> 3;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 o4;
-        __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = c0 + i * 8 + 2 * q;
-          const float e0 = c < n_valid ? af_ex2(fmaf(__uint_as_float(v[i * 8 + 2 * q]), p.scale_log2, -m_new)) : 0.f;
-          const float e1 = c + 1 < n_valid ? af_ex2(fmaf(__uint_as_float(v[i * 8 + 2 * q + 1]), p.scale_log2, -m_new)) : 0.f;
-          sum += e0 + e1;
-          o2[q] = __floats2bfloat162_rn(e0, e1);
-        }
-        *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
-      }
-    }
+    for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + t_row + (uint32_t)(c * 32), sv[c]);
+    tmem_ld_wait();
+    float alpha, sum;
+    if (n_valid == AF_BK) af_softmax_block<false>(sv, n_valid, p.scale_log2, m_run, alpha, sum, prow, r);   // no per-key masks
+    else af_softmax_block<true>(sv, n_valid, p.scale_log2, m_run, alpha, sum, prow, r);
     l_run = l_run * alpha + sum;
     fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy
     tc_fence_before();

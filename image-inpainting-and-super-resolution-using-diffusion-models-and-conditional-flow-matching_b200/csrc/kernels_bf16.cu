@@ -200,9 +200,10 @@ static GnGeom gn_geometry(const Op& op) {
   static const int target = [] { const char* v = getenv("CFM_GN_ITEM_BYTES"); return v ? atoi(v) : 64 * 1024; }();
   // slab: a multiple of `base` dividing C, preferably a whole number of 64-byte DRAM bursts per pixel (32 channels;
   // e.g. 96 for C = 384, where 48-channel slabs would straddle bursts) and at most 64 channels when that works
+  static const int pref_slab = [] { const char* v = getenv("CFM_GN_PREF_SLAB"); return v ? atoi(v) : 64; }();
   int slab = 0;
   for (int sl = base; sl <= GN_MAX_SLAB; sl += base)
-    if (C % sl == 0 && sl % 32 == 0) { if (slab == 0 || sl <= 64) slab = sl; }
+    if (C % sl == 0 && sl % 32 == 0) { if (slab == 0 || sl <= pref_slab) slab = sl; }
   if (slab == 0) { slab = base; while (slab * 2 <= 64 && C % (slab * 2) == 0) slab *= 2; }
   // bring the per-CTA bytes to the target: split the pixels over a cluster first, then narrow the slab (>= 64 B per pixel)
   int cs = 1;
