@@ -41,7 +41,8 @@ class DdpmTablesC(C.Structure):
 
 class DdpmOptionsC(C.Structure):
     _fields_ = [("mode", C.c_int32), ("pad_value", C.c_float), ("replace_below_step", C.c_int32),
-                ("noise_condition", C.c_int32), ("use_graph", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("noise_condition", C.c_int32), ("use_graph", C.c_uint32), ("n_corrector", C.c_uint32),
+                ("corrector_delta", C.c_float), ("reserved", C.c_uint32 * 1)]
 
 
 # name -> (restype, argtypes); mirrors include/cfm_b200.h one to one

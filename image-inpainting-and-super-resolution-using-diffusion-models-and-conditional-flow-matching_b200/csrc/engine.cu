@@ -903,6 +903,10 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   const long long n = (long long)batch * e.x_channels() * S * S;
   const bool repl = opt->mode == CFM_DDPM_REPLACEMENT;
   const bool amort = opt->mode == CFM_DDPM_AMORTIZED;
+  const int n_corr = (int)opt->n_corrector;
+  if (n_corr < 0 || n_corr > 16) return fail(e, CFM_ERR_INVALID, "n_corrector out of range");
+  if (n_corr > 0 && !repl) return fail(e, CFM_ERR_INVALID, "corrector steps are implemented for Replacement conditioning only");
+  const int n_slots = 2 + n_corr;
   int rc = ensure_batch(e, batch); if (rc) return rc;
   if ((rc = ensure_sampler(e, n, condition_dev ? n : 0, batch, Ns))) return rc;
   e.launches = 0;
@@ -921,8 +925,18 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
     s.blend_next = blend_at(i - 1);
     s.noise_condition = opt->noise_condition; s.pad_value = opt->pad_value;
     if (s.blend_next) { s.sa = tb->sqrt_alphas_cumprod[i - 1]; s.sb = tb->sqrt_one_minus_alphas_cumprod[i - 1]; }
-    s.final_clip = i == 0;
+    s.final_clip = i == 0 && n_corr == 0;      // with correctors the last corrector of step 0 clips
     s.chain_index = i;
+    s.n_slots = n_slots;
+    if (n_corr > 0) {
+      // un-fused order: [blend i] -> U-Net -> posterior draw -> n_corr x (U-Net -> Langevin step)
+      s.blend_cur = blend_at(i); s.blend_next = 0;
+      s.sa_cur = tb->sqrt_alphas_cumprod[i]; s.sb_cur = tb->sqrt_one_minus_alphas_cumprod[i];
+      s.corr_r = 1.0f / tb->sqrt_one_minus_alphas_cumprod[i];
+      const double dt = (1.0 - 0.00001) / Ns;            // (tmax - tmin) / Ns, sde_diffusion.py:130-132
+      s.corr_cd = (float)(0.5 * dt * (double)opt->corrector_delta);
+      s.corr_cn = (float)std::sqrt(dt * (double)opt->corrector_delta);
+    }
     tab[k] = s;
     tt[k] = tb->model_time[i];
   }
@@ -932,23 +946,31 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   CU_CHECK(e, cudaMemcpyAsync(e.t_table, tt.data(), sizeof(float) * Ns, cudaMemcpyHostToDevice, st));
   CU_CHECK(e, cudaMemsetAsync(e.step_counter, 0, sizeof(int), st));
   CU_CHECK(e, cudaStreamSynchronize(st));   // host staging vectors go out of scope below
-  if (blend_at(Ns - 1)) {
+  if (n_corr == 0 && blend_at(Ns - 1)) {
     ddpm_blend_kernel<<<ew_blocks(e, n), 256, 0, st>>>(e.x_work, e.cond_work, tb->sqrt_alphas_cumprod[Ns - 1],
         tb->sqrt_one_minus_alphas_cumprod[Ns - 1], opt->pad_value, opt->noise_condition,
         noise_dev ? noise_dev + ((long long)(Ns - 1) * 2) * n : nullptr, seed, 2u * (Ns - 1), n);
     e.launches++;
   }
   auto body = [&](cudaStream_t s2) -> int {
+    if (n_corr > 0) { ddpm_blend_table_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.cond_work, e.ddpm_table, e.step_counter, noise_dev, seed, n); e.launches++; }
     int r = forward_impl(e, batch, e.x_work, amort ? e.cond_work : nullptr, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
     if (r) return r;
     ddpm_step_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter,
                                                      condition_dev ? e.cond_work : nullptr, noise_dev, seed, n);
+    for (int c = 0; c < n_corr; ++c) {
+      r = forward_impl(e, batch, e.x_work, nullptr, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
+      if (r) return r;
+      ddpm_corrector_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter, noise_dev, seed, 2 + c, c == n_corr - 1, n);
+      e.launches++;
+    }
     counter_add_kernel<<<1, 1, 0, s2>>>(e.step_counter);
     e.launches += 2;
     return 0;
   };
   char key[160];
-  snprintf(key, sizeof(key), "ddpm:%d:%d:%d:%p:%llu", batch, opt->mode, condition_dev != nullptr, (const void*)noise_dev, (unsigned long long)seed);
+  uint32_t d_bits; std::memcpy(&d_bits, &opt->corrector_delta, 4);
+  snprintf(key, sizeof(key), "ddpm:%d:%d:%d:%p:%llu:%d:%08x", batch, opt->mode, condition_dev != nullptr, (const void*)noise_dev, (unsigned long long)seed, n_corr, d_bits);
   if (opt->use_graph && !e.graphs.count(key)) {
     if ((rc = forward_impl(e, batch, e.x_work, amort ? e.cond_work : nullptr, nullptr, 0.f, nullptr, e.v_buf, st, e.t_table, e.step_counter))) return rc;
   }

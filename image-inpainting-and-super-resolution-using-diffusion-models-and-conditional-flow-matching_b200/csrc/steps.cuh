@@ -81,6 +81,11 @@ struct DdpmStepScalars {
   int blend_next; int noise_condition; float sa, sb, pad_value;   // sqrt_ac[i-1], sqrt_1mac[i-1]
   int final_clip;              // i == 0: clip(x, -1, 1)
   int chain_index;             // i (noise slots / Philox streams are indexed by it)
+  // Langevin corrector steps (sampling.py:241-250): the blend of step i then runs as its own launch BEFORE the U-Net
+  // call (blend_cur) because corrector evaluations sit between the posterior draw and the next step's blend
+  int n_slots;                 // noise slots per chain step: 2 + n_corrector
+  int blend_cur; float sa_cur, sb_cur;   // sqrt_ac[i], sqrt_1mac[i]
+  float corr_r, corr_cd, corr_cn;        // 1/sqrt(1-abar_i), 0.5*dt*delta, sqrt(dt*delta)
 };
 
 // x: in = xi (already blended for step i), out = state handed to the next U-Net call.
@@ -93,9 +98,10 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
                                  unsigned long long seed, long long n) {
   const DdpmStepScalars s = table[*step_counter];
   const int ci = s.chain_index;
-  const float* z_post = noise ? noise + ((long long)ci * 2 + 1) * n : nullptr;
-  const float* z_blend = (noise && s.blend_next) ? noise + ((long long)(ci - 1) * 2) * n : nullptr;
-  const unsigned stream_post = 2u * ci + 1u, stream_blend = 2u * (ci - 1);
+  const int ns = s.n_slots;
+  const float* z_post = noise ? noise + ((long long)ci * ns + 1) * n : nullptr;
+  const float* z_blend = (noise && s.blend_next) ? noise + ((long long)(ci - 1) * ns) * n : nullptr;
+  const unsigned stream_post = (unsigned)(ns * ci + 1), stream_blend = (unsigned)(ns * (ci - 1));
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float xi = x[i];
@@ -116,6 +122,49 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
       nx = (c == s.pad_value) ? nx : nc;
     }
     if (s.final_clip) nx = fminf(fmaxf(nx, -1.0f), 1.0f);
+    x[i] = nx;
+  }
+}
+
+// Blend of the CURRENT step from the device table (chains with corrector steps): x = where(cond == pad, x, q_sample(cond)).
+__global__ void ddpm_blend_table_kernel(float* __restrict__ x, const float* __restrict__ cond,
+                                        const DdpmStepScalars* __restrict__ table, const int* __restrict__ step_counter,
+                                        const float* __restrict__ noise, unsigned long long seed, long long n) {
+  const DdpmStepScalars s = table[*step_counter];
+  if (!s.blend_cur) return;
+  const float* z_blend = noise ? noise + ((long long)s.chain_index * s.n_slots) * n : nullptr;
+  const unsigned stream = (unsigned)(s.n_slots * s.chain_index);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float c = cond[i];
+    float nc = c;
+    if (s.noise_condition) {
+      const float z = z_blend ? z_blend[i] : philox_normal(seed, stream, (unsigned long long)i);
+      nc = __fadd_rn(__fmul_rn(s.sa_cur, c), __fmul_rn(s.sb_cur, z));
+    }
+    if (!(c == s.pad_value)) x[i] = nc;
+  }
+}
+
+// Langevin corrector (sampling.py:241-250, sde_diffusion.py:214-217): with eps = model(x, t_i),
+//   x0 = clip(a x - b eps),  score = -(x0 / sqrt(1 - abar_i)),  x += (0.5 dt delta) score + sqrt(dt delta) z
+// in the reference's order of fp32 operations.  `last`: final corrector of chain step 0 -> clip(x, -1, 1).
+__global__ void ddpm_corrector_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                      const DdpmStepScalars* __restrict__ table, const int* __restrict__ step_counter,
+                                      const float* __restrict__ noise, unsigned long long seed, int slot, int last, long long n) {
+  const DdpmStepScalars s = table[*step_counter];
+  const float* zc = noise ? noise + ((long long)s.chain_index * s.n_slots + slot) * n : nullptr;
+  const unsigned stream = (unsigned)(s.n_slots * s.chain_index + slot);
+  const bool clip = last && s.chain_index == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float xi = x[i];
+    float x0 = __fsub_rn(__fmul_rn(s.a, xi), __fmul_rn(s.b, eps[i]));
+    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    const float score = -__fmul_rn(s.corr_r, x0);
+    const float z = zc ? zc[i] : philox_normal(seed, stream, (unsigned long long)i);
+    float nx = __fadd_rn(xi, __fadd_rn(__fmul_rn(s.corr_cd, score), __fmul_rn(s.corr_cn, z)));
+    if (clip) nx = fminf(fmaxf(nx, -1.0f), 1.0f);
     x[i] = nx;
   }
 }

@@ -231,7 +231,7 @@ class EpsModel:
 def _noise_tensor(noise, Ns, x):
     if noise is None or torch.is_tensor(noise):
         return noise
-    raise TypeError("noise must be a [Ns, 2, B*C*H*W] tensor or None")
+    raise TypeError("noise must be a [Ns, 2 + n_corrector, B*C*H*W] tensor or None")
 
 
 def get_prior_sample_fn(eps_model, ddpm: DDPM, conditioning=None, likelihood=None, *, noise=None, seed: int = 0,
@@ -256,8 +256,8 @@ def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *
                               use_graph: bool = False) -> Callable:
     if not isinstance(eps_model, EpsModel):
         raise TypeError("wrap the network as EpsModel(network, ddpm) so the sampler can run on the engine")
-    if getattr(conditioning, "n_corrector", 0):
-        raise NotImplementedError("Langevin corrector steps (n_corrector > 0) are a 'next' row (SURVEY 8f.3)")
+    if getattr(conditioning, "n_corrector", 0) and not isinstance(conditioning, Replacement):
+        raise NotImplementedError("Langevin corrector steps (n_corrector > 0) run on the engine for Replacement conditioning only")
 
     if isinstance(conditioning, Amortized):
         @torch.no_grad()
@@ -277,7 +277,8 @@ def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *
             return eps_model.network.engine().sample_ddpm(
                 xT, ddpm.tables(), mode="replacement", condition=condition, pad_value=float(pad),
                 replace_below_step=int(ddpm.Ns * conditioning.start_fraction), noise_condition=bool(conditioning.noise),
-                noise=_noise_tensor(noise, ddpm.Ns, xT), seed=seed, use_graph=use_graph)
+                noise=_noise_tensor(noise, ddpm.Ns, xT), seed=seed, use_graph=use_graph,
+                n_corrector=int(getattr(conditioning, "n_corrector", 0)), corrector_delta=float(conditioning.delta))
         return sample
 
     raise NotImplementedError(f"no engine sampler for conditioning {type(conditioning).__name__}")

@@ -220,7 +220,8 @@ class Engine:
     def sample_ddpm(self, xT: torch.Tensor, tables: Dict[str, torch.Tensor], mode: str = "prior",
                     condition: Optional[torch.Tensor] = None, pad_value: float = -2.0,
                     replace_below_step: Optional[int] = None, noise_condition: bool = True,
-                    noise: Optional[torch.Tensor] = None, seed: int = 0, use_graph: bool = False) -> torch.Tensor:
+                    noise: Optional[torch.Tensor] = None, seed: int = 0, use_graph: bool = False,
+                    n_corrector: int = 0, corrector_delta: float = 0.1) -> torch.Tensor:
         Ns = int(tables["sqrt_alphas_cumprod"].numel())
         x = _as_f32_cuda(xT, self.device).clone()
         cd = None if condition is None else _as_f32_cuda(condition, self.device)
@@ -240,10 +241,12 @@ class Engine:
         opt.replace_below_step = Ns if replace_below_step is None else int(replace_below_step)
         opt.noise_condition = int(noise_condition)
         opt.use_graph = int(use_graph)
+        opt.n_corrector = int(n_corrector)
+        opt.corrector_delta = float(corrector_delta)
         nd = None
         if noise is not None:
             nd = _as_f32_cuda(noise, self.device)
-            assert nd.numel() == Ns * 2 * x.numel(), "noise must be [Ns, 2, B*C*H*W]"
+            assert nd.numel() == Ns * (2 + int(n_corrector)) * x.numel(), "noise must be [Ns, 2 + n_corrector, B*C*H*W]"
         with torch.cuda.device(self.device):
             rc = self.lib.cfm_sample_ddpm(self._h, x.shape[0], _ptr(x), _ptr(cd), C.byref(tb), C.byref(opt),
                                           _ptr(nd), C.c_uint64(seed), _stream_ptr(self.device))

@@ -173,15 +173,17 @@ typedef struct cfm_ddpm_options {
   int32_t replace_below_step;  /* blend while i < this (int(Ns * start_fraction))            */
   int32_t noise_condition;     /* Replacement: q_sample the condition (1) or use it raw (0)  */
   uint32_t use_graph;
-  uint32_t reserved[3];
+  uint32_t n_corrector;        /* Langevin corrector steps after every predictor step (Replacement only; sampling.py:241-256) */
+  float   corrector_delta;     /* conditioning.delta: step = 0.5*dt*delta*score + sqrt(dt*delta)*z, dt = (1 - 1e-5)/Ns      */
+  uint32_t reserved[1];
 } cfm_ddpm_options;
 
 /* Reverse chain i = Ns-1 .. 0.  x_dev [B,C,H,W] holds xT on entry and clip(x0,-1,1) on
  * return.  condition_dev: [B,C,H,W] (Replacement: image with pad_value holes; Amortized:
  * the conditioning image, concatenated on channels) or NULL for PRIOR.
- * Noise: if noise_dev != NULL it is [Ns, 2, B*C*H*W] fp32: slot (i,0) is the q_sample
- * draw for the mask blend at step i, slot (i,1) the posterior draw at step i (the
- * reference's two randn_like calls, in call order).  Otherwise a counter-based Philox
+ * Noise: if noise_dev != NULL it is [Ns, 2 + n_corrector, B*C*H*W] fp32: slot (i,0) is the q_sample
+ * draw for the mask blend at step i, slot (i,1) the posterior draw at step i, slots (i,2..) the
+ * corrector draws (the reference's randn_like calls, in call order).  Otherwise a counter-based Philox
  * generator seeded with `seed` is used on the device. */
 int cfm_sample_ddpm(cfm_engine* e, int32_t batch, float* x_dev, const float* condition_dev,
                     const cfm_ddpm_tables* tables, const cfm_ddpm_options* opt,

@@ -125,7 +125,9 @@ def corrector_step(tb, eps_model, Ns, xi, i, delta, noise):
     x0 = torch.clip(tb["sqrt_recip_alphas_cumprod"][i] * xi - tb["sqrt_recipm1_alphas_cumprod"][i] * eps, -1, 1)
     score = -tb["recip_sqrt_m1_alphas_cumprod"][i] * x0
     dt = (1.0 - 0.00001) / Ns
-    return xi + 0.5 * dt * delta * score + math.sqrt(dt * delta) * noise(xi.shape)
+    drift = 0.5 * dt * delta * score
+    nz = math.sqrt(dt * delta) * noise(xi.shape)
+    return xi + (drift + nz)            # the reference writes ``xi += drift + noise``
 
 
 # --- condition construction --------------------------------------------------------------

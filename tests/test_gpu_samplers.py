@@ -233,3 +233,49 @@ def test_classifier_free_guidance_euler(pkg, cuda, precision, tol):
     _, _, unc = small_cfm(pkg, cuda, precision)
     with pytest.raises(Exception):
         pkg.sample_euler(unc, x0.to(cuda), t_span, guidance_weight=w)   # needs a class-conditional model
+
+
+class SlotTape:
+    """Replays a [Ns, 2 + n_corrector, n] noise tensor in the reference's call order for the Replacement sampler:
+    per chain step i (descending): q_sample draw (slot 0), posterior draw (slot 1, skipped at i = 0), corrector draws."""
+
+    def __init__(self, Ns, shape, n_corrector):
+        self.t = torch.randn(Ns, 2 + n_corrector, int(np.prod(shape)))
+        self.order = []
+        for i in reversed(range(Ns)):
+            self.order.append((i, 0))
+            if i > 0:
+                self.order.append((i, 1))
+            self.order += [(i, 2 + c) for c in range(n_corrector)]
+        self.pos = 0
+
+    def __call__(self, shape):
+        i, s = self.order[self.pos]
+        self.pos += 1
+        return self.t[i, s].reshape(shape)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 6e-2)])
+def test_ddpm_replacement_with_langevin_corrector(pkg, cuda, precision, tol):
+    """Predictor-corrector Replacement chain (sampling.py:241-256): one extra U-Net evaluation and one Langevin step
+    per corrector, the mask blend of step i running before that step's U-Net call."""
+    Ns, n_corr, delta = 24, 2, 0.1
+    net, ddpm, eps_oracle = ddpm_setup(pkg, cuda, precision, 1, Ns)
+    torch.manual_seed(4)
+    img = torch.rand(3, 1, 16, 16) * 2 - 1
+    cond = img.clone(); cond[:, :, 4:10, 6:12] = -2.0
+    xT = torch.randn(3, 1, 16, 16)
+    tape = SlotTape(Ns, xT.shape, n_corr)
+    want = D.sample_replacement(eps_oracle, Ns, xT, cond, tape, n_corrector=n_corr, delta=delta)
+    assert tape.pos == len(tape.order)
+    for use_graph in (False, True):
+        fn = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm,
+                                           pkg.Replacement(delta=delta, start_fraction=1.0, noise=True, n_corrector=n_corr),
+                                           pkg.InPainting(6, -2.0), noise=tape.t, use_graph=use_graph)
+        got = fn(xT.to(cuda), cond.to(cuda)).cpu()
+        assert got.abs().max() <= 1.0
+        d = rel_l2(got, want)
+        print(f"ddpm replacement + {n_corr} correctors [{precision}, graph={use_graph}] drift = {d:.3e}")
+        assert d < tol
+    with pytest.raises(NotImplementedError):
+        pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(0.9, 1, 0.1), pkg.InPainting(6, -2.0))
