@@ -21,8 +21,8 @@ void* tensor_ptr(const Engine& e, int id, int B);
 
 constexpr int AT_T = 256, AT_D = 64, AT_M = 128;
 constexpr int AT_V_OFF = 0, AT_Q_OFF = 32768, AT_K_OFF = 49152, AT_P_OFF = 32768;
-constexpr int AT_BAR_OFF = 98304;
-constexpr int AT_SMEM = AT_BAR_OFF + 64 + 1024;
+constexpr int AT_BAR_OFF = 98304, AT_XCH_OFF = 98304 + 64;
+constexpr int AT_SMEM = AT_XCH_OFF + 2 * 256 * 4 + 1024;
 
 struct AttnTcParams { int heads, C, new_order; float scale_log2; bf16* out; };
 
@@ -32,7 +32,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map, const AttnTcParams p) {
+// 256 threads per CTA: thread t and thread t + 128 share query row (t & 127) - warps w and w + 4 may both read TMEM
+// lanes 32 (w & 3) .. +31 - and split the 256 keys (softmax) / the 64 output channels (epilogue) between them, so the
+// serial load -> max -> exp -> store chain of a row is half as long and 16 warps per SM hide its latency.
+__global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bar_qk = (uint64_t*)(smem + AT_BAR_OFF);
@@ -40,6 +43,7 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   uint64_t* bar_s = bar_qk + 2;
   uint64_t* bar_o = bar_qk + 3;
   uint32_t* tmem_slot = (uint32_t*)(bar_qk + 4);
+  float* xch = (float*)(smem + AT_XCH_OFF);            // [2][256]: per-thread partial max / sum for the row partner
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
   const int qcol = p.new_order ? h * AT_D : h * 3 * AT_D;
@@ -82,23 +86,28 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
     __syncwarp();
   }
 
-  // ---- softmax: thread = query row (TMEM lane) ----
+  // ---- softmax: thread = (query row, key half) ----
+  const int r = tid & 127;                     // query row = TMEM lane
+  const int half = tid >> 7;                   // keys [128 half, +128) / output channels [32 half, +32)
   mbar_wait(bar_s, 0);
   tc_fence_after();
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int cbase = half * 128;
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < AT_T; c0 += 32) {
+  for (int c0 = 0; c0 < 128; c0 += 32) {
     uint32_t v[32];
-    tmem_ld32(t_row + (uint32_t)c0, v);
+    tmem_ld32(t_row + (uint32_t)(cbase + c0), v);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
   }
+  xch[tid] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, xch[tid ^ 128]);
   const float mxs = mx * p.scale_log2;
   float sum = 0.f;
-  const int r = tid;
   uint8_t* prow = smem + AT_P_OFF + r * 128;
-  for (int c0 = 0; c0 < AT_T; c0 += 32) {
+  for (int c0 = cbase; c0 < cbase + 128; c0 += 32) {
     uint32_t v[32];
     tmem_ld32(t_row + (uint32_t)c0, v);
     tmem_ld_wait();
@@ -118,9 +127,11 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
       *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
     }
   }
+  xch[256 + tid] = sum;
   fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy
   tc_fence_before();
   __syncthreads();
+  sum += xch[256 + (tid ^ 128)];
 
   if (warp == 0) {
     mbar_wait(bar_v, 0);
@@ -141,10 +152,10 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
   mbar_wait(bar_o, 0);
   tc_fence_after();
   const float inv = 1.0f / sum;
-  // each thread owns one output row: 64 B per chunk as two 256-bit stores (whole sectors)
-  bf16* op = p.out + ((long long)(row0 + mt * AT_M + r)) * p.C + h * AT_D;
-#pragma unroll
-  for (int c0 = 0; c0 < AT_D; c0 += 32) {
+  // each thread stores 32 channels (64 B) of its row as two 256-bit stores (whole sectors)
+  {
+    const int c0 = half * 32;
+    bf16* op = p.out + ((long long)(row0 + mt * AT_M + r)) * p.C + h * AT_D + c0;
     uint32_t v[32];
     tmem_ld32(t_row + (uint32_t)c0, v);
     tmem_ld_wait();
@@ -156,8 +167,8 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(const __grid_constant__
       for (int q = 0; q < 4; ++q)
         o2[q] = __floats2bfloat162_rn(__uint_as_float(v[i * 8 + 2 * q]) * inv, __uint_as_float(v[i * 8 + 2 * q + 1]) * inv);
     }
-    stg256(op + c0, o[0], o[1]);
-    stg256(op + c0 + 16, o[2], o[3]);
+    stg256(op, o[0], o[1]);
+    stg256(op + 16, o[2], o[3]);
   }
   tc_fence_before();
   __syncthreads();
@@ -206,7 +217,7 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.heads = op.heads; p.C = op.Cin; p.new_order = e.cfg.use_new_attention_order;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
-  LaunchCfg lc(dim3(AT_T / AT_M, B * op.heads), dim3(128), AT_SMEM, st, 1, pdl_enabled());
+  LaunchCfg lc(dim3(AT_T / AT_M, B * op.heads), dim3(256), AT_SMEM, st, 1, pdl_enabled());
   if (cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel, it->second, p) != cudaSuccess) { e.err = "attn_tc_kernel launch failed"; return CFM_ERR_CUDA; }
   return 0;
 }

@@ -604,7 +604,7 @@ static int forward_impl(Engine& e, int B, const float* x, const float* cond, con
   const int rows = uniform ? std::max(1, e.cfg.num_classes) : B;
   const int n = std::max(rows, B);
   setup_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, rows, uniform, t_scalar, t_dev, t_table, step_counter, (const long long*)y, e.t_rows, e.label_idx, e.row_of_sample);
-  time_hidden_kernel<<<rows, 256, sizeof(float) * e.cfg.model_channels, st>>>(e.t_rows, e.cfg.model_channels, e.ted, e.w_t1, e.b_t1, e.hidden);
+  time_hidden_kernel<<<dim3(rows, (e.ted + 7) / 8), 256, sizeof(float) * e.cfg.model_channels, st>>>(e.t_rows, e.cfg.model_channels, e.ted, e.w_t1, e.b_t1, e.hidden);
   linear_rows_kernel<<<dim3((e.ted + 7) / 8, rows), 256, 0, st>>>(e.hidden, e.ted, e.w_t2, e.b_t2, e.ted, drop_labels ? nullptr : e.label_emb, e.label_idx, 1, e.semb);
   linear_rows_kernel<<<dim3((e.emb_total + 7) / 8, rows), 256, 0, st>>>(e.semb, e.ted, e.w_emb_cat, e.b_emb_cat, e.emb_total, nullptr, nullptr, 0, e.emb_out);
   e.launches += 4;

@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(256) attention_generic_kernel(AttnArgs<T> a) {
 // Timestep / class embedding path (fp32 always; rows = distinct (t, y) combinations).
 // ---------------------------------------------------------------------------------------
 // semb[row] = SiLU( W2 * SiLU(W1 * sinus(t_row) + b1) + b2 + label_emb[y_row] )
-// Kernel 1: hidden[row][j] = SiLU(W1 sinus + b1)       (one CTA per row)
+// Kernel 1: hidden[row][j] = SiLU(W1 sinus + b1)       (grid = (ceil(ted / warps), rows): one output per warp, so the
+// weight rows stream in parallel instead of as 64 dependent DRAM round trips in one CTA)
 __global__ void time_hidden_kernel(const float* __restrict__ t_rows, int mc, int ted,
                                    const float* __restrict__ w1, const float* __restrict__ b1,
                                    float* __restrict__ hidden) {
@@ -347,7 +348,7 @@ __global__ void time_hidden_kernel(const float* __restrict__ t_rows, int mc, int
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = warp; j < ted; j += nw) {
+  for (int j = blockIdx.y * nw + warp; j < ted; j += nw * gridDim.y) {
     float s = 0.f;
     for (int i = lane; i < mc; i += 32) s = fmaf(w1[(long long)j * mc + i], sin_emb[i], s);
     s = warp_sum(s);
