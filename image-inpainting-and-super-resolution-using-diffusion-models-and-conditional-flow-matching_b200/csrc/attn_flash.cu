@@ -26,7 +26,7 @@ constexpr int AF_M = 128, AF_BK = 128;
 constexpr int AF_Q_OFF = 0, AF_K_OFF = 16384, AF_V_OFF = 49152, AF_P_OFF = 81920, AF_BAR_OFF = 114688;
 constexpr int AF_SMEM = AF_BAR_OFF + 128 + 1024;
 
-struct AttnFlashParams { int T, heads, C, new_order, n_kv; float scale_log2; bf16* out; };
+struct AttnFlashParams { int T, heads, C, new_order, n_kv, pack, B; float scale_log2; bf16* out; };   // pack: samples per 128-row tile (T <= 64)
 
 __device__ __forceinline__ float af_ex2(float x) {
   float y;
@@ -35,17 +35,18 @@ __device__ __forceinline__ float af_ex2(float x) {
 }
 
 // One row's 128 scores of a key block (registers) -> running max update, p = 2^(s*scale - m), row sum, and P as bf16
-// in shared memory (K-major SWIZZLE_128B, two 64-key sub-tiles).  kMasked: keys >= n_valid do not exist (last block).
+// in shared memory (K-major SWIZZLE_128B, two 64-key sub-tiles).  kMasked: only keys in [lo, hi) belong to this row
+// (last block of a long sequence, or the row's own sample when several short sequences share a tile).
 // Four independent max / sum chains keep the dependent-issue latency of a 128-long reduction off the critical path.
 template <bool kMasked>
-__device__ __forceinline__ void af_softmax_block(const uint32_t (&sv)[4][32], int n_valid, float scale_log2, float& m_run,
+__device__ __forceinline__ void af_softmax_block(const uint32_t (&sv)[4][32], int lo, int hi, float scale_log2, float& m_run,
                                                  float& alpha, float& sum, uint8_t* prow, int r) {
   float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (!kMasked || c * 32 + i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+      if (!kMasked || (c * 32 + i >= lo && c * 32 + i < hi)) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
   const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
   const float m_new = fmaxf(m_run, mx * scale_log2);
   alpha = af_ex2(m_run - m_new);           // 0 for the first block (m_run = -inf)
@@ -65,7 +66,7 @@ __device__ __forceinline__ void af_softmax_block(const uint32_t (&sv)[4][32], in
         const int cc = c0 + i * 8 + 2 * q;
         float e0 = af_ex2(fmaf(__uint_as_float(sv[c][i * 8 + 2 * q]), scale_log2, -m_new));
         float e1 = af_ex2(fmaf(__uint_as_float(sv[c][i * 8 + 2 * q + 1]), scale_log2, -m_new));
-        if (kMasked) { if (cc >= n_valid) e0 = 0.f; if (cc + 1 >= n_valid) e1 = 0.f; }
+        if (kMasked) { if (cc < lo || cc >= hi) e0 = 0.f; if (cc + 1 < lo || cc + 1 >= hi) e1 = 0.f; }
         s4[q] += e0 + e1;
         o2[q] = __floats2bfloat162_rn(e0, e1);
       }
@@ -86,12 +87,12 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
   uint64_t* bar_o = bar_q + 6;
   uint32_t* tmem_slot = (uint32_t*)(bar_q + 7);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
+  const int mt = blockIdx.x, b = (blockIdx.y / p.heads) * p.pack, h = blockIdx.y % p.heads;   // b: first sample of the tile
   const int qcol = p.new_order ? h * D : h * 3 * D;
   const int kcol = p.new_order ? p.C + h * D : h * 3 * D + D;
   const int vcol = p.new_order ? 2 * p.C + h * D : h * 3 * D + 2 * D;
   constexpr int ROWB = D * 2;                 // bytes of one q / k / v row
-  constexpr int TILE_B = 128 * ROWB;          // one 128-row operand tile
+  const int TILE_B = (p.pack > 1 ? p.pack * p.T : 128) * ROWB;   // bytes of one operand tile (box rows x row bytes)
 
   pdl_launch_dependents();
   if (tid == 0) {
@@ -126,6 +127,13 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
     tma_load_3d(smem + AF_V_OFF + buf * 16384, &map, &bar_v[buf], vcol, j * AF_BK, b);
   };
 
+  if (p.pack > 1 && p.pack * p.T < 128) {
+    // packed tiles that do not fill 128 rows (7x7 maps: 2 x 49): the TMA box leaves V rows [pack*T, 128) untouched, and
+    // 0 (P) x stale NaN (V) would poison the PV product - clear them (visible to the MMA after fence.proxy.async below)
+    uint4* vz = (uint4*)(smem + AF_V_OFF + p.pack * p.T * ROWB);
+    const int nz = (128 - p.pack * p.T) * ROWB / 16;
+    for (int i = tid; i < nz; i += 128) vz[i] = make_uint4(0, 0, 0, 0);
+  }
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(bar_q, TILE_B);
@@ -150,7 +158,9 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
 
   for (int j = 0; j < p.n_kv; ++j) {
     const int kv0 = j * AF_BK;
-    const int n_valid = min(AF_BK, p.T - kv0);           // keys of this block that exist
+    // keys of this block that belong to this row: the existing ones, or (packed tiles) those of the row's own sample
+    int lo = 0, hi = min(AF_BK, p.T - kv0);
+    if (p.pack > 1) { const int sidx = min(r / p.T, p.pack - 1); lo = sidx * p.T; hi = lo + p.T; }
     // ---- the block's 128 scores of this row go to registers once: all four TMEM loads are issued before one wait ----
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
@@ -159,8 +169,8 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
     for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + t_row + (uint32_t)(c * 32), sv[c]);
     tmem_ld_wait();
     float alpha, sum;
-    if (n_valid == AF_BK) af_softmax_block<false>(sv, n_valid, p.scale_log2, m_run, alpha, sum, prow, r);   // no per-key masks
-    else af_softmax_block<true>(sv, n_valid, p.scale_log2, m_run, alpha, sum, prow, r);
+    if (lo == 0 && hi == AF_BK) af_softmax_block<false>(sv, lo, hi, p.scale_log2, m_run, alpha, sum, prow, r);   // no per-key masks
+    else af_softmax_block<true>(sv, lo, hi, p.scale_log2, m_run, alpha, sum, prow, r);
     l_run = l_run * alpha + sum;
     fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy
     tc_fence_before();
@@ -203,8 +213,11 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
 
   // ---- normalise, store: this thread's row, 64 B per chunk as two 256-bit stores (whole sectors) ----
   const float inv = 1.0f / l_run;
-  if (mt * AF_M + r < p.T) {
-    bf16* op = p.out + ((long long)b * p.T + mt * AF_M + r) * p.C + h * D;
+  // row -> (sample, token): one sample per tile, or p.pack short sequences back to back
+  const int s_idx = p.pack > 1 ? r / p.T : 0;
+  const int tok = p.pack > 1 ? r - s_idx * p.T : mt * AF_M + r;
+  if (tok < p.T && s_idx < p.pack && b + s_idx < p.B) {
+    bf16* op = p.out + ((long long)(b + s_idx) * p.T + tok) * p.C + h * D;
 #pragma unroll
     for (int c0 = 0; c0 < D; c0 += 32) {
       uint4 ov[4];
@@ -258,7 +271,8 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     const int C3 = 3 * op.Cin;
     cuuint64_t dims[3] = {(cuuint64_t)C3, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)C3 * 2, (cuuint64_t)T * C3 * 2};
-    cuuint32_t box[3] = {(cuuint32_t)op.ch, 128, 1};
+    const int pack = T <= 64 ? 128 / T : 1;
+    cuuint32_t box[3] = {(cuuint32_t)op.ch, (cuuint32_t)(pack > 1 ? T : 128), (cuuint32_t)pack};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_flash_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 op.ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -269,9 +283,11 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   AttnFlashParams p{};
   p.T = T; p.heads = op.heads; p.C = op.Cin; p.new_order = e.cfg.use_new_attention_order;
   p.n_kv = (T + AF_BK - 1) / AF_BK;
+  p.pack = T <= 64 ? 128 / T : 1;      // short sequences (middle blocks: 4x4, 7x7, 8x8 maps): several samples per tile
+  p.B = B;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
-  LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, B * op.heads), dim3(128), AF_SMEM, st, 1, pdl_enabled());
+  LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, ((B + p.pack - 1) / p.pack) * op.heads), dim3(128), AF_SMEM, st, 1, pdl_enabled());
   cudaError_t ce = op.ch == 64 ? cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<64>, it->second, p)
                                : cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<32>, it->second, p);
   if (ce != cudaSuccess) { e.err = std::string("attn_flash_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
