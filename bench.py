@@ -256,7 +256,7 @@ def run_engine(args):
                 traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved,
+        roofline = {"bound": "tensor", "kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv, all 64 launches of an NFE)", "achieved": achieved,
                     "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"], "traffic": traffic,
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                     "launches_per_nfe": len(tc), "flops_per_launch_avg": tc_fl / len(tc), "ms_per_launch_avg": tc_ms / len(tc),
