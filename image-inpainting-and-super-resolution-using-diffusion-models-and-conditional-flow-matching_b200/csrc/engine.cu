@@ -416,6 +416,7 @@ static int ensure_batch(Engine& e, int B) {
     tc_conv_release(e);   // tensor maps hold arena addresses
     attn_tc_release(e);
     attn_flash_release(e);
+    attn_wide_release(e);
     drop_graphs(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
     CU_CHECK(e, cudaMalloc(&e.arena, bytes));
@@ -560,6 +561,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         }
         if (attn_flash_supported(e, op)) {
           int rc = attn_flash_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
+        if (attn_wide_supported(e, op)) {
+          int rc = attn_wide_launch(e, op, B, st);
           if (rc) return rc;
           e.launches++;
           break;
@@ -738,6 +745,7 @@ void cfm_engine_destroy(cfm_engine* h) {
   tc_conv_release(e);
   attn_tc_forget(e);
   attn_flash_forget(e);
+  attn_wide_forget(e);
   drop_graphs(e);
   for (void* p : {(void*)e.x_work, (void*)e.cond_work, (void*)e.img_work, (void*)e.y_work, (void*)e.t_table, (void*)e.dt_table,
                   (void*)e.ddpm_table, (void*)e.step_counter})
@@ -804,7 +812,7 @@ int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t n
   if (kind) {
     if (op.kind == OP_CONV) *kind = op.tc ? 4 : 0;
     else if (op.kind == OP_IM2COL) *kind = 2;
-    else if (op.kind == OP_ATTN) *kind = (attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op)) ? 5 : 3;
+    else if (op.kind == OP_ATTN) *kind = (attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op) || attn_wide_supported(h->impl, op)) ? 5 : 3;
     else *kind = (int)op.kind;
   }
   if (ms) *ms = h->impl.prof_ms[i];

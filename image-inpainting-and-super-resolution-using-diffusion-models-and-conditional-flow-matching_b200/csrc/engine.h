@@ -131,6 +131,11 @@ bool attn_flash_supported(const Engine& e, const Op& op);
 int  attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 void attn_flash_release(Engine& e);
 void attn_flash_forget(Engine& e);
+// attn_wide.cu
+bool attn_wide_supported(const Engine& e, const Op& op);
+int  attn_wide_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+void attn_wide_release(Engine& e);
+void attn_wide_forget(Engine& e);
 bool gn_bf16_supported(const Engine& e, const Op& op);
 bool resample_bf16_supported(const Engine& e, const Op& op);
 int  resample_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);

@@ -213,6 +213,7 @@ static GnGeom gn_geometry(const Op& op) {
   if (bytes > 160 * 1024) return g;
   const int vpp = slab / 8;
   const int unit = 32 / gcd_i(32, vpp) * vpp;          // lcm(32, vpp): whole warps, multiple of vpp
+  if (unit > GN_MAX_THREADS) return g;                 // e.g. 18 channels per group (C = 576): 9 vectors per pixel -> generic kernel
   const int nvec = (int)(bytes / 16);
   int threads = ((nvec + 7) / 8 + unit - 1) / unit * unit;   // ~8 vectors per thread
   threads = std::min(std::max(threads, cs > 1 ? std::max(unit, (GN_MAX_SLAB + unit - 1) / unit * unit) : unit), GN_MAX_THREADS / unit * unit);

@@ -138,10 +138,12 @@ def test_bf16_runs_on_tensor_core_kernels(pkg, cuda, name):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("size,mult,heads,hc,attn", [(20, (1, 2), -1, 32, "1,2"), (12, (1, 1, 2), 2, -1, "1"), (24, (2, 1), -1, 64, "2")])
+@pytest.mark.parametrize("size,mult,heads,hc,attn", [(20, (1, 2), -1, 32, "1,2"), (12, (1, 1, 2), 2, -1, "1"), (24, (2, 1), -1, 64, "2"),
+                                                      (16, (2, 4, 6), 1, -1, "1,2"), (8, (3, 6), -1, 192, "1"), (8, (8,), 1, -1, "1")])
 def test_odd_maps_and_head_widths_match_oracle(pkg, cuda, precision, size, mult, heads, hc, attn):
     # maps that are not powers of two (20/10, 12/6/3, 24/12), sequence lengths 400/100/144, 32- and 64-wide heads,
-    # strided and folded-upsample convs on them: the flash attention and the generalised conv tiles against the oracle
+    # strided and folded-upsample convs on them: the flash attention and the generalised conv tiles against the oracle;
+    # the last two: single 128 / 256 / 384-wide heads over 256 / 64 / 16 tokens and 192 / 512-wide heads (wide-head kernel)
     kw = dict(channel_mult=list(mult), attention_resolutions=",".join(str(size // int(a)) for a in attn.split(",")))
     if hc > 0: kw.update(num_head_channels=hc)
     else: kw.update(num_heads=heads)
@@ -157,3 +159,20 @@ def test_odd_maps_and_head_widths_match_oracle(pkg, cuda, precision, size, mult,
     r = rel_l2(got, want)
     print(f"odd[{size},{mult},{precision}] rel-L2 = {r:.3e}")
     assert r < TOL[precision], r
+
+
+def test_superres_config_runs_on_tensor_core_kernels(pkg, cuda):
+    # BASELINE config 5 (4x super-resolution, 128x128, low-res image concatenated): single 384 / 512-wide heads take the
+    # wide-head attention kernel, everything else the same tcgen05 kernels; checked against the oracle at batch 1
+    cfg = O.config_from_create_model(image_size=128, in_channels=6, out_channels=3, num_channels=128, num_res_blocks=1)
+    params = O.seeded_params(cfg, 3)
+    m = build(pkg, cfg, params, "bf16", cuda)
+    x = torch.randn(1, 6, 128, 128)
+    t = torch.tensor([0.4])
+    kinds = _kinds(m, x.to(cuda), 0.4)
+    assert "conv_generic" not in kinds and "attention_generic" not in kinds, kinds
+    want = O.unet_forward(cfg, params, x, t)
+    got = m(x.to(cuda), t.to(cuda)).cpu()
+    r = rel_l2(got, want)
+    print(f"superres128[bf16] rel-L2 = {r:.3e}")
+    assert r < TOL["bf16"], r
