@@ -24,7 +24,8 @@ void* tensor_ptr(const Engine& e, int id, int B);
 
 constexpr int AF_M = 128, AF_BK = 128;
 constexpr int AF_Q_OFF = 0, AF_K_OFF = 16384, AF_V_OFF = 49152, AF_P_OFF = 81920, AF_BAR_OFF = 114688;
-constexpr int AF_SMEM = AF_BAR_OFF + 128 + 1024;
+constexpr int AF_XCH_OFF = AF_BAR_OFF + 128;
+constexpr int AF_SMEM = AF_XCH_OFF + 2 * 256 * 4 + 1024;
 
 struct AttnFlashParams { int T, heads, C, new_order, n_kv, pack, B; float scale_log2; bf16* out; };   // pack: samples per 128-row tile (T <= 64)
 
@@ -34,50 +35,52 @@ __device__ __forceinline__ float af_ex2(float x) {
   return y;
 }
 
-// One row's 128 scores of a key block (registers) -> running max update, p = 2^(s*scale - m), row sum, and P as bf16
-// in shared memory (K-major SWIZZLE_128B, two 64-key sub-tiles).  kMasked: only keys in [lo, hi) belong to this row
-// (last block of a long sequence, or the row's own sample when several short sequences share a tile).
-// Four independent max / sum chains keep the dependent-issue latency of a 128-long reduction off the critical path.
+// 64 scores of one row (this thread's half of a 128-key block, in registers) -> p = 2^(s*scale - m), partial row sum,
+// and P as bf16 in shared memory (K-major SWIZZLE_128B; a thread's 64 keys are exactly one 64-key sub-tile row).
+// kMasked: only keys in [lo, hi) belong to this row (last block of a long sequence, or the row's own sample when
+// several short sequences share a tile).  Independent sum chains keep dependent-issue latency off the critical path.
 template <bool kMasked>
-__device__ __forceinline__ void af_softmax_block(const uint32_t (&sv)[4][32], int lo, int hi, float scale_log2, float& m_run,
-                                                 float& alpha, float& sum, uint8_t* prow, int r) {
+__device__ __forceinline__ float af_local_max(const uint32_t (&sv)[2][32], int kbase, int lo, int hi) {
   float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < 2; ++c)
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (!kMasked || (c * 32 + i >= lo && c * 32 + i < hi)) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
-  const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-  const float m_new = fmaxf(m_run, mx * scale_log2);
-  alpha = af_ex2(m_run - m_new);           // 0 for the first block (m_run = -inf)
-  m_run = m_new;
+      if (!kMasked || (kbase + c * 32 + i >= lo && kbase + c * 32 + i < hi)) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+  return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+}
+template <bool kMasked>
+__device__ __forceinline__ float af_exp_block(const uint32_t (&sv)[2][32], int kbase, int lo, int hi, float scale_log2, float m_new,
+                                              uint8_t* prow64, int r) {
   float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int c0 = c * 32;
-    uint8_t* pchunk = prow + (c0 >> 6) * 16384;
-    const int c16 = (c0 & 63) >> 3;
+  for (int c = 0; c < 2; ++c) {
+    const int c16 = c * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint4 o4;
       __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int cc = c0 + i * 8 + 2 * q;
+        const int cc = kbase + c * 32 + i * 8 + 2 * q;
         float e0 = af_ex2(fmaf(__uint_as_float(sv[c][i * 8 + 2 * q]), scale_log2, -m_new));
         float e1 = af_ex2(fmaf(__uint_as_float(sv[c][i * 8 + 2 * q + 1]), scale_log2, -m_new));
         if (kMasked) { if (cc < lo || cc >= hi) e0 = 0.f; if (cc + 1 < lo || cc + 1 >= hi) e1 = 0.f; }
         s4[q] += e0 + e1;
         o2[q] = __floats2bfloat162_rn(e0, e1);
       }
-      *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+      *(uint4*)(prow64 + (((c16 + i) ^ (r & 7)) << 4)) = o4;
     }
   }
-  sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  return (s4[0] + s4[1]) + (s4[2] + s4[3]);
 }
 
+// 256 threads: thread t and t + 128 share query row (t & 127) - warps w and w + 4 may both read TMEM lanes
+// 32 (w & 3) .. +31.  Each takes 64 of a block's 128 keys (scores in registers: one TMEM pass) and D/2 of the output
+// channels; the running max is exchanged through shared memory once per block, the row sums only at the end.
+// 16 warps per SM (2 CTAs) instead of 8 hide the MUFU / TMEM latencies of this exp-bound loop.
 template <int D>
-__global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constant__ CUtensorMap map, const AttnFlashParams p) {
+__global__ void __launch_bounds__(256, 2) attn_flash_kernel(const __grid_constant__ CUtensorMap map, const AttnFlashParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bar_q = (uint64_t*)(smem + AF_BAR_OFF);
@@ -86,12 +89,14 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
   uint64_t* bar_s = bar_q + 5;
   uint64_t* bar_o = bar_q + 6;
   uint32_t* tmem_slot = (uint32_t*)(bar_q + 7);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* xch = (float*)(smem + AF_XCH_OFF);            // [2][256]: per-block max (double-buffered by block parity)
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int mt = blockIdx.x, b = (blockIdx.y / p.heads) * p.pack, h = blockIdx.y % p.heads;   // b: first sample of the tile
   const int qcol = p.new_order ? h * D : h * 3 * D;
   const int kcol = p.new_order ? p.C + h * D : h * 3 * D + D;
   const int vcol = p.new_order ? 2 * p.C + h * D : h * 3 * D + 2 * D;
   constexpr int ROWB = D * 2;                 // bytes of one q / k / v row
+  constexpr int DH = D / 2;                   // output channels per thread
   const int TILE_B = (p.pack > 1 ? p.pack * p.T : 128) * ROWB;   // bytes of one operand tile (box rows x row bytes)
 
   pdl_launch_dependents();
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
     // 0 (P) x stale NaN (V) would poison the PV product - clear them (visible to the MMA after fence.proxy.async below)
     uint4* vz = (uint4*)(smem + AF_V_OFF + p.pack * p.T * ROWB);
     const int nz = (128 - p.pack * p.T) * ROWB / 16;
-    for (int i = tid; i < nz; i += 128) vz[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < nz; i += 256) vz[i] = make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) {
     if (elect_one()) {
@@ -148,29 +153,38 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
     __syncwarp();
   }
 
-  const int r = tid;                           // query row of this thread = TMEM lane
-  const uint32_t t_row = ((uint32_t)(warp * 32) << 16);
-  float m_run = -INFINITY, l_run = 0.f;        // running max (scaled to log2 units) and sum
-  float o[D];
+  const int r = tid & 127;                     // query row of this thread = TMEM lane
+  const int half = tid >> 7;                   // keys [64 half, +64) of every block, output channels [DH half, +DH)
+  const uint32_t t_row = ((uint32_t)((warp & 3) * 32) << 16);
+  const int kbase = half * 64;
+  float m_run = -INFINITY, l_run = 0.f;        // running max (log2 units, shared by the pair) and this thread's partial sum
+  float o[DH];
 #pragma unroll
-  for (int i = 0; i < D; ++i) o[i] = 0.f;
-  uint8_t* prow = smem + AF_P_OFF + r * 128;
+  for (int i = 0; i < DH; ++i) o[i] = 0.f;
+  uint8_t* prow64 = smem + AF_P_OFF + half * 16384 + r * 128;
 
   for (int j = 0; j < p.n_kv; ++j) {
     const int kv0 = j * AF_BK;
     // keys of this block that belong to this row: the existing ones, or (packed tiles) those of the row's own sample
     int lo = 0, hi = min(AF_BK, p.T - kv0);
     if (p.pack > 1) { const int sidx = min(r / p.T, p.pack - 1); lo = sidx * p.T; hi = lo + p.T; }
-    // ---- the block's 128 scores of this row go to registers once: all four TMEM loads are issued before one wait ----
+    const bool masked = !(lo == 0 && hi == AF_BK);
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
-    uint32_t sv[4][32];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + t_row + (uint32_t)(c * 32), sv[c]);
+    uint32_t sv[2][32];
+    tmem_ld32(tmem_s + t_row + (uint32_t)kbase, sv[0]);
+    tmem_ld32(tmem_s + t_row + (uint32_t)(kbase + 32), sv[1]);
     tmem_ld_wait();
-    float alpha, sum;
-    if (lo == 0 && hi == AF_BK) af_softmax_block<false>(sv, lo, hi, p.scale_log2, m_run, alpha, sum, prow, r);   // no per-key masks
-    else af_softmax_block<true>(sv, lo, hi, p.scale_log2, m_run, alpha, sum, prow, r);
+    const float lmx = masked ? af_local_max<true>(sv, kbase, lo, hi) : af_local_max<false>(sv, kbase, lo, hi);
+    float* xb = xch + (j & 1) * 256;
+    xb[tid] = lmx;
+    __syncthreads();
+    const float mx = fmaxf(lmx, xb[tid ^ 128]);
+    const float m_new = fmaxf(m_run, mx * p.scale_log2);
+    const float alpha = af_ex2(m_run - m_new);           // 0 for the first block (m_run = -inf)
+    m_run = m_new;
+    const float sum = masked ? af_exp_block<true>(sv, kbase, lo, hi, p.scale_log2, m_new, prow64, r)
+                             : af_exp_block<false>(sv, kbase, lo, hi, p.scale_log2, m_new, prow64, r);
     l_run = l_run * alpha + sum;
     fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy
     tc_fence_before();
@@ -192,16 +206,16 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
       }
       __syncwarp();
     }
-    // ---- o = o * alpha + O_j ----
+    // ---- o = o * alpha + O_j (this thread's DH channels) ----
     mbar_wait(bar_o, j & 1);
     tc_fence_after();
-#pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_o + t_row + (uint32_t)c0, v);
+    {
+      uint32_t v[DH];
+      if (DH == 32) tmem_ld32(tmem_o + t_row + (uint32_t)(half * DH), (uint32_t*)v);
+      else tmem_ld16(tmem_o + t_row + (uint32_t)(half * DH), (uint32_t*)v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, __uint_as_float(v[i]));
+      for (int i = 0; i < DH; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
     }
     // K_j / V_j buffers are free (S_j and O_j have completed): fetch block j + 2 into them
     if (warp == 0 && j + 2 < p.n_kv) {
@@ -211,24 +225,26 @@ __global__ void __launch_bounds__(128, 2) attn_flash_kernel(const __grid_constan
     tc_fence_before();            // order this thread's TMEM reads before the next block's MMAs (issued after the next sync)
   }
 
-  // ---- normalise, store: this thread's row, 64 B per chunk as two 256-bit stores (whole sectors) ----
-  const float inv = 1.0f / l_run;
+  // ---- combine the pair's partial row sums, normalise, store this thread's DH channels with 256-bit stores ----
+  __syncthreads();
+  xch[tid] = l_run;
+  __syncthreads();
+  const float inv = 1.0f / (l_run + xch[tid ^ 128]);
   // row -> (sample, token): one sample per tile, or p.pack short sequences back to back
   const int s_idx = p.pack > 1 ? r / p.T : 0;
   const int tok = p.pack > 1 ? r - s_idx * p.T : mt * AF_M + r;
   if (tok < p.T && s_idx < p.pack && b + s_idx < p.B) {
-    bf16* op = p.out + ((long long)(b + s_idx) * p.T + tok) * p.C + h * D;
+    bf16* op = p.out + ((long long)(b + s_idx) * p.T + tok) * p.C + h * D + half * DH;
 #pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      uint4 ov[4];
+    for (int c0 = 0; c0 < DH; c0 += 16) {
+      uint4 ov[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         __nv_bfloat162* o2 = (__nv_bfloat162*)&ov[i];
 #pragma unroll
         for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(o[c0 + i * 8 + 2 * q] * inv, o[c0 + i * 8 + 2 * q + 1] * inv);
       }
       stg256(op + c0, ov[0], ov[1]);
-      stg256(op + c0 + 16, ov[2], ov[3]);
     }
   }
   tc_fence_before();
@@ -287,7 +303,7 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.B = B;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
-  LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, ((B + p.pack - 1) / p.pack) * op.heads), dim3(128), AF_SMEM, st, 1, pdl_enabled());
+  LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, ((B + p.pack - 1) / p.pack) * op.heads), dim3(256), AF_SMEM, st, 1, pdl_enabled());
   cudaError_t ce = op.ch == 64 ? cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<64>, it->second, p)
                                : cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<32>, it->second, p);
   if (ce != cudaSuccess) { e.err = std::string("attn_flash_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
