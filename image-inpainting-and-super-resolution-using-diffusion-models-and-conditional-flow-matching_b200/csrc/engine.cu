@@ -193,12 +193,23 @@ static int add_attention(Engine& e, const std::string& p, Cur x, int heads, Cur*
   if (heads <= 0 || C % heads) return fail(e, CFM_ERR_INVALID, "bad head count at " + p);
   const int a = new_tensor(e, C, x.H, x.W);
   if ((rc = add_gn(e, p + ".norm", p + ".norm", x.id, -1, C, 0, false, -1, a))) return rc;
-  const int qkv = new_tensor(e, 3 * C, x.H, x.W);
-  if ((rc = add_conv(e, p + ".qkv", p + ".qkv", 1, 1, 0, a, -1, false, C, x.H, x.W, 3 * C, "", -1, -1, 0, -1, -1, -1, qkv, false))) return rc;
   const int att = new_tensor(e, C, x.H, x.W);
-  Op op; op.kind = OP_ATTN; op.name = p + ".attention"; op.src0 = qkv; op.out = att;
+  Op op; op.kind = OP_ATTN; op.name = p + ".attention"; op.out = att;
   op.heads = heads; op.ch = C / heads; op.Cin = C; op.Hin = x.H; op.Win = x.W;
   op.flops = 2.0 * 2.0 * (double)(x.H * x.W) * (x.H * x.W) * C;
+  if (attn_qkv_shape_ok(e, C, heads, x.H * x.W)) {
+    // q, k, v are projected inside the attention kernel: no qkv conv, no [B, T, 3C] tensor
+    const float *w = nullptr, *b = nullptr;
+    if ((rc = fetch(e, p + ".qkv.weight", (int64_t)3 * C * C, &w))) return rc;
+    if ((rc = fetch(e, p + ".qkv.bias", 3 * C, &b))) return rc;
+    op.name = p + ".qkv+attention"; op.src0 = a;
+    op.flops += 2.0 * (double)(x.H * x.W) * C * 3 * C;
+    if ((rc = attn_qkv_prepare(e, op, w, b))) return rc;
+  } else {
+    const int qkv = new_tensor(e, 3 * C, x.H, x.W);
+    if ((rc = add_conv(e, p + ".qkv", p + ".qkv", 1, 1, 0, a, -1, false, C, x.H, x.W, 3 * C, "", -1, -1, 0, -1, -1, -1, qkv, false))) return rc;
+    op.src0 = qkv;
+  }
   e.ops.push_back(op);
   const int o = new_tensor(e, C, x.H, x.W);
   if ((rc = add_conv(e, p + ".proj_out", p + ".proj_out", 1, 1, 0, att, -1, false, C, x.H, x.W, C, "", -1, -1, 0, x.id, -1, -1, o, false))) return rc;
@@ -416,6 +427,7 @@ static int ensure_batch(Engine& e, int B) {
     tc_conv_release(e);   // tensor maps hold arena addresses
     attn_tc_release(e);
     attn_flash_release(e);
+    attn_qkv_release(e);
     attn_wide_release(e);
     drop_graphs(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
@@ -553,6 +565,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_ATTN: {
+        if (op.fq) {
+          int rc = attn_qkv_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
         if (attn_tc_supported(e, op)) {
           int rc = attn_tc_launch(e, op, B, st);
           if (rc) return rc;
@@ -812,7 +830,7 @@ int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t n
   if (kind) {
     if (op.kind == OP_CONV) *kind = op.tc ? 4 : 0;
     else if (op.kind == OP_IM2COL) *kind = 2;
-    else if (op.kind == OP_ATTN) *kind = (attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op) || attn_wide_supported(h->impl, op)) ? 5 : 3;
+    else if (op.kind == OP_ATTN) *kind = (op.fq || attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op) || attn_wide_supported(h->impl, op)) ? 5 : 3;
     else *kind = (int)op.kind;
   }
   if (ms) *ms = h->impl.prof_ms[i];

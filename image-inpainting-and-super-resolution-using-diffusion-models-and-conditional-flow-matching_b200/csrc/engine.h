@@ -24,6 +24,7 @@ struct TensorDesc {
 enum OpKind { OP_CONV = 0, OP_GN = 1, OP_RESAMPLE = 2, OP_ATTN = 3, OP_IM2COL = 4 };
 
 struct TcConvPlan;   // tcgen05 implicit-GEMM lowering of a conv op (conv_tc.cu)
+struct AttnQkvPlan;  // attention with the qkv projection fused in (attn_qkv.cu)
 
 struct Op {
   OpKind kind;
@@ -43,6 +44,7 @@ struct Op {
   int heads = 0, ch = 0;
   // tensor-core lowering (bf16 mode), null when the generic kernel runs this op
   TcConvPlan* tc = nullptr;
+  AttnQkvPlan* fq = nullptr;   // attention op that takes the GroupNorm output and projects q, k, v itself
   double flops = 0;        // 2*MAC per sample
 };
 
@@ -126,6 +128,11 @@ bool attn_tc_supported(const Engine& e, const Op& op);
 int  attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 void attn_tc_release(Engine& e);
 void attn_tc_forget(Engine& e);
+// attn_qkv.cu
+bool attn_qkv_shape_ok(const Engine& e, int C, int heads, int T);
+int  attn_qkv_prepare(Engine& e, Op& op, const float* w_oi, const float* bias);
+int  attn_qkv_launch(Engine& e, const Op& op, int B, cudaStream_t st);
+void attn_qkv_release(Engine& e);
 // attn_flash.cu
 bool attn_flash_supported(const Engine& e, const Op& op);
 int  attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st);

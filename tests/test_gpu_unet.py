@@ -176,3 +176,17 @@ def test_superres_config_runs_on_tensor_core_kernels(pkg, cuda):
     r = rel_l2(got, want)
     print(f"superres128[bf16] rel-L2 = {r:.3e}")
     assert r < TOL["bf16"], r
+
+
+def test_fused_qkv_attention_opt_in(pkg, cuda, monkeypatch):
+    # experimental kernel that projects q, k, v inside the attention kernel (CFM_ENABLE_FUSED_QKV=1): kept parity-green
+    monkeypatch.setenv("CFM_ENABLE_FUSED_QKV", "1")
+    cfg, _, _ = GOLDEN_CONFIGS["cifar"]
+    g = np.load(os.path.join(GOLD, "unet_cifar.npz"))
+    params = O.seeded_params(cfg, int(g["seed"]))
+    m = build(pkg, cfg, params, "bf16", cuda)
+    x = torch.from_numpy(g["x"]).to(cuda)
+    names = [r["name"] for r in m.engine().profile_forward(x, 0.5, repeats=1)]
+    assert any(n.endswith("qkv+attention") for n in names)
+    out = m(x, torch.from_numpy(g["t"]).to(cuda)).cpu()
+    assert rel_l2(out, torch.from_numpy(g["out"])) < TOL["bf16"]
