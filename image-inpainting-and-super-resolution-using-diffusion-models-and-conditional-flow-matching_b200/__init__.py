@@ -13,6 +13,6 @@ from .integrators import NeuralODE, odeint, sample_euler, euler_time_grid, rk_co
 from .diffusion import (DDPM, EpsModel, Amortized, Replacement, ReconstructionGuidance, InPainting, OutPainting,
                         HyperResolution, get_conditioning, get_likelihood, get_prior_sample_fn,
                         get_conditional_sample_fn, downsample_images, extract)
-from .distributed import shard_range, sample_euler_sharded, gather_uint8
+from .distributed import shard_range, sample_euler_sharded, gather_uint8, odeint_sharded
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -49,3 +49,17 @@ def sample_euler_sharded(model, x0_global: torch.Tensor, t_span: torch.Tensor, y
     cond = None if cond_global is None else cond_global[lo:hi].to(dev)
     x, img = sample_euler(model, x0, t_span, y=y, cond=cond, return_uint8=True, use_graph=use_graph)
     return x, gather_uint8(img, x0_global.shape[0], group)
+
+
+def odeint_sharded(func, y0_global: torch.Tensor, t: torch.Tensor, rtol: float = 1e-5, atol: float = 1e-5, group=None,
+                   stats: Optional[dict] = None):
+    """dopri5 over a batch-sharded state with ONE step controller: every rank integrates its slice of `y0_global`
+    and the error norms are all-reduced (a few doubles per attempted step), so all ranks accept / reject the same
+    steps a single process would on the whole batch (torchdiffeq's norm is global over the state).
+    Returns the local trajectory [len(t), n_local, ...]."""
+    from .integrators import odeint
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_range(y0_global.shape[0], rank, world)
+    g = (group if group is not None else dist.group.WORLD) if dist.is_initialized() else None
+    return odeint(func, y0_global[lo:hi].cuda(), t, rtol=rtol, atol=atol, method="dopri5", stats=stats, norm_group=g)

@@ -140,10 +140,24 @@ def sample_euler(model: UNetModel, x0: torch.Tensor, t_span: torch.Tensor, y=Non
 State = Union[torch.Tensor, Tuple[torch.Tensor, ...]]
 
 
+def _allreduce_sum(values: Sequence[float], group) -> List[float]:
+    """Sum a few host scalars over the ranks of ``group`` (NCCL: on the device; gloo: on the host)."""
+    import torch.distributed as dist
+    buf = torch.tensor(list(values), dtype=torch.float64)
+    if dist.get_backend(group) == "nccl":
+        buf = buf.cuda()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return [float(v) for v in buf.cpu()]
+
+
 @torch.no_grad()
 def odeint(func: Callable, y0: State, t: torch.Tensor, rtol: float = 1e-7, atol: float = 1e-9,
-           method: str = "dopri5", options=None, stats: Optional[dict] = None) -> State:
-    """``torchdiffeq.odeint`` for method in {"dopri5", "euler"}; tuple state in -> tuple out."""
+           method: str = "dopri5", options=None, stats: Optional[dict] = None, norm_group=None) -> State:
+    """``torchdiffeq.odeint`` for method in {"dopri5", "euler"}; tuple state in -> tuple out.
+
+    ``norm_group`` (extension for batch-sharded sampling): a ``torch.distributed`` process group over which the
+    error / initial-step norms are summed, so every rank takes the step sequence a single process would take on the
+    whole batch (one small all-reduce per attempted step)."""
     if method == "euler":
         assert torch.is_tensor(y0)
         return NeuralODE(func, "euler").trajectory(y0, t)
@@ -176,17 +190,27 @@ def odeint(func: Callable, y0: State, t: torch.Tensor, rtol: float = 1e-7, atol:
 
     scratch = torch.zeros(1, dtype=torch.float64, device=dev)
 
+    # element counts of each state component over all ranks that share the step controller
+    gsizes = [float(n) for n in sizes]
+    if norm_group is not None:
+        gsizes = _allreduce_sum(gsizes, norm_group)
+
     def mixed_norm_of_ratio(y_a, y_b, ks, coefs, dt) -> float:
         """max over components of RMS(err/tol) - one fused kernel + one host read per component."""
-        out = 0.0
+        sums = []
         for i in range(len(sizes)):
             sl = slice(offs[i], offs[i + 1])
             s = rk_error_sumsq(y_a[sl], y_b[sl], [k[sl] for k in ks], coefs, dt, rtol, atol, scratch)
-            out = max(out, (float(s.item()) / sizes[i]) ** 0.5)
-        return out
+            sums.append(float(s.item()))
+        if norm_group is not None:
+            sums = _allreduce_sum(sums, norm_group)
+        return max((s / n) ** 0.5 for s, n in zip(sums, gsizes))
 
     def norm(v: torch.Tensor) -> float:
-        return max(float(v[offs[i]:offs[i + 1]].abs().pow(2).mean().sqrt()) for i in range(len(sizes)))
+        if norm_group is None:
+            return max(float(v[offs[i]:offs[i + 1]].abs().pow(2).mean().sqrt()) for i in range(len(sizes)))
+        sums = _allreduce_sum([float(v[offs[i]:offs[i + 1]].double().pow(2).sum()) for i in range(len(sizes))], norm_group)
+        return max((s / n) ** 0.5 for s, n in zip(sums, gsizes))
 
     y = torch.cat([c.reshape(-1) for c in comps])
     t_list = [float(v) for v in t]

@@ -279,3 +279,53 @@ def test_ddpm_replacement_with_langevin_corrector(pkg, cuda, precision, tol):
         assert d < tol
     with pytest.raises(NotImplementedError):
         pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(0.9, 1, 0.1), pkg.InPainting(6, -2.0))
+
+
+def _dopri5_shard_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    from oracle import unet as O2
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # both ranks share cuda:0; scalars travel over gloo
+    cfg = O2.config_from_wrapper((3, 16, 16), 32, 1, channel_mult=(1, 2), attention_resolutions="8", num_heads=2)
+    m = pkg.UNetModelWrapper(dim=(3, 16, 16), num_channels=32, num_res_blocks=1, channel_mult=(1, 2),
+                             attention_resolutions="8", num_heads=2, precision="fp32")
+    m.load_state_dict(O2.seeded_params(cfg, 31))
+    m = m.to("cuda:0").eval()
+    torch.manual_seed(11)
+    x0 = torch.randn(6, 3, 16, 16)
+    t = torch.linspace(0, 1, 2)
+    stats = {}
+    traj = pkg.odeint_sharded(m, x0, t, rtol=1e-4, atol=1e-4, stats=stats)
+    lo, hi = pkg.shard_range(6, rank, world)
+    q.put((rank, lo, hi, traj[-1].cpu(), stats))
+    dist.destroy_process_group()
+
+
+def test_dopri5_sharded_shares_one_step_controller(pkg, cuda):
+    """Two ranks, each with half of the batch, all-reduce the error norms: both take exactly the accepted / rejected
+    step sequence of a single process integrating the whole batch, and the final states agree with it."""
+    import os
+    import torch.multiprocessing as mp
+    cfg, params, m = small_cfm(pkg, cuda, "fp32")
+    torch.manual_seed(11)
+    x0 = torch.randn(6, 3, 16, 16)
+    t = torch.linspace(0, 1, 2)
+    ref_stats = {}
+    ref = pkg.odeint(m, x0.to(cuda), t.to(cuda), rtol=1e-4, atol=1e-4, method="dopri5", stats=ref_stats)[-1].cpu()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dopri5_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+    for rank, lo, hi, xf, stats in res:
+        assert stats["steps"] == ref_stats["steps"] and stats["accepted"] == ref_stats["accepted"], (stats, ref_stats)
+        assert rel_l2(xf, ref[lo:hi]) < 1e-5

@@ -126,6 +126,9 @@ def _gloo_worker(rank, world, port, total, q):
     s = feats.sum(0)
     dist.all_reduce(s)
     ok = ok and torch.allclose(s, full.double().reshape(total, -1).sum(0))
+    # the scalar all-reduce behind the shared dopri5 step controller (integrators._allreduce_sum)
+    tot = pkg.integrators._allreduce_sum([float(rank + 1), 0.5], dist.group.WORLD)
+    ok = ok and tot == [float(sum(range(1, world + 1))), 0.5 * world]
     q.put((rank, ok))
     dist.destroy_process_group()
 
