@@ -231,13 +231,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   pdl_launch_dependents();      // the next kernel's CTAs may take over SMs as ours retire and run their prologue
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
-    if (p.n_seg > 1) prefetch_tmap(&mapA1);
-    if (p.n_seg > 2) prefetch_tmap(&mapA2);
-    for (int s = 0; s < TC_MAX_A; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < TC_MAX_B; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], TC_EPI_WARPS); }
+  if (warp == 0) {
+    // the 52 barriers are initialised by the 32 lanes in parallel (one thread doing all of them costs ~1 us per launch)
+    if (lane == 0) {
+      prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+      if (p.n_seg > 1) prefetch_tmap(&mapA1);
+      if (p.n_seg > 2) prefetch_tmap(&mapA2);
+    }
+    if (lane < TC_MAX_A) { mbar_init(&fullA[lane], 1); mbar_init(&emptyA[lane], 1); }
+    if (lane < TC_MAX_B) { mbar_init(&fullB[lane], 1); mbar_init(&emptyB[lane], 1); }
+    if (lane < 2) { mbar_init(&tfull_bar[lane], 1); mbar_init(&tempty_bar[lane], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -431,13 +434,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const int pair_tiles = ((tiles128 + 1) >> 1) * p.tiles_n * p.n_phase;
 
   pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
-    if (p.n_seg > 1) prefetch_tmap(&mapA1);
-    if (p.n_seg > 2) prefetch_tmap(&mapA2);
-    for (int s = 0; s < TC_MAX_A; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < TC_MAX_B; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * TC_EPI_WARPS); }
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+      if (p.n_seg > 1) prefetch_tmap(&mapA1);
+      if (p.n_seg > 2) prefetch_tmap(&mapA2);
+    }
+    if (lane < TC_MAX_A) { mbar_init(&fullA[lane], 1); mbar_init(&emptyA[lane], 1); }
+    if (lane < TC_MAX_B) { mbar_init(&fullB[lane], 1); mbar_init(&emptyB[lane], 1); }
+    if (lane < 2) { mbar_init(&tfull_bar[lane], 1); mbar_init(&tempty_bar[lane], 2 * TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
