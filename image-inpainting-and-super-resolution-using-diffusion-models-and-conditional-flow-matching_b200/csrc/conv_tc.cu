@@ -82,6 +82,7 @@ struct TcParams {
   const bf16* res0; const bf16* res1; int R0, R1;
   bf16* out;
   float* out_nchw; int cout_real;   // network head: fp32 NCHW output of the first cout_real channels
+  float* out_f32;                   // fp32 NHWC output (head taps: 32 partial products per pixel)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -182,6 +183,14 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
     return;
   }
   if (!r.valid) return;
+  if (p.out_f32) {                  // 32 fp32 = 128 B of this row: four 256-bit stores
+    float* op = p.out_f32 + r.pix * p.Cout + cg;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8)
+      stg256(op + j, make_uint4(__float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]), __float_as_uint(f[j + 3])),
+             make_uint4(__float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]), __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7])));
+    return;
+  }
   if (p.res0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -854,6 +863,7 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.res0 = (const bf16*)tensor_ptr(e, op.res0, B); p.R0 = op.res0 >= 0 ? e.tensors[op.res0].C : 0;
   p.res1 = (const bf16*)tensor_ptr(e, op.res1, B); p.R1 = op.res1 >= 0 ? e.tensors[op.res1].C : 0;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
+  if (op.out_f32) p.out_f32 = (float*)tensor_ptr(e, op.out, B);
   if (op.out_is_output) { p.out_nchw = out_nchw; p.cout_real = op.Cout; }
   if (pl->pair) {
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;

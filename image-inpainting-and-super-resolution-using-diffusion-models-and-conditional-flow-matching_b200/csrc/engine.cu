@@ -253,6 +253,40 @@ static int add_stem_tc(Engine& e, int Cin, int S, int Cout, int out, bool* done)
   return 0;
 }
 
+// Tensor-core head: the 3x3 conv to <= 3 channels as (1) a 1x1 GEMM to the 9 x Cout per-tap partial products
+// (fp32, 32 per pixel) and (2) a gather that sums each pixel's 3x3 neighbourhood of them.  *done stays false (and
+// nothing is added) when the shapes do not fit.
+static int add_head_tc(Engine& e, int a, Cur h, int Cout, bool* done) {
+  const char* off = getenv("CFM_DISABLE_TC_HEAD_TAPS");
+  // 2 or 3 output channels fill the 32-wide row of partial products (18 / 27 of 32); with one channel (MNIST) the fp32
+  // row is mostly padding and the direct 3x3 conv measured the same
+  if ((off && off[0] == '1') || 9 * Cout > 32 || 9 * Cout <= 16) return 0;
+  Op op; op.kind = OP_CONV; op.name = "out.2";
+  op.ks = 1; op.stride = 1; op.ups = 0; op.src0 = a; op.Cin = h.C; op.Hin = op.Hout = h.H; op.Win = op.Wout = h.W; op.Cout = 32;
+  op.out_f32 = true;
+  if (!tc_conv_supported(e, op)) return 0;
+  const float *w = nullptr, *b = nullptr; int rc;
+  if ((rc = fetch(e, "out.2.weight", (int64_t)Cout * h.C * 9, &w))) return rc;
+  if ((rc = fetch(e, "out.2.bias", Cout, &b))) return rc;
+  std::vector<float> w_eff((size_t)32 * h.C, 0.f);      // [32][Cin]: row tap * Cout + o
+  for (int tap = 0; tap < 9; ++tap)
+    for (int o = 0; o < Cout; ++o)
+      for (int c = 0; c < h.C; ++c) w_eff[(size_t)(tap * Cout + o) * h.C + c] = w[((size_t)o * h.C + c) * 9 + tap];
+  std::vector<float> wkn = to_kn(w_eff.data(), 32, h.C, 1), zeros(32, 0.f);
+  if ((rc = upload(e, wkn.data(), wkn.size(), &op.w_main))) return rc;
+  if ((rc = upload(e, zeros.data(), 32, &op.bias))) return rc;
+  op.out = new_tensor(e, 64, h.H, h.W);                  // 32 fp32 per pixel = 64 bf16-sized elements
+  op.flops = 2.0 * h.H * h.W * Cout * 9.0 * h.C;
+  if ((rc = tc_conv_prepare(e, op, w_eff, {}))) return rc;
+  e.n_tc_convs++;
+  e.ops.push_back(op);
+  Op g; g.kind = OP_HEAD_GATHER; g.name = "out.2.gather"; g.src0 = op.out; g.Cout = Cout; g.Hin = h.H; g.Win = h.W; g.out_is_output = true;
+  if ((rc = upload(e, b, Cout, &g.bias))) return rc;
+  e.ops.push_back(g);
+  *done = true;
+  return 0;
+}
+
 static int build_plan(Engine& e) {
   const cfm_unet_config& c = e.cfg;
   const int mc = c.model_channels;
@@ -344,7 +378,9 @@ static int build_plan(Engine& e) {
   {
     const int a = new_tensor(e, h.C, h.H, h.W);
     if ((rc = add_gn(e, "out.0", "out.0", h.id, -1, h.C, 1, false, -1, a))) return rc;
-    if ((rc = add_conv(e, "out.2", "out.2", 3, 1, 0, a, -1, false, h.C, h.H, h.W, c.out_channels, "", -1, -1, 0, -1, -1, -1, -1, true))) return rc;
+    bool head_done = false;
+    if (e.bf16 && (rc = add_head_tc(e, a, h, c.out_channels, &head_done))) return rc;
+    if (!head_done && (rc = add_conv(e, "out.2", "out.2", 3, 1, 0, a, -1, false, h.C, h.H, h.W, c.out_channels, "", -1, -1, 0, -1, -1, -1, -1, true))) return rc;
   }
 
   // ---- embedding path weights ----
@@ -542,6 +578,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         const int cap = kGnSmemBytes / 4;
         a.smem_elems = n <= cap ? n : 0;
         groupnorm_kernel<T><<<B * 32, 256, (size_t)a.smem_elems * 4, st>>>(a);
+        e.launches++;
+        break;
+      }
+      case OP_HEAD_GATHER: {
+        int rc = head_gather_launch(e, op, B, out, st);
+        if (rc) return rc;
         e.launches++;
         break;
       }
@@ -829,7 +871,7 @@ int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t n
   if (name && name_cap > 0) { std::strncpy(name, op.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
   if (kind) {
     if (op.kind == OP_CONV) *kind = op.tc ? 4 : 0;
-    else if (op.kind == OP_IM2COL) *kind = 2;
+    else if (op.kind == OP_IM2COL || op.kind == OP_HEAD_GATHER) *kind = 2;
     else if (op.kind == OP_ATTN) *kind = (op.fq || attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op) || attn_wide_supported(h->impl, op)) ? 5 : 3;
     else *kind = (int)op.kind;
   }

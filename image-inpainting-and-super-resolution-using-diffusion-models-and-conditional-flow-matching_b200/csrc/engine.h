@@ -21,7 +21,7 @@ struct TensorDesc {
   long long elems() const { return (long long)C * H * W; }
 };
 
-enum OpKind { OP_CONV = 0, OP_GN = 1, OP_RESAMPLE = 2, OP_ATTN = 3, OP_IM2COL = 4 };
+enum OpKind { OP_CONV = 0, OP_GN = 1, OP_RESAMPLE = 2, OP_ATTN = 3, OP_IM2COL = 4, OP_HEAD_GATHER = 5 };
 
 struct TcConvPlan;   // tcgen05 implicit-GEMM lowering of a conv op (conv_tc.cu)
 struct AttnQkvPlan;  // attention with the qkv projection fused in (attn_qkv.cu)
@@ -32,6 +32,7 @@ struct Op {
   // tensor ids (-1 = none). For convs: src = main operand, skip = 1x1 operand, res = identity residual.
   int src0 = -1, src1 = -1, skip0 = -1, skip1 = -1, res0 = -1, res1 = -1, out = -1;
   bool src_is_input = false, out_is_output = false;
+  bool out_f32 = false;    // tcgen05 conv writing fp32 NHWC rows (the head's per-tap partial products)
   // conv
   int ks = 3, stride = 1, ups = 0, Cin = 0, Cskip = 0, Cout = 0, Hin = 0, Win = 0, Hout = 0, Wout = 0;
   float* w_main = nullptr; float* w_skip = nullptr; float* bias = nullptr;   // fp32 device
@@ -151,5 +152,6 @@ int  head_conv_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t s
 bool stem_conv_supported(const Engine& e, const Op& op);
 int  stem_conv_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st);
 int  stem_im2col_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st);
+int  head_gather_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t st);
 
 }  // namespace cfm

@@ -510,4 +510,61 @@ int stem_im2col_launch(Engine& e, const Op& op, int B, const float* x, const flo
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Network head, second half.  The 3x3 head conv (C -> <= 3 channels) runs as a 1x1 tensor-core GEMM that produces, per
+// pixel, the 9 x Cout per-tap partial products Y[p][tap * Cout + o] = sum_c a[p][c] w[o][c][tap] (fp32, 32 values per
+// pixel); this kernel adds the bias and sums the 9 taps of the 3x3 neighbourhood (zero outside the image) into the
+// fp32 NCHW network output.  The activation tensor is read once instead of nine times.
+// ------------------------------------------------------------------------------------------------
+// One CTA per strip of image rows (<= 256 pixels): the strip's partial products plus one halo row above and below
+// are staged in shared memory with coalesced 16-byte loads (28 of the 32 floats of a pixel; row stride 29 floats keeps
+// the per-pixel reads of a warp on distinct banks), then each thread sums its pixel's 9 taps.
+constexpr int HG_STRIDE = 29;
+
+__global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int B, int H, int W, int Cout, int R) {
+  extern __shared__ float hg_smem[];       // [(R + 2) * W][HG_STRIDE]
+  const int strips = (H + R - 1) / R;
+  const int b = blockIdx.x / strips, y0 = (blockIdx.x % strips) * R;
+  const int rows = min(R, H - y0);
+  const int npix = (rows + 2) * W;          // halo rows y0 - 1 .. y0 + rows
+  const int n4 = (9 * Cout + 3) >> 2;       // 16-byte vectors of a pixel that carry partial products (7 for 3 channels)
+  for (int i = threadIdx.x; i < npix * n4; i += blockDim.x) {
+    const int px = i / n4, k4 = i - px * n4;
+    const int iy = y0 - 1 + px / W, ix = px % W;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H) v = __ldg((const float4*)(Y + ((((long long)b * H + iy) * W + ix) << 5)) + k4);
+    float* sp = hg_smem + px * HG_STRIDE + 4 * k4;
+    sp[0] = v.x; sp[1] = v.y; sp[2] = v.z; sp[3] = v.w;
+  }
+  __syncthreads();
+  const long long hw = (long long)H * W;
+  for (int m = threadIdx.x; m < rows * W; m += blockDim.x) {
+    const int ry = m / W, x = m - ry * W;
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ix = x + tap % 3 - 1;
+      if (ix < 0 || ix >= W) continue;                       // rows outside the image were staged as zeros
+      const float* sp = hg_smem + ((ry + tap / 3) * W + ix) * HG_STRIDE + tap * Cout;
+      for (int o = 0; o < Cout; ++o) acc[o] += sp[o];
+    }
+    for (int o = 0; o < Cout; ++o) out[((long long)b * Cout + o) * hw + (long long)(y0 + ry) * W + x] = acc[o] + bias[o];
+  }
+}
+
+int head_gather_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t st) {
+  const int R = std::max(1, std::min(op.Hin, 256 / op.Win));
+  const int strips = (op.Hin + R - 1) / R;
+  const size_t smem = sizeof(float) * (size_t)(R + 2) * op.Win * HG_STRIDE;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(head_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) { e.err = "cudaFuncSetAttribute(head_gather_kernel) failed"; return CFM_ERR_CUDA; }
+    attr = true;
+  }
+  if (smem > 96 * 1024) { e.err = "head gather strip does not fit shared memory"; return CFM_ERR_INVALID; }
+  head_gather_kernel<<<B * strips, 256, smem, st>>>((const float*)tensor_ptr(e, op.src0, B), op.bias, out, B, op.Hin, op.Win, op.Cout, R);
+  return 0;
+}
+
 }  // namespace cfm
