@@ -253,7 +253,160 @@ __global__ void __launch_bounds__(256, 2) attn_flash_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-struct AttnFlashPlan { std::map<int, CUtensorMap> maps; };
+// Long sequences (T > 128: the 28x28 MNIST maps): the same online-softmax loop with 64-key blocks and one thread per
+// query row.  A CTA then needs 128 TMEM columns (S 64 + O <= 64) and 42 / 66 KB of shared memory, so 4 (D = 32) or
+// 3 (D = 64) CTAs share an SM instead of 2: the loop is a chain of short dependent phases (MMA round trip, TMEM load,
+// exp, shared-memory store, barrier) and only more independent CTAs keep the MUFU / ALU pipes busy.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128, D == 32 ? 4 : 3)
+attn_flash64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV, const AttnFlashParams p) {
+  constexpr int BK = 64;
+  constexpr int ROWB = D * 2, QB = 128 * ROWB, KB = BK * ROWB;
+  constexpr int K_OFF = QB, V_OFF = QB + 2 * KB, P_OFF = QB + 4 * KB, BAR_OFF = P_OFF + 16384;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar_q = (uint64_t*)(smem + BAR_OFF);
+  uint64_t* bar_k = bar_q + 1;      // [2]
+  uint64_t* bar_v = bar_q + 3;      // [2]
+  uint64_t* bar_s = bar_q + 5;
+  uint64_t* bar_o = bar_q + 6;
+  uint32_t* tmem_slot = (uint32_t*)(bar_q + 7);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
+  const int qcol = p.new_order ? h * D : h * 3 * D;
+  const int kcol = p.new_order ? p.C + h * D : h * 3 * D + D;
+  const int vcol = p.new_order ? 2 * p.C + h * D : h * 3 * D + 2 * D;
+  const int n_kv = (p.T + BK - 1) / BK;
+
+  pdl_launch_dependents();
+  if (tid == 0) {
+    prefetch_tmap(&mapQ); prefetch_tmap(&mapKV);
+    for (int i = 0; i < 7; ++i) mbar_init(bar_q + i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + 64;
+  const uint32_t idesc_s = make_idesc(128, BK);
+  const uint32_t idesc_o = make_idesc_major(128, D, 0, 1);
+  const uint32_t q_addr = smem_u32(smem), p_addr = smem_u32(smem + P_OFF);
+
+  auto issue_s = [&](int j) {
+    const uint64_t ad = make_desc_k(q_addr, D), bd = make_desc_k(smem_u32(smem + K_OFF + (j & 1) * KB), D);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k) umma_bf16(tmem_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_s, k > 0);
+    umma_commit(bar_s);
+  };
+  auto load_kv = [&](int j) {
+    const int buf = j & 1;
+    mbar_expect_tx(&bar_k[buf], KB);
+    tma_load_3d(smem + K_OFF + buf * KB, &mapKV, &bar_k[buf], kcol, j * BK, b);
+    mbar_expect_tx(&bar_v[buf], KB);
+    tma_load_3d(smem + V_OFF + buf * KB, &mapKV, &bar_v[buf], vcol, j * BK, b);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, QB);
+      tma_load_3d(smem, &mapQ, bar_q, qcol, mt * 128, b);
+      load_kv(0);
+      if (n_kv > 1) load_kv(1);
+    }
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_k[0], 0);
+    tc_fence_after();
+    if (elect_one()) issue_s(0);
+    __syncwarp();
+  }
+
+  const int r = tid;                           // query row of this thread = TMEM lane
+  const uint32_t t_row = ((uint32_t)(warp * 32) << 16);
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) o[i] = 0.f;
+  uint8_t* prow = smem + P_OFF + r * 128;
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int hi = min(BK, p.T - j * BK);      // keys of this block that exist
+    const bool masked = hi != BK;
+    mbar_wait(bar_s, j & 1);
+    tc_fence_after();
+    uint32_t sv[2][32];
+    tmem_ld32(tmem_s + t_row, sv[0]);
+    tmem_ld32(tmem_s + t_row + 32u, sv[1]);
+    tmem_ld_wait();
+    const float mx = masked ? af_local_max<true>(sv, 0, 0, hi) : af_local_max<false>(sv, 0, 0, hi);
+    const float m_new = fmaxf(m_run, mx * p.scale_log2);
+    const float alpha = af_ex2(m_run - m_new);           // 0 for the first block (m_run = -inf)
+    m_run = m_new;
+    const float sum = masked ? af_exp_block<true>(sv, 0, 0, hi, p.scale_log2, m_new, prow, r)
+                             : af_exp_block<false>(sv, 0, 0, hi, p.scale_log2, m_new, prow, r);
+    l_run = l_run * alpha + sum;
+    fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();              // every row of P written, every thread done reading S_j
+    if (warp == 0) {
+      mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
+      if (j + 1 < n_kv) mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t vbase = smem_u32(smem + V_OFF + (j & 1) * KB);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ad = make_desc_k(p_addr + k * 32, 64);
+          const uint64_t bd = make_desc_mn(vbase + k * 16 * ROWB, 1024, D);
+          umma_bf16(tmem_o, ad, bd, idesc_o, k > 0);
+        }
+        umma_commit(bar_o);
+        if (j + 1 < n_kv) issue_s(j + 1);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_o, j & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + t_row + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, __uint_as_float(v[i]));
+    }
+    if (warp == 0 && j + 2 < n_kv) {             // K_j / V_j buffers are free: fetch block j + 2 into them
+      if (elect_one()) load_kv(j + 2);
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+
+  const float inv = 1.0f / l_run;
+  if (mt * 128 + r < p.T) {
+    bf16* op = p.out + ((long long)b * p.T + mt * 128 + r) * p.C + h * D;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 16) {
+      uint4 ov[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        __nv_bfloat162* o2 = (__nv_bfloat162*)&ov[i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o2[q] = __floats2bfloat162_rn(o[c0 + i * 8 + 2 * q] * inv, o[c0 + i * 8 + 2 * q + 1] * inv);
+      }
+      stg256(op + c0, ov[0], ov[1]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct AttnFlashPlan { std::map<int, CUtensorMap> maps; std::map<int, CUtensorMap> maps64; };   // maps64: 64-row K / V boxes
 static std::map<const Op*, AttnFlashPlan> g_flash_plans;   // keyed by op address (ops vector is stable after build)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -274,7 +427,9 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_flash_encode = (EncodeTiledFn)fn;
     if (cudaFuncSetAttribute(attn_flash_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess) {
+        cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_flash64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_flash64_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(attn_flash_kernel) failed"; return CFM_ERR_CUDA;
     }
   }
@@ -303,6 +458,31 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.B = B;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
+  static const bool no64 = [] { const char* v = getenv("CFM_DISABLE_FLASH64"); return v && v[0] == '1'; }();
+  if (T > 128 && !no64) {
+    // long sequences: 64-key blocks, 3-4 CTAs per SM
+    auto it64 = pl.maps64.find(B);
+    if (it64 == pl.maps64.end()) {
+      CUtensorMap m;
+      const int C3 = 3 * op.Cin;
+      cuuint64_t dims[3] = {(cuuint64_t)C3, (cuuint64_t)T, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)C3 * 2, (cuuint64_t)T * C3 * 2};
+      cuuint32_t box[3] = {(cuuint32_t)op.ch, 64, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = g_flash_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  op.ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(qkv, flash64) failed"; return CFM_ERR_CUDA; }
+      it64 = pl.maps64.emplace(B, m).first;
+    }
+    const int rowb = op.ch * 2;
+    const size_t smem64 = (size_t)128 * rowb + 4 * 64 * rowb + 16384 + 128 + 1024;
+    LaunchCfg lc64(dim3((T + 127) / 128, B * op.heads), dim3(128), smem64, st, 1, pdl_enabled());
+    cudaError_t ce64 = op.ch == 64 ? cudaLaunchKernelEx(&lc64.cfg, attn_flash64_kernel<64>, it->second, it64->second, p)
+                                   : cudaLaunchKernelEx(&lc64.cfg, attn_flash64_kernel<32>, it->second, it64->second, p);
+    if (ce64 != cudaSuccess) { e.err = std::string("attn_flash64_kernel launch failed: ") + cudaGetErrorString(ce64); return CFM_ERR_CUDA; }
+    return 0;
+  }
   LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, ((B + p.pack - 1) / p.pack) * op.heads), dim3(256), AF_SMEM, st, 1, pdl_enabled());
   cudaError_t ce = op.ch == 64 ? cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<64>, it->second, p)
                                : cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<32>, it->second, p);
@@ -313,7 +493,7 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
 void attn_flash_release(Engine& e) {
   for (const Op& op : e.ops) {
     auto it = g_flash_plans.find(&op);
-    if (it != g_flash_plans.end()) it->second.maps.clear();
+    if (it != g_flash_plans.end()) { it->second.maps.clear(); it->second.maps64.clear(); }
   }
 }
 
