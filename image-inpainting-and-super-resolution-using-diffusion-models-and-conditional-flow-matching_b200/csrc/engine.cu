@@ -973,10 +973,14 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   const bool amort = opt->mode == CFM_DDPM_AMORTIZED;
   const int n_corr = (int)opt->n_corrector;
   if (n_corr < 0 || n_corr > 16) return fail(e, CFM_ERR_INVALID, "n_corrector out of range");
-  if (n_corr > 0 && !repl) return fail(e, CFM_ERR_INVALID, "corrector steps are implemented for Replacement conditioning only");
+  if (n_corr > 0 && !repl && !amort) return fail(e, CFM_ERR_INVALID, "corrector steps need Replacement or Amortized conditioning");
   const int n_slots = 2 + n_corr;
   int rc = ensure_batch(e, batch); if (rc) return rc;
   if ((rc = ensure_sampler(e, n, condition_dev ? n : 0, batch, Ns))) return rc;
+  // Amortized correctors call x0_model without a condition, i.e. with likelihood.none_like(xi): a constant image
+  // (sampling.py:34-37, 116); pad_value carries that constant.
+  if (amort && n_corr > 0 && (rc = grow(e, &e.v2_buf, &e.v2_cap, n))) return rc;
+  const float* corr_cond = amort && n_corr > 0 ? e.v2_buf : nullptr;
   e.launches = 0;
   auto blend_at = [&](int i) { return repl && i >= 0 && i < opt->replace_below_step; };
 
@@ -1013,6 +1017,7 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   CU_CHECK(e, cudaMemcpyAsync(e.ddpm_table, tab.data(), sizeof(DdpmStepScalars) * Ns, cudaMemcpyHostToDevice, st));
   CU_CHECK(e, cudaMemcpyAsync(e.t_table, tt.data(), sizeof(float) * Ns, cudaMemcpyHostToDevice, st));
   CU_CHECK(e, cudaMemsetAsync(e.step_counter, 0, sizeof(int), st));
+  if (corr_cond) { fill_f32_kernel<<<ew_blocks(e, n), 256, 0, st>>>(e.v2_buf, opt->pad_value, n); e.launches++; }
   CU_CHECK(e, cudaStreamSynchronize(st));   // host staging vectors go out of scope below
   if (n_corr == 0 && blend_at(Ns - 1)) {
     ddpm_blend_kernel<<<ew_blocks(e, n), 256, 0, st>>>(e.x_work, e.cond_work, tb->sqrt_alphas_cumprod[Ns - 1],
@@ -1021,13 +1026,13 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
     e.launches++;
   }
   auto body = [&](cudaStream_t s2) -> int {
-    if (n_corr > 0) { ddpm_blend_table_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.cond_work, e.ddpm_table, e.step_counter, noise_dev, seed, n); e.launches++; }
+    if (n_corr > 0 && repl) { ddpm_blend_table_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.cond_work, e.ddpm_table, e.step_counter, noise_dev, seed, n); e.launches++; }
     int r = forward_impl(e, batch, e.x_work, amort ? e.cond_work : nullptr, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
     if (r) return r;
     ddpm_step_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter,
                                                      condition_dev ? e.cond_work : nullptr, noise_dev, seed, n);
     for (int c = 0; c < n_corr; ++c) {
-      r = forward_impl(e, batch, e.x_work, nullptr, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
+      r = forward_impl(e, batch, e.x_work, corr_cond, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
       if (r) return r;
       ddpm_corrector_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter, noise_dev, seed, 2 + c, c == n_corr - 1, n);
       e.launches++;

@@ -59,6 +59,10 @@ __global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict
       cond[i] = __fadd_rn(cond[i], __fmul_rn(dt, cond[i]));
 }
 
+__global__ void fill_f32_kernel(float* __restrict__ p, float v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // classifier-free guidance: v_c <- v_c + w (v_c - v_u)   (= (1 + w) v_c - w v_u), evaluated in this order
 __global__ void cfg_combine_kernel(float* __restrict__ vc, const float* __restrict__ vu, float w, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;

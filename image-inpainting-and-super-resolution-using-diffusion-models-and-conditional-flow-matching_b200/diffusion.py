@@ -256,15 +256,28 @@ def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *
                               use_graph: bool = False) -> Callable:
     if not isinstance(eps_model, EpsModel):
         raise TypeError("wrap the network as EpsModel(network, ddpm) so the sampler can run on the engine")
-    if getattr(conditioning, "n_corrector", 0) and not isinstance(conditioning, Replacement):
-        raise NotImplementedError("Langevin corrector steps (n_corrector > 0) run on the engine for Replacement conditioning only")
+    if getattr(conditioning, "n_corrector", 0) and not isinstance(conditioning, (Replacement, Amortized)):
+        raise NotImplementedError("Langevin corrector steps (n_corrector > 0) run on the engine for Replacement and "
+                                  "Amortized conditioning only")
 
     if isinstance(conditioning, Amortized):
+        n_corr = int(getattr(conditioning, "n_corrector", 0))
+
         @torch.no_grad()
         def sample(xT, condition):
+            none_value = 0.0
+            if n_corr:
+                # the corrector's x0_model call has no condition -> likelihood.none_like(xi) (sampling.py:36-37, 116);
+                # every reference likelihood returns a constant image there, which is what the engine takes
+                none = likelihood.none_like(xT[:1])
+                none_value = float(none.flatten()[0])
+                if not bool((none == none_value).all()):
+                    raise NotImplementedError("Amortized corrector steps need a constant likelihood.none_like()")
             return eps_model.network.engine().sample_ddpm(xT, ddpm.tables(), mode="amortized", condition=condition,
+                                                          pad_value=none_value,
                                                           noise=_noise_tensor(noise, ddpm.Ns, xT), seed=seed,
-                                                          use_graph=use_graph)
+                                                          use_graph=use_graph, n_corrector=n_corr,
+                                                          corrector_delta=float(conditioning.delta))
         return sample
 
     if isinstance(conditioning, Replacement):

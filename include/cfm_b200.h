@@ -169,11 +169,13 @@ typedef struct cfm_ddpm_tables {
 
 typedef struct cfm_ddpm_options {
   int32_t mode;                /* cfm_ddpm_mode */
-  float   pad_value;           /* mask marker, exact compare (likelihoods.py pad_value = -2) */
+  float   pad_value;           /* Replacement: mask marker, exact compare (likelihoods.py pad_value = -2);
+                                * Amortized with correctors: the constant of likelihood.none_like() (sampling.py:36-37) */
   int32_t replace_below_step;  /* blend while i < this (int(Ns * start_fraction))            */
   int32_t noise_condition;     /* Replacement: q_sample the condition (1) or use it raw (0)  */
   uint32_t use_graph;
-  uint32_t n_corrector;        /* Langevin corrector steps after every predictor step (Replacement only; sampling.py:241-256) */
+  uint32_t n_corrector;        /* Langevin corrector steps after every predictor step (Replacement: sampling.py:241-256;
+                                * Amortized: sampling.py:113-127, the corrector's U-Net call sees none_like() as condition) */
   float   corrector_delta;     /* conditioning.delta: step = 0.5*dt*delta*score + sqrt(dt*delta)*z, dt = (1 - 1e-5)/Ns      */
   uint32_t reserved[1];
 } cfm_ddpm_options;

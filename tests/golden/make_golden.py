@@ -17,12 +17,62 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from _refload import load_reference  # noqa: E402
+from _refload import load_reference, load_reference_samplers  # noqa: E402
+from golden_configs import CHAIN_CASES, CHAIN_NS, chain_inputs, chain_net_cfg  # noqa: E402
 from oracle import unet as O  # noqa: E402
 from golden_configs import GOLDEN_CONFIGS  # noqa: E402
 
 
+def _ref_unet(ref, cfg, params):
+    model = ref.unet.UNetModel(
+        image_size=cfg.image_size, in_channels=cfg.in_channels, model_channels=cfg.model_channels,
+        out_channels=cfg.out_channels, num_res_blocks=cfg.num_res_blocks, attention_resolutions=cfg.attention_ds,
+        channel_mult=cfg.channel_mult, num_classes=None, num_heads=cfg.num_heads,
+        num_head_channels=cfg.num_head_channels, num_heads_upsample=cfg.num_heads_upsample,
+        use_scale_shift_norm=cfg.use_scale_shift_norm, resblock_updown=cfg.resblock_updown,
+        use_new_attention_order=cfg.use_new_attention_order).eval()
+    model.load_state_dict(params)
+    return model
+
+
+def chains():
+    """Whole reverse chains from the reference's own ``sampling.py`` (prior / Replacement / Amortized, with and without
+    Langevin correctors) on a small seeded network; the global torch generator is seeded right before each call."""
+    ref = load_reference_samplers()
+    d = {}
+    ddpm = ref.sde_diffusion.DDPM(CHAIN_NS)
+    lik = ref.likelihoods.InPainting(patch_size=6, pad_value=-2.0)
+    for name, case in CHAIN_CASES.items():
+        cfg = chain_net_cfg(case["in_ch"])
+        net = _ref_unet(ref, cfg, O.seeded_params(cfg, 41))
+        eps_model = lambda xi, i, net=net: net(xi, 1.0 * i / ddpm.Ns)      # experiments/main.py:140
+        if case["kind"] == "amortized":
+            cnd = ref.conditioning.Amortized(p_cond=0.9, n_corrector=case["n_corrector"], delta=case["delta"])
+        else:
+            cnd = ref.conditioning.Replacement(delta=case["delta"], start_fraction=case["start_fraction"],
+                                               noise=case["noise"], n_corrector=case["n_corrector"])
+        xT, cond = chain_inputs(case["seed"])
+        torch.manual_seed(case["seed"])
+        if case["prior"]:
+            out = ref.sampling.get_prior_sample_fn(eps_model, ddpm, cnd, lik)(xT.clone())
+        else:
+            out = ref.sampling.get_conditional_sample_fn(eps_model, ddpm, cnd, lik)(xT.clone(), cond.clone())
+        d[name] = out.numpy()
+        print(f"chain {name}: rms={float(out.pow(2).mean().sqrt()):.4f}")
+    # likelihoods.py condition builders under a seeded global generator (box draws: h first, then w, per sample)
+    rs = np.random.RandomState(77)
+    imgs = torch.from_numpy(rs.uniform(-1, 1, size=(3, 1, 28, 28)).astype(np.float32))
+    d["lik.images"] = imgs.numpy()
+    torch.manual_seed(7)
+    d["lik.inpaint"] = ref.likelihoods.InPainting(14, -2.0).sample(imgs).numpy()
+    torch.manual_seed(8)
+    d["lik.outpaint"] = ref.likelihoods.OutPainting(10, -2.0).sample(imgs).numpy()
+    d["lik.hyperres"] = ref.likelihoods.HyperResolution(7, 7).sample(imgs).numpy()
+    np.savez_compressed(os.path.join(HERE, "ddpm_chains.npz"), **d)
+
+
 def main():
+    chains()
     ref = load_reference()
     assert ref is not None, "/root/reference is required to generate golden vectors"
     torch.set_num_threads(os.cpu_count())

@@ -26,3 +26,39 @@ GOLDEN_CONFIGS = {
                                                  num_res_blocks=1, channel_mult="1,2", attention_resolutions="8",
                                                  num_heads=2, use_new_attention_order=True), 3, 5),
 }
+
+# --- whole DDPM reverse chains, run through the reference's sampling.py (tests/golden/ddpm_chains.npz) -----------------
+CHAIN_NS = 24      # beta_max = 20 / Ns must stay below 1 (sde_diffusion.py:14-15)
+
+
+def chain_net_cfg(in_ch):
+    return O.config_from_create_model(image_size=16, in_channels=in_ch, out_channels=1, num_channels=32, num_res_blocks=1,
+                                      channel_mult="1,2", attention_resolutions="8", resblock_updown=True)
+
+
+def chain_inputs(seed):
+    """xT and an in-painting condition (6x6 hole := -2) from a frozen numpy stream."""
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(500 + seed)
+    xT = torch.from_numpy(rs.standard_normal((2, 1, 16, 16)).astype(np.float32))
+    cond = torch.from_numpy(rs.uniform(-1, 1, size=(2, 1, 16, 16)).astype(np.float32))
+    cond[0, :, 5:11, 6:12] = -2.0
+    cond[1, :, 7:13, 5:11] = -2.0
+    return xT, cond
+
+
+def _case(kind, in_ch, seed, prior=False, n_corrector=0, delta=0.1, start_fraction=1.0, noise=True):
+    return dict(kind=kind, in_ch=in_ch, seed=seed, prior=prior, n_corrector=n_corrector, delta=delta,
+                start_fraction=start_fraction, noise=noise)
+
+
+CHAIN_CASES = {
+    "prior": _case("replacement", 1, 101, prior=True),
+    "prior_amortized": _case("amortized", 2, 102, prior=True),
+    "replacement": _case("replacement", 1, 103, start_fraction=0.75),
+    "replacement_raw_condition": _case("replacement", 1, 104, noise=False),
+    "replacement_corrector2": _case("replacement", 1, 105, n_corrector=2, delta=0.1),
+    "amortized": _case("amortized", 2, 106),
+    "amortized_corrector1": _case("amortized", 2, 107, n_corrector=1, delta=0.2),
+}

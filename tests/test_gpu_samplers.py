@@ -277,8 +277,39 @@ def test_ddpm_replacement_with_langevin_corrector(pkg, cuda, precision, tol):
         d = rel_l2(got, want)
         print(f"ddpm replacement + {n_corr} correctors [{precision}, graph={use_graph}] drift = {d:.3e}")
         assert d < tol
-    with pytest.raises(NotImplementedError):
-        pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(0.9, 1, 0.1), pkg.InPainting(6, -2.0))
+
+
+class AmortTape(SlotTape):
+    """Amortized chain: no q_sample draw; posterior draw (slot 1, skipped at i = 0), then the corrector draws."""
+
+    def __init__(self, Ns, shape, n_corrector):
+        super().__init__(Ns, shape, n_corrector)
+        self.order = [(i, s) for (i, s) in self.order if s != 0]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 6e-2)])
+def test_ddpm_amortized_with_langevin_corrector(pkg, cuda, precision, tol):
+    """Amortized predictor-corrector chain (sampling.py:113-127): the predictor's U-Net call sees the condition, the
+    corrector's sees likelihood.none_like(xi) = pad_value everywhere (sampling.py:36-37)."""
+    Ns, n_corr, delta = 24, 1, 0.2
+    net, ddpm, eps_oracle = ddpm_setup(pkg, cuda, precision, 2, Ns)
+    torch.manual_seed(9)
+    img = torch.rand(3, 1, 16, 16) * 2 - 1
+    cond = img.clone(); cond[:, :, 3:9, 5:11] = -2.0
+    xT = torch.randn(3, 1, 16, 16)
+    tape = AmortTape(Ns, xT.shape, n_corr)
+    want = D.sample_amortized(eps_oracle, Ns, xT, cond, tape, n_corrector=n_corr, delta=delta, none_value=-2.0)
+    assert tape.pos == len(tape.order)
+    plain = D.sample_amortized(eps_oracle, Ns, xT, cond, AmortTape(Ns, xT.shape, 0))
+    assert rel_l2(plain, want) > 10 * tol          # the corrector (and its none-condition) is visible in the result
+    for use_graph in (False, True):
+        fn = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(0.9, n_corr, delta),
+                                           pkg.InPainting(6, -2.0), noise=tape.t, use_graph=use_graph)
+        got = fn(xT.to(cuda), cond.to(cuda)).cpu()
+        assert got.abs().max() <= 1.0
+        d = rel_l2(got, want)
+        print(f"ddpm amortized + {n_corr} corrector [{precision}, graph={use_graph}] drift = {d:.3e}")
+        assert d < tol
 
 
 def _dopri5_shard_worker(rank, world, port, q):
@@ -329,3 +360,48 @@ def test_dopri5_sharded_shares_one_step_controller(pkg, cuda):
     for rank, lo, hi, xf, stats in res:
         assert stats["steps"] == ref_stats["steps"] and stats["accepted"] == ref_stats["accepted"], (stats, ref_stats)
         assert rel_l2(xf, ref[lo:hi]) < 1e-5
+
+
+def _reference_noise_tensor(case, Ns, shape):
+    """The draws the reference's sampler makes after ``torch.manual_seed(case.seed)`` (q_sample draw while blending,
+    posterior draw for i > 0, corrector draws), laid out as the engine's [Ns, 2 + n_corrector, n] tensor."""
+    n_corr = case["n_corrector"]
+    t = torch.zeros(Ns, 2 + n_corr, int(np.prod(shape)))
+    repl = case["kind"] == "replacement" and not case["prior"]
+    torch.manual_seed(case["seed"])
+    for i in reversed(range(Ns)):
+        if repl and case["noise"] and i < int(Ns * case["start_fraction"]):
+            t[i, 0] = torch.randn(shape).flatten()
+        if i > 0:
+            t[i, 1] = torch.randn(shape).flatten()
+        for c in range(n_corr):
+            t[i, 2 + c] = torch.randn(shape).flatten()
+    return t
+
+
+@pytest.mark.parametrize("name", ["prior", "prior_amortized", "replacement", "replacement_raw_condition",
+                                  "replacement_corrector2", "amortized", "amortized_corrector1"])
+def test_ddpm_chains_match_reference_golden(pkg, cuda, name):
+    """Engine chains against outputs of the reference's own sampling.py (tests/golden/ddpm_chains.npz)."""
+    import os
+    from golden_configs import CHAIN_CASES, CHAIN_NS, chain_inputs
+    case = CHAIN_CASES[name]
+    want = torch.from_numpy(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddpm_chains.npz"))[name])
+    net, ddpm, _ = ddpm_setup(pkg, cuda, "fp32", case["in_ch"], CHAIN_NS)
+    xT, cond = chain_inputs(case["seed"])
+    noise = _reference_noise_tensor(case, CHAIN_NS, xT.shape)
+    lik = pkg.InPainting(6, -2.0)
+    if case["kind"] == "amortized":
+        cnd = pkg.Amortized(0.9, case["n_corrector"], case["delta"])
+    else:
+        cnd = pkg.Replacement(delta=case["delta"], start_fraction=case["start_fraction"], noise=case["noise"],
+                              n_corrector=case["n_corrector"])
+    for use_graph in (False, True):
+        if case["prior"]:
+            got = pkg.get_prior_sample_fn(pkg.EpsModel(net, ddpm), ddpm, cnd, lik, noise=noise, use_graph=use_graph)(xT.to(cuda))
+        else:
+            got = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, cnd, lik, noise=noise,
+                                                use_graph=use_graph)(xT.to(cuda), cond.to(cuda))
+        d = rel_l2(got.cpu(), want)
+        print(f"{name} [graph={use_graph}] vs reference chain: rel-L2 = {d:.3e}")
+        assert d < 1e-3

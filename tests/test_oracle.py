@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from _refload import load_reference, reference_available
-from golden_configs import GOLDEN_CONFIGS
+from golden_configs import CHAIN_CASES, CHAIN_NS, GOLDEN_CONFIGS, chain_inputs, chain_net_cfg
 from oracle import ddpm as D
 from oracle import unet as O
 
@@ -107,3 +107,44 @@ def test_samplers_consume_noise_in_reference_order():
     calls.clear()
     out = D.sample_amortized(lambda x, t: torch.zeros(x.shape[0], 1, 8, 8), 30, xT, cond, noise)
     assert len(calls) == 29 and out.abs().max() <= 1
+
+
+@pytest.mark.parametrize("name", list(CHAIN_CASES))
+def test_ddpm_chains_match_reference_sampling(name):
+    """Whole reverse chains of the oracle against outputs of the reference's own ``sampling.py`` (ddpm_chains.npz,
+    tests/golden/make_golden.py): prior / Replacement / Amortized, with and without Langevin correctors.  The reference
+    draws with ``torch.randn_like`` from the global generator; the oracle's ``noise`` callable draws ``torch.randn`` of
+    the same shapes in the same order after the same seed, so the two chains see identical noise."""
+    case = CHAIN_CASES[name]
+    want = torch.from_numpy(np.load(os.path.join(GOLD, "ddpm_chains.npz"))[name])
+    cfg = chain_net_cfg(case["in_ch"])
+    params = O.seeded_params(cfg, 41)
+    eps = lambda xi, t: O.unet_forward(cfg, params, xi, t)
+    xT, cond = chain_inputs(case["seed"])
+    noise = lambda shape: torch.randn(tuple(shape))
+    torch.manual_seed(case["seed"])
+    if case["prior"] and case["kind"] == "amortized":
+        got = D.sample_amortized(eps, CHAIN_NS, xT, torch.full_like(xT, -2.0), noise)     # none_like as the condition
+    elif case["prior"]:
+        got = D.sample_prior(eps, CHAIN_NS, xT, noise)
+    elif case["kind"] == "amortized":
+        got = D.sample_amortized(eps, CHAIN_NS, xT, cond, noise, n_corrector=case["n_corrector"], delta=case["delta"],
+                                 none_value=-2.0)
+    else:
+        got = D.sample_replacement(eps, CHAIN_NS, xT, cond, noise, pad_value=-2.0, start_fraction=case["start_fraction"],
+                                   noise_condition=case["noise"], n_corrector=case["n_corrector"], delta=case["delta"])
+    err = float((got - want).abs().max())
+    print(f"{name}: max abs diff vs reference chain = {err:.2e}")
+    assert err < 2e-4
+
+
+def test_condition_builders_match_reference_likelihoods():
+    """likelihoods.py In/OutPainting/HyperResolution ``sample`` outputs (ddpm_chains.npz, ``lik.*``) against the oracle's
+    builders drawing from the same seeded global generator."""
+    g = np.load(os.path.join(GOLD, "ddpm_chains.npz"))
+    imgs = torch.from_numpy(g["lik.images"])
+    torch.manual_seed(7)
+    assert np.array_equal(D.inpainting_condition(imgs, 14, -2.0).numpy(), g["lik.inpaint"])
+    torch.manual_seed(8)
+    assert np.array_equal(D.outpainting_condition(imgs, 10, -2.0).numpy(), g["lik.outpaint"])
+    assert np.array_equal(D.hyperresolution_condition(imgs, (7, 7)).numpy(), g["lik.hyperres"])
