@@ -77,6 +77,7 @@ struct TcParams {
   int a_tile_bytes, a_halo_bytes;             // bytes of a plain / halo A load
   int kc;                      // channels per K-iteration: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int valid_rows;              // bw*bh*bn: rows of the tile that carry pixels (< 128*mh for maps such as 28x28)
+  int b_stat;                  // pair kernel, short-K 1x1 convs: the weight tile of this pair's N block stays in shared memory
   const float* bias;
   const float* emb; int emb_stride; const int* emb_row;
   const bf16* res0; const bf16* res1; int R0, R1;
@@ -468,6 +469,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     if (elect_one()) {
       Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+        const bool load_b = !p.b_stat || pt == pair;               // stationary weights: loaded with the first tile only
         const TileCoord tc = decode_pair_tile(p, pt, (int)rank);   // tb may equal tiles_b for the odd tail: all-OOB loads
         const int w0 = tc.tw * p.bw, h0 = tc.th * p.bh, n0 = tc.tb * p.bn;
         int brow = tc.ph * p.total_k * p.Cout + tc.nt * p.block_n + (int)rank * (p.block_n >> 1);
@@ -499,10 +501,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 if (leader) mbar_expect_tx(&fullA[ra.slot], 2 * p.a_tile_bytes);
                 tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * p.kc, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
                 ra.next();
-                mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
-                if (leader) mbar_expect_tx(&fullB[rb.slot], 2 * p.b_slot_bytes);
-                tma_load_2d_2sm(ring_b + rb.slot * p.b_slot_bytes, &mapB, mapa_u32(smem_u32(&fullB[rb.slot]), 0), 0, brow);
-                rb.next();
+                if (load_b) {
+                  mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
+                  if (leader) mbar_expect_tx(&fullB[rb.slot], 2 * p.b_slot_bytes);
+                  tma_load_2d_2sm(ring_b + rb.slot * p.b_slot_bytes, &mapB, mapa_u32(smem_u32(&fullB[rb.slot]), 0), 0, brow);
+                  rb.next();
+                }
               }
             }
           }
@@ -520,6 +524,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       Ring ra{0, 0, p.n_a}, rb{0, 0, p.n_b};
       int acc = 0; uint32_t acc_phase = 0;
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+        const bool wait_b = !p.b_stat || pt == pair;      // stationary weights (n_b == total_k: slot == K step) arrive once
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
@@ -532,7 +537,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             mbar_wait(&fullA[ra.slot], ra.phase);
             const uint32_t sa = smem_u32(ring_a + ra.slot * p.a_slot_bytes);
             for (int j = 0; j < G; ++j, ++kdone) {
-              mbar_wait(&fullB[rb.slot], rb.phase);
+              if (wait_b) mbar_wait(&fullB[rb.slot], rb.phase);
               tc_fence_after();
               if (elect_one()) {
                 const uint64_t adesc = make_desc_k(sa, p.kc) + (uint64_t)(sg.halo ? (uint32_t)j * row_step : 0u);
@@ -545,7 +550,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                     if (kMH == 2)   // each CTA's second 128 rows against the same (shared) weight tile
                       umma_bf16_2sm(d_tmem + (uint32_t)p.block_n, adesc + (uint64_t)half_step + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
                   }
-                umma_commit_2sm(&emptyB[rb.slot], 3);                         // both CTAs may refill this B slot
+                if (!p.b_stat) umma_commit_2sm(&emptyB[rb.slot], 3);          // both CTAs may refill this B slot
                 if (j == G - 1) umma_commit_2sm(&emptyA[ra.slot], 3);         // last view of this A slot
                 if (kdone == p.total_k - 1) umma_commit_2sm(&tfull_bar[acc], 3);   // both CTAs' epilogues may drain
               }
@@ -623,6 +628,7 @@ struct TcConvPlan {
   bool pair = false;                    // CTA-pair (cta_group::2) kernel
   int a_slot_bytes = 0, b_slot_bytes = 0, n_a = 0, n_b = 0, a_tile_bytes = 0, a_halo_bytes = 0;
   int kc = 64, valid_rows = 0;
+  bool b_stat = false;          // weights resident in shared memory across the M tiles of a pair (n_b == total_k)
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
@@ -734,6 +740,19 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   pl->a_slot_bytes = halo ? pl->a_halo_bytes : rows * row_bytes;
   if (halo && !size_rings(pl, eks)) { halo = false; pl->a_slot_bytes = rows * row_bytes; }
   if (!halo && !size_rings(pl, 1)) { e.err = "conv tile does not fit the shared-memory rings: " + op.name; delete pl; return CFM_ERR_INVALID; }
+  // Short-K 1x1 convs (qkv, proj_out) on the pair kernel: every M tile of a pair uses the same N block (the launch makes
+  // the number of pairs a multiple of tiles_n), so its whole K extent of weights is loaded once and stays in shared
+  // memory; the ring then only carries activations.  Re-loading 64 KB of weights per 64 KB of activations is what kept
+  // these layers at ~45 % of both the tensor pipe and DRAM with L2 -> SM traffic as the limiter.
+  {
+    const int tk = Cin / kc;
+    if (pl->pair && ks == 1 && !op.ups && op.skip0 < 0 && op.skip1 < 0 && tk <= TC_MAX_B && !env_off("CFM_DISABLE_TC_BSTAT") &&
+        (long long)tk * pl->b_slot_bytes + 3LL * pl->a_slot_bytes <= TC_RING_BYTES) {
+      pl->b_stat = true;
+      pl->n_b = tk;
+      pl->n_a = (int)std::min<long long>(TC_MAX_A, (TC_RING_BYTES - (long long)tk * pl->b_slot_bytes) / pl->a_slot_bytes);
+    }
+  }
   pl->seg[0] = {0, Cin / kc, eks, op.stride, halo ? 1 : 0}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
   if (op.skip0 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip0].C / kc, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip0; pl->n_seg++; }
   if (op.skip1 >= 0) { pl->seg[pl->n_seg] = {pl->n_seg, e.tensors[op.skip1].C / kc, 1, 1, 0}; pl->seg_tensor[pl->n_seg] = op.skip1; pl->n_seg++; }
@@ -868,7 +887,13 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   if (pl->pair) {
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
-    LaunchCfg lc(dim3(2 * std::min(pair_tiles, e.sm_count / 2)), dim3(TC_THREADS), TC_SMEM_BYTES, st, 2, pdl_enabled());
+    int n_pairs = std::min(pair_tiles, e.sm_count / 2);
+    if (pl->b_stat) {     // pairs walk pt = pair + k * n_pairs and nt = pt % tiles_n: constant per pair iff tiles_n | n_pairs
+      n_pairs = std::min(pair_tiles, e.sm_count / 2 / p.tiles_n * p.tiles_n);
+      p.b_stat = n_pairs > 0 && n_pairs % p.tiles_n == 0;
+      if (!p.b_stat) n_pairs = std::min(pair_tiles, e.sm_count / 2);
+    }
+    LaunchCfg lc(dim3(2 * n_pairs), dim3(TC_THREADS), TC_SMEM_BYTES, st, 2, pdl_enabled());
     auto kern = pl->mh == 2 ? conv_tc2_kernel<2> : conv_tc2_kernel<1>;
     cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, kern, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
     if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
