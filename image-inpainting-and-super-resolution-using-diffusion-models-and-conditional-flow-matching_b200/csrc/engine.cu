@@ -554,6 +554,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_GN: {
+        if (e.bf16 && gn_stream_supported(e, op)) {       // large maps: persistent TMA-pipelined kernel
+          int rc = gn_stream_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
         if (e.bf16 && gn_bf16_supported(e, op)) {
           int rc = gn_bf16_launch(e, op, B, st);
           if (rc) return rc;

@@ -145,6 +145,8 @@ int  attn_wide_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 void attn_wide_release(Engine& e);
 void attn_wide_forget(Engine& e);
 bool gn_bf16_supported(const Engine& e, const Op& op);
+bool gn_stream_supported(const Engine& e, const Op& op);
+int  gn_stream_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 bool resample_bf16_supported(const Engine& e, const Op& op);
 int  resample_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 bool head_conv_supported(const Engine& e, const Op& op);
