@@ -18,8 +18,8 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:44s} launches={a[0]:3d} total_us={a[1]:9.1f} share={100 * a[1] / tot:5.1f}%  dram_read_MB={a[2] / 1e6:9.1f} dram_write_MB={a[3] / 1e6:9.1f}")
 print(f"TOTAL launches={sum(a[0] for a in agg.values())} total_us={tot:.1f} dram_GB={sum(a[2] + a[3] for a in agg.values()) / 1e9:.2f}")
 if len(sys.argv) > 2:
-    conv = [a for k, a in agg.items() if k.startswith("conv_tc")]
+    conv = [a for k, a in agg.items() if "conv_tc" in k]
     n = sum(a[0] for a in conv)
     json.dump({"dram_bytes_per_launch": sum(a[2] + a[3] for a in conv) / n, "launches": n,
-               "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv_tc*/conv_tc2 launches of one NFE (profiles/r01_launch_list_v2.csv)"},
+               "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv_tc*/conv_tc2 launches of one NFE (" + sys.argv[1] + ")"},
               open(sys.argv[2], "w"), indent=1)
