@@ -426,12 +426,16 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_flash_encode = (EncodeTiledFn)fn;
+  }
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(attn_flash_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(attn_flash64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(attn_flash64_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(attn_flash_kernel) failed"; return CFM_ERR_CUDA;
     }
+    attr.done(e.device);
   }
   const int T = op.Hin * op.Win;
   AttnFlashPlan& pl = g_flash_plans[&op];

@@ -289,7 +289,11 @@ int attn_qkv_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_qkv_encode = (EncodeTiledFn)fn;
+  }
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(attn_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_qkv_kernel) failed"; return CFM_ERR_CUDA; }
+    attr.done(e.device);
   }
   const int C = op.Cin;
   if (!pl->mapW_ok) {

@@ -196,7 +196,11 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_attn_encode = (EncodeTiledFn)fn;
+  }
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_tc_kernel) failed"; return CFM_ERR_CUDA; }
+    attr.done(e.device);
   }
   AttnTcPlan& pl = g_attn_plans[&op];
   const void* qkv = tensor_ptr(e, op.src0, B);

@@ -218,7 +218,11 @@ int attn_wide_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_wide_encode = (EncodeTiledFn)fn;
+  }
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_wide_kernel) failed"; return CFM_ERR_CUDA; }
+    attr.done(e.device);
   }
   const int T = op.Hin * op.Win;
   AttnWidePlan& pl = g_wide_plans[&op];

@@ -812,14 +812,14 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
     pl->bias_pad = (float*)bp;
   }
   op.tc = pl;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending(e.device)) {
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(conv_tc_kernel, smem) failed"; return CFM_ERR_CUDA;
     }
-    attr_set = true;
+    attr_set.done(e.device);
   }
   return get_encode(e);
 }

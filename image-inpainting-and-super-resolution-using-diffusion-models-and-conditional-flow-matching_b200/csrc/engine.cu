@@ -575,11 +575,11 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         a.exact = e.bf16 ? 0 : 1;
         const int n = (op.Cin / 32) * a.HW;
         constexpr int kGnSmemBytes = 200 * 1024;
-        static bool gn_attr_set = false;
-        if (!gn_attr_set) {
+        static DeviceOnce gn_attr_set;
+        if (gn_attr_set.pending(e.device)) {
           CU_CHECK(e, cudaFuncSetAttribute(groupnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemBytes));
           CU_CHECK(e, cudaFuncSetAttribute(groupnorm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemBytes));
-          gn_attr_set = true;
+          gn_attr_set.done(e.device);
         }
         const int cap = kGnSmemBytes / 4;
         a.smem_elems = n <= cap ? n : 0;

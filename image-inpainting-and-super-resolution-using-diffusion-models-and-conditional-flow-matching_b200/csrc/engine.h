@@ -144,6 +144,14 @@ bool attn_wide_supported(const Engine& e, const Op& op);
 int  attn_wide_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 void attn_wide_release(Engine& e);
 void attn_wide_forget(Engine& e);
+// cudaFuncSetAttribute acts on the current device's context: remember what was set per device, not per process
+// (one process may own engines on several GPUs).
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  bool pending(int dev) const { return dev < 0 || dev >= 64 || !((mask >> dev) & 1ull); }
+  void done(int dev) { if (dev >= 0 && dev < 64) mask |= 1ull << dev; }
+};
+
 bool gn_bf16_supported(const Engine& e, const Op& op);
 bool gn_stream_supported(const Engine& e, const Op& op);
 int  gn_stream_launch(Engine& e, const Op& op, int B, cudaStream_t st);

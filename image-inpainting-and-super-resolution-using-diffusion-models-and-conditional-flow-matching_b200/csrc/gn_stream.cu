@@ -231,8 +231,8 @@ static int gs_encode(Engine& e, CUtensorMap* m, const void* ptr, int Csrc, long 
 }
 
 int gn_stream_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(gn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(gn_stream_kernel) failed"; return CFM_ERR_CUDA;
     }
@@ -240,7 +240,7 @@ int gn_stream_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     cudaDriverEntryPointQueryResult qr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_gs_encode = (GsEncodeFn)fn;
-    attr = true;
+    attr.done(e.device);
   }
   const GsGeom g = gs_geometry(e, op);
   const int HW = op.Hin * op.Win;

@@ -239,12 +239,12 @@ bool gn_bf16_supported(const Engine& e, const Op& op) {
 }
 
 int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(groupnorm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(groupnorm_bf16_kernel) failed"; return CFM_ERR_CUDA;
     }
-    attr = true;
+    attr.done(e.device);
   }
   const GnGeom g = gn_geometry(op);
   GnFastArgs a{};
@@ -354,10 +354,10 @@ bool head_conv_supported(const Engine& e, const Op& op) {
 
 int head_conv_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t st) {
   const size_t smem = (size_t)9 * op.Cin * HEAD_MAX_COUT * 4;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(head_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) { e.err = "cudaFuncSetAttribute(head_conv_kernel) failed"; return CFM_ERR_CUDA; }
-    attr = true;
+    attr.done(e.device);
   }
   const long long total = (long long)B * op.Hout * op.Wout;
   head_conv_kernel<<<(unsigned)((total + 127) / 128), 128, smem, st>>>((const bf16*)tensor_ptr(e, op.src0, B), op.w_main, op.bias, out, B, op.Hout, op.Wout, op.Cin, op.Cout);
@@ -423,10 +423,10 @@ bool stem_conv_supported(const Engine& e, const Op& op) {
 int stem_conv_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st) {
   const int cx = cond ? e.x_channels() : e.cfg.in_channels;
   const size_t smem = (size_t)(9 * op.Cin + 1) * op.Cout * 4;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) { e.err = "cudaFuncSetAttribute(stem_conv_kernel) failed"; return CFM_ERR_CUDA; }
-    attr = true;
+    attr.done(e.device);
   }
   const long long total = (long long)B * op.Hout * op.Wout * (op.Cout / 8);
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e.sm_count * 8);
@@ -557,10 +557,10 @@ int head_gather_launch(Engine& e, const Op& op, int B, float* out, cudaStream_t 
   const int R = std::max(1, std::min(op.Hin, 256 / op.Win));
   const int strips = (op.Hin + R - 1) / R;
   const size_t smem = sizeof(float) * (size_t)(R + 2) * op.Win * HG_STRIDE;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending(e.device)) {
     if (cudaFuncSetAttribute(head_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) { e.err = "cudaFuncSetAttribute(head_gather_kernel) failed"; return CFM_ERR_CUDA; }
-    attr = true;
+    attr.done(e.device);
   }
   if (smem > 96 * 1024) { e.err = "head gather strip does not fit shared memory"; return CFM_ERR_INVALID; }
   head_gather_kernel<<<B * strips, 256, smem, st>>>((const float*)tensor_ptr(e, op.src0, B), op.bias, out, B, op.Hin, op.Win, op.Cout, R);

@@ -209,3 +209,21 @@ def test_stream_groupnorm_opt_in(pkg, cuda, monkeypatch):
         d = rel_l2(out, base)
         print(f"stream GroupNorm vs staged GroupNorm [{name}]: rel-L2 = {d:.3e}")
         assert d < TOL["bf16"]          # other summation order -> different bf16 roundings downstream, same tolerance
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_engines_on_two_devices_in_one_process(pkg):
+    # kernel attributes (dynamic shared memory) are per device context: a second engine on another GPU of the same
+    # process must set them again; both devices must give the same bits
+    outs = []
+    for name in ("cifar", "mnist_ddpm"):
+        cfg, _, _ = GOLDEN_CONFIGS[name]
+        g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
+        params = O.seeded_params(cfg, int(g["seed"]))
+        for precision in ("bf16", "fp32"):
+            per_dev = []
+            for dev in ("cuda:0", "cuda:1"):
+                m = build(pkg, cfg, params, precision, torch.device(dev))
+                per_dev.append(m(torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["t"]).to(dev)).cpu())
+            assert torch.equal(per_dev[0], per_dev[1]), (name, precision)
+            assert rel_l2(per_dev[1], torch.from_numpy(g["out"])) < TOL[precision]
