@@ -157,6 +157,8 @@ class Engine:
             t_scalar = float(t)
         if out is None:
             out = torch.empty((B, self.config.out_channels, S, S), device=self.device, dtype=torch.float32)
+        if B == 0:          # empty batch: like the PyTorch module, an empty result (the C ABI rejects batch <= 0)
+            return out
         with torch.cuda.device(self.device):
             rc = self.lib.cfm_engine_forward(self._h, B, _ptr(xd), _ptr(cd), _ptr(t_dev), t_scalar, _ptr(yd),
                                              _ptr(out), _stream_ptr(self.device))
@@ -206,6 +208,8 @@ class Engine:
         tg = (C.c_float * max(n_steps, 1))(*[float(v) for v in t_grid])
         dg = (C.c_float * max(n_steps, 1))(*[float(v) for v in dt_grid])
         flags = (_lib.EULER_COND_DRIFT if cond_drift else 0) | (_lib.EULER_USE_GRAPH if use_graph else 0)
+        if B == 0:          # empty shard (more ranks than samples): nothing to integrate
+            return x, traj, img
         with torch.cuda.device(self.device):
             if guidance_weight is None:
                 rc = self.lib.cfm_sample_euler(self._h, B, _ptr(x), _ptr(cd), _ptr(yd), tg, dg, n_steps, flags,
@@ -247,6 +251,8 @@ class Engine:
         if noise is not None:
             nd = _as_f32_cuda(noise, self.device)
             assert nd.numel() == Ns * (2 + int(n_corrector)) * x.numel(), "noise must be [Ns, 2 + n_corrector, B*C*H*W]"
+        if x.shape[0] == 0:
+            return x
         with torch.cuda.device(self.device):
             rc = self.lib.cfm_sample_ddpm(self._h, x.shape[0], _ptr(x), _ptr(cd), C.byref(tb), C.byref(opt),
                                           _ptr(nd), C.c_uint64(seed), _stream_ptr(self.device))

@@ -109,6 +109,13 @@ def test_batch_independence_and_ragged_batches(pkg, cuda):
         assert torch.equal(full, parts)
     with pytest.raises(ValueError):
         m(torch.randn(2, 3, 15, 16, device=cuda), torch.rand(2, device=cuda))
+    # empty batch (a rank with no samples): an empty result like the PyTorch module, from the forward and the samplers
+    empty = m(torch.zeros(0, 3, 16, 16, device=cuda), torch.zeros(0, device=cuda))
+    assert tuple(empty.shape) == (0, 3, 16, 16)
+    e = m.engine()
+    xe, traj, img = e.sample_euler(torch.zeros(0, 3, 16, 16, device=cuda), [0.0, 0.5], [0.5, 0.5], return_trajectory=True,
+                                   return_uint8=True)
+    assert tuple(xe.shape) == (0, 3, 16, 16) and tuple(traj.shape) == (3, 0, 3, 16, 16) and img.numel() == 0
 
 
 def test_engine_flops_and_param_accounting(pkg, cuda):
