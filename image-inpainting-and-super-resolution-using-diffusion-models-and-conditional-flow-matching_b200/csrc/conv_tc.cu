@@ -35,6 +35,9 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;        // warp 0: TMA, warp 1
 constexpr int TC_MAX_COUT = 2048;                         // bias staged in smem
 constexpr int TC_MAX_A = 8, TC_MAX_B = 16;                // ring depths (A slots, B slots)
 constexpr int TC_RING_BYTES = 216 * 1024;                 // A ring + B ring
+constexpr int TC_STAGE_BUF = 16 * 1024;                   // TMA-store epilogue: one 128-row x 64-channel bf16 box
+constexpr int TC_STAGE_BYTES = 4 * TC_STAGE_BUF;          // two per epilogue warp group, taken from the top of the rings
+constexpr int TC_STAGE_OFF = TC_RING_BYTES - TC_STAGE_BYTES;
 constexpr int TC_BAR_BYTES = 512;
 constexpr int TC_SMEM_BYTES = TC_RING_BYTES + TC_MAX_COUT * 4 + TC_BAR_BYTES + 1024 /*align*/;
 
@@ -77,6 +80,8 @@ struct TcParams {
   int a_tile_bytes, a_halo_bytes;             // bytes of a plain / halo A load
   int kc;                      // channels per K-iteration: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int valid_rows;              // bw*bh*bn: rows of the tile that carry pixels (< 128*mh for maps such as 28x28)
+  int tma_store;               // pair kernel: epilogue stages bf16 rows in swizzled shared memory, TMA writes them out
+  int st_dh, st_dn;            // ... box origin of a CTA's second 128-row half (kMH = 2): rows / samples to skip
   int b_stat;                  // pair kernel, short-K 1x1 convs: the weight tile of this pair's N block stays in shared memory
   const float* bias;
   const float* emb; int emb_stride; const int* emb_row;
@@ -150,6 +155,17 @@ __device__ __forceinline__ void epi_load_res(const TcParams& p, const EpiRow& r,
     ldg256(rp + 16, res[2], res[3]);
   }
 }
+// pull the residual rows of a LATER tile into L2 (no registers held): the epilogue's residual loads are its only
+// DRAM-latency operand and, issued one chunk ahead, they left ~1 us exposed per chunk on the short-K layers
+__device__ __forceinline__ void epi_prefetch_res(const TcParams& p, const EpiRow& r, int c_begin, int n_cols) {
+  if (p.res0 && r.valid) {
+    for (int c = 0; c < n_cols; c += 64) {
+      const int cg = c_begin + c;
+      const bf16* rp = (cg < p.R0) ? p.res0 + r.pix * p.R0 + cg : p.res1 + r.pix * p.R1 + (cg - p.R0);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+    }
+  }
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -210,6 +226,43 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
   bf16* op = p.out + r.pix * p.Cout + cg;      // 64 B of this row: two full 32 B sectors per store instruction
   stg256(op, o[0], o[1]);
   stg256(op + 16, o[2], o[3]);
+}
+// TMA-store variant: the same arithmetic (bias + embedding + residual, one rounding to bf16), but the 64 bytes of this
+// row go to the staging box in shared memory - 128-byte rows, 16-byte chunks XOR-swizzled with the row (SWIZZLE_128B) -
+// `chunk0` = first of the four chunks (0 or 4).  Rows that are not pixels are written too: TMA clips them.
+__device__ __forceinline__ void epi_finish_smem(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
+                                                uint32_t s_bias_addr, uint32_t stage_row_addr, int row, int chunk0) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = lds_f4(s_bias_addr + (uint32_t)(cg + j) * 4u);
+    f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+  }
+  if (p.emb && r.valid) {
+    const float* embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 e4 = __ldg((const float4*)(embp + cg + j));
+      f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
+    }
+  }
+  if (p.res0 && r.valid) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 o;
+    __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+    sts_u4(stage_row_addr + (uint32_t)(((chunk0 + j) ^ (row & 7)) << 4), o);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -421,7 +474,7 @@ template <int kMH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
-                const TcParams p) {
+                const __grid_constant__ CUtensorMap mapOut, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring_a = smem;
@@ -572,11 +625,73 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int acc_cols = p.block_n * kMH;
     const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
+    if (p.tma_store) {
+      // ---- staged epilogue: each group of four warps (one per TMEM lane quadrant) owns two 16 KB staging boxes.  A unit
+      // is one 128-row x 64-channel box of the output: two 32-column TMEM chunks per thread, written as bf16 into the
+      // swizzled box, then ONE thread hands the box to TMA (full 128-byte lines, no per-lane sector stores).
+      const int n_cb = p.block_n >> 6;
+      const int n_units = n_cb * kMH;
+      const uint32_t stage0 = smem_u32(smem + TC_STAGE_OFF) + (uint32_t)(sub * 2 * TC_STAGE_BUF);
+      const int row = quad * 32 + lane;
+      const bool issuer = quad == 0 && lane == 0;
+      uint32_t n_store = 0;
+      if (issuer) prefetch_tmap(&mapOut);
+      for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+        const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
+        const int nt = tc.nt;
+        const EpiRow row0 = epi_decode_row(p, tc, row);
+        const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + row) : row0;
+        if (p.res0 && sub == 0 && pt + n_pairs < pair_tiles) {
+          const TileCoord tn = decode_pair_tile(p, pt + n_pairs, (int)rank);
+          epi_prefetch_res(p, epi_decode_row(p, tn, row), tn.nt * p.block_n, p.block_n);
+          if (kMH == 2) epi_prefetch_res(p, epi_decode_row(p, tn, 128 + row), tn.nt * p.block_n, p.block_n);
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
+        for (int u = sub; u < n_units; u += TC_EPI_WARPS / 4) {
+          const int half = (kMH == 2 && u >= n_cb) ? 1 : 0;
+          const int cb = u - half * n_cb;
+          const EpiRow rr = epi_pick(row0, row1, half != 0);
+          const uint32_t buf = stage0 + (n_store & 1u) * (uint32_t)TC_STAGE_BUF;
+          uint4 res[2][4];
+          epi_load_res(p, rr, lane, nt * p.block_n + (cb << 6), res[0]);
+          epi_load_res(p, rr, lane, nt * p.block_n + (cb << 6) + 32, res[1]);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int c0 = (cb << 6) + (it << 5);
+            uint32_t v[32];
+            tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
+            tmem_ld_wait();
+            epi_finish_smem(p, rr, nt * p.block_n + c0, v, res[it], s_bias_addr, buf + (uint32_t)row * 128u, row, it * 4);
+          }
+          fence_proxy_async();                      // generic-proxy writes of this thread -> visible to the TMA engine
+          if (issuer) bulk_wait_group_read0();      // the box stored one unit ago has been read: free after the barrier
+          named_bar_sync(1 + sub, 128);
+          if (issuer) {
+            tma_store_4d(&mapOut, smem + TC_STAGE_OFF + (sub * 2 + (int)(n_store & 1u)) * TC_STAGE_BUF, nt * p.block_n + (cb << 6),
+                         tc.tw * p.bw, tc.th * p.bh + half * p.st_dh, tc.tb * p.bn + half * p.st_dn);
+            bulk_commit_group();
+          }
+          ++n_store;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (issuer) bulk_wait_group0();               // shared memory stays valid until every box has left
+    } else
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
       const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
       const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;   // kMH = 1: never selected
+      if (p.res0 && sub == 0 && pt + n_pairs < pair_tiles) {
+        const TileCoord tn = decode_pair_tile(p, pt + n_pairs, (int)rank);
+        epi_prefetch_res(p, epi_decode_row(p, tn, quad * 32 + lane), tn.nt * p.block_n, p.block_n);
+        if (kMH == 2) epi_prefetch_res(p, epi_decode_row(p, tn, 128 + quad * 32 + lane), tn.nt * p.block_n, p.block_n);
+      }
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
         const int half = (kMH == 2 && sub >= chunks_per_half) ? 1 : 0;
@@ -616,7 +731,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct TcMaps { CUtensorMap a[3]; CUtensorMap b; };
+struct TcMaps { CUtensorMap a[3]; CUtensorMap b; CUtensorMap out; };
 
 struct TcConvPlan {
   bf16* w_packed = nullptr;     // [n_phase * total_k * Cout][64], K-iterations in the order the producer walks them
@@ -628,6 +743,9 @@ struct TcConvPlan {
   bool pair = false;                    // CTA-pair (cta_group::2) kernel
   int a_slot_bytes = 0, b_slot_bytes = 0, n_a = 0, n_b = 0, a_tile_bytes = 0, a_halo_bytes = 0;
   int kc = 64, valid_rows = 0;
+  bool tma_store = false;       // staged epilogue + TMA store (short-K layers on the pair kernel)
+  int st_bh = 0, st_bn = 0, st_dh = 0, st_dn = 0;   // store box (128 rows) and the origin shift of the second half
+  int ring_bytes = TC_RING_BYTES;
   bool b_stat = false;          // weights resident in shared memory across the M tiles of a pair (n_b == total_k)
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
@@ -683,7 +801,7 @@ static bool size_rings(TcConvPlan* pl, int G) {
   for (int D = 12; D >= G; --D) {
     const int n_b = D, n_a = (D + G - 1) / G + (G > 1 ? 1 : 0);
     if (n_a > TC_MAX_A || n_b > TC_MAX_B) continue;
-    if ((long long)n_a * pl->a_slot_bytes + (long long)n_b * pl->b_slot_bytes > TC_RING_BYTES) continue;
+    if ((long long)n_a * pl->a_slot_bytes + (long long)n_b * pl->b_slot_bytes > pl->ring_bytes) continue;
     pl->n_a = n_a; pl->n_b = n_b;
     return true;
   }
@@ -731,6 +849,22 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
       pl->bw = bwp; pl->bh = rows / bwp; pl->bn = 1; pl->valid_rows = rows;
     }
   }
+  // Short-K layers (stem, qkv, proj_out: <= 8 K-iterations per tile) are bound by their epilogue's row-per-lane stores
+  // (32 sectors of 32 different lines per instruction); they stage the tile in shared memory and let TMA write it.
+  // The staging boxes come out of the ring space, which these layers do not need.
+  {
+    static const int max_k = [] { const char* v = getenv("CFM_TC_TMA_STORE_MAX_K"); return v ? atoi(v) : 8; }();
+    const int tk_all = eks * eks * (Cin / kc) + op.Cskip / kc;
+    const bool halves_ok = pl->mh == 1 || pl->bn % 2 == 0 || (pl->bn == 1 && pl->bh % 2 == 0);
+    if (pl->pair && !op.out_is_output && !op.out_f32 && !op.ups && pl->block_n % 64 == 0 && Cout % 64 == 0 && tk_all <= max_k &&
+        pl->valid_rows == rows && pl->bw == Wg && halves_ok && !env_off("CFM_DISABLE_TC_TMA_STORE")) {
+      pl->tma_store = true;
+      pl->ring_bytes = TC_STAGE_OFF;
+      if (pl->mh == 1) { pl->st_bh = pl->bh; pl->st_bn = pl->bn; }
+      else if (pl->bn % 2 == 0) { pl->st_bh = pl->bh; pl->st_bn = pl->bn / 2; pl->st_dn = pl->bn / 2; }
+      else { pl->st_bh = pl->bh / 2; pl->st_bn = 1; pl->st_dh = pl->bh / 2; }
+    }
+  }
   // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous), fill its rows exactly and
   // an image row must be a whole number of 8-row swizzle atoms
   bool halo = eks > 1 && op.stride == 1 && pl->bn == 1 && pl->bw % 8 == 0 && pl->valid_rows == rows && !env_off("CFM_DISABLE_TC_HALO");
@@ -747,10 +881,10 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   {
     const int tk = Cin / kc;
     if (pl->pair && ks == 1 && !op.ups && op.skip0 < 0 && op.skip1 < 0 && tk <= TC_MAX_B && !env_off("CFM_DISABLE_TC_BSTAT") &&
-        (long long)tk * pl->b_slot_bytes + 3LL * pl->a_slot_bytes <= TC_RING_BYTES) {
+        (long long)tk * pl->b_slot_bytes + 3LL * pl->a_slot_bytes <= pl->ring_bytes) {
       pl->b_stat = true;
       pl->n_b = tk;
-      pl->n_a = (int)std::min<long long>(TC_MAX_A, (TC_RING_BYTES - (long long)tk * pl->b_slot_bytes) / pl->a_slot_bytes);
+      pl->n_a = (int)std::min<long long>(TC_MAX_A, (pl->ring_bytes - (long long)tk * pl->b_slot_bytes) / pl->a_slot_bytes);
     }
   }
   pl->seg[0] = {0, Cin / kc, eks, op.stride, halo ? 1 : 0}; pl->seg_tensor[0] = op.src0; pl->n_seg = 1;
@@ -850,6 +984,18 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(B) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
+  m->out = m->a[0];
+  if (pl->tma_store) {
+    const TensorDesc& t = e.tensors[op.out];
+    cuuint64_t odims[4] = {(cuuint64_t)t.C, (cuuint64_t)t.W, (cuuint64_t)t.H, (cuuint64_t)B};
+    cuuint64_t ostrides[3] = {(cuuint64_t)t.C * 2, (cuuint64_t)t.W * t.C * 2, (cuuint64_t)t.H * t.W * t.C * 2};
+    cuuint32_t obox[4] = {64, (cuuint32_t)pl->bw, (cuuint32_t)pl->st_bh, (cuuint32_t)pl->st_bn};
+    cuuint32_t oestr[4] = {1, 1, 1, 1};
+    r = g_encode(&m->out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, tensor_ptr(e, op.out, B), odims, ostrides, obox, oestr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { e.err = "cuTensorMapEncodeTiled(out) failed for " + op.name + " code " + std::to_string((int)r); return CFM_ERR_CUDA; }
+  }
   return 0;
 }
 
@@ -895,7 +1041,8 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
     }
     LaunchCfg lc(dim3(2 * n_pairs), dim3(TC_THREADS), TC_SMEM_BYTES, st, 2, pdl_enabled());
     auto kern = pl->mh == 2 ? conv_tc2_kernel<2> : conv_tc2_kernel<1>;
-    cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, kern, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
+    p.tma_store = pl->tma_store ? 1 : 0; p.st_dh = pl->st_dh; p.st_dn = pl->st_dn;
+    cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, kern, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, it->second.out, p);
     if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
     return 0;
   }
