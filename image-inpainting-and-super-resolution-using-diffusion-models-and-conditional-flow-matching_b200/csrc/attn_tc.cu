@@ -24,7 +24,7 @@ constexpr int AT_V_OFF = 0, AT_Q_OFF = 32768, AT_K_OFF = 49152, AT_P_OFF = 32768
 constexpr int AT_BAR_OFF = 98304, AT_XCH_OFF = 98304 + 64;
 constexpr int AT_SMEM = AT_XCH_OFF + 2 * 256 * 4 + 1024;
 
-struct AttnTcParams { int heads, C, new_order; float scale_log2; bf16* out; };
+struct AttnTcParams { int heads, C, new_order; float scale_log2; bf16* out; int pf_ahead; };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -73,6 +73,20 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
       mbar_expect_tx(bar_v, 2 * 16384);
       tma_load_2d(smem + AT_V_OFF, &map, bar_v, vcol, row0);
       tma_load_2d(smem + AT_V_OFF + 16384, &map, bar_v, vcol, row0 + 128);
+      // the CTA that inherits this SM slot is pf_ahead (sample, head) pairs further on: have its q / k / v boxes in L2
+      // by the time it starts (this kernel is a chain of dependent phases per CTA; its load is pure exposed latency)
+      const int y2 = (int)blockIdx.y + p.pf_ahead;
+      if (p.pf_ahead > 0 && y2 < (int)gridDim.y) {
+        const int b2 = y2 / p.heads, h2 = y2 % p.heads;
+        const int q2 = p.new_order ? h2 * AT_D : h2 * 3 * AT_D;
+        const int k2 = p.new_order ? p.C + h2 * AT_D : h2 * 3 * AT_D + AT_D;
+        const int v2 = p.new_order ? 2 * p.C + h2 * AT_D : h2 * 3 * AT_D + 2 * AT_D;
+        tma_prefetch_2d(&map, q2, b2 * AT_T + mt * AT_M);
+        if (mt == 0) {                          // k and v are shared by the two query tiles of a head
+          tma_prefetch_2d(&map, k2, b2 * AT_T); tma_prefetch_2d(&map, k2, b2 * AT_T + 128);
+          tma_prefetch_2d(&map, v2, b2 * AT_T); tma_prefetch_2d(&map, v2, b2 * AT_T + 128);
+        }
+      }
     }
     mbar_wait(bar_qk, 0);
     tc_fence_after();
@@ -221,6 +235,11 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.heads = op.heads; p.C = op.Cin; p.new_order = e.cfg.use_new_attention_order;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
+  {
+    // two CTAs per SM, two CTAs (query tiles) per (sample, head): one wave covers sm_count pairs
+    static const int pf = [] { const char* v = getenv("CFM_ATTN_PREFETCH"); return v ? atoi(v) : 1; }();
+    p.pf_ahead = pf * e.sm_count;
+  }
   LaunchCfg lc(dim3(AT_T / AT_M, B * op.heads), dim3(256), AT_SMEM, st, 1, pdl_enabled());
   if (cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel, it->second, p) != cudaSuccess) { e.err = "attn_tc_kernel launch failed"; return CFM_ERR_CUDA; }
   return 0;
