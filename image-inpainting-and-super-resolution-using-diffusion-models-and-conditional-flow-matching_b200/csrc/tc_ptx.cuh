@@ -196,6 +196,17 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
 }
+// cluster barrier without the release fence (for ordering mbarrier initialisation only, after fence_barrier_init)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+// remote shared-memory store that reports its bytes to an mbarrier of the destination CTA: the receiver just waits on
+// its own barrier - no cluster-wide barrier, no release fence on the sender
+__device__ __forceinline__ void st_async_v2f32(uint32_t cluster_addr, float x, float y, uint32_t cluster_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(x), "f"(y), "r"(cluster_mbar) : "memory");
+}
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
   float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory"); return v;
 }
