@@ -24,7 +24,7 @@ constexpr int AT_V_OFF = 0, AT_Q_OFF = 32768, AT_K_OFF = 49152, AT_P_OFF = 32768
 constexpr int AT_BAR_OFF = 98304, AT_XCH_OFF = 98304 + 64;
 constexpr int AT_SMEM = AT_XCH_OFF + 2 * 256 * 4 + 1024;
 
-struct AttnTcParams { int heads, C, new_order; float scale_log2; bf16* out; int pf_ahead; };
+struct AttnTcParams { int heads, C, new_order; float scale_log2; bf16* out; int pf_db, pf_dh; };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
   uint32_t* tmem_slot = (uint32_t*)(bar_qk + 4);
   float* xch = (float*)(smem + AT_XCH_OFF);            // [2][256]: per-thread partial max / sum for the row partner
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
+  // grid = (query tile, head, sample): no integer division in the prologue (the I2F / MUFU.RCP / F2I sequence of a
+  // division queued behind the other resident CTA's exponentials: 6.7 % of the kernel's stall samples)
+  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int qcol = p.new_order ? h * AT_D : h * 3 * AT_D;
   const int kcol = p.new_order ? p.C + h * AT_D : h * 3 * AT_D + AT_D;
   const int vcol = p.new_order ? 2 * p.C + h * AT_D : h * 3 * AT_D + 2 * AT_D;
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);      // in parallel with warp 0's barrier initialisation
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -75,9 +77,9 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
       tma_load_2d(smem + AT_V_OFF + 16384, &map, bar_v, vcol, row0 + 128);
       // the CTA that inherits this SM slot is pf_ahead (sample, head) pairs further on: have its q / k / v boxes in L2
       // by the time it starts (this kernel is a chain of dependent phases per CTA; its load is pure exposed latency)
-      const int y2 = (int)blockIdx.y + p.pf_ahead;
-      if (p.pf_ahead > 0 && y2 < (int)gridDim.y) {
-        const int b2 = y2 / p.heads, h2 = y2 % p.heads;
+      int h2 = h + p.pf_dh, b2 = b + p.pf_db;
+      if (h2 >= p.heads) { h2 -= p.heads; ++b2; }
+      if ((p.pf_db | p.pf_dh) != 0 && b2 < (int)gridDim.z) {
         const int q2 = p.new_order ? h2 * AT_D : h2 * 3 * AT_D;
         const int k2 = p.new_order ? p.C + h2 * AT_D : h2 * 3 * AT_D + AT_D;
         const int v2 = p.new_order ? 2 * p.C + h2 * AT_D : h2 * 3 * AT_D + 2 * AT_D;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,9 +240,10 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   {
     // two CTAs per SM, two CTAs (query tiles) per (sample, head): one wave covers sm_count pairs
     static const int pf = [] { const char* v = getenv("CFM_ATTN_PREFETCH"); return v ? atoi(v) : 1; }();
-    p.pf_ahead = pf * e.sm_count;
+    p.pf_db = pf * e.sm_count / op.heads; p.pf_dh = pf * e.sm_count % op.heads;
   }
-  LaunchCfg lc(dim3(AT_T / AT_M, B * op.heads), dim3(256), AT_SMEM, st, 1, pdl_enabled());
+  if (B > 65535) { e.err = "attn_tc: batch too large for the grid"; return CFM_ERR_INVALID; }
+  LaunchCfg lc(dim3(AT_T / AT_M, op.heads, B), dim3(256), AT_SMEM, st, 1, pdl_enabled());
   if (cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel, it->second, p) != cudaSuccess) { e.err = "attn_tc_kernel launch failed"; return CFM_ERR_CUDA; }
   return 0;
 }
