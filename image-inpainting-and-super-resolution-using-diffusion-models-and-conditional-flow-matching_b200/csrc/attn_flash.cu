@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256, 2) attn_flash_kernel(const __grid_constan
   uint32_t* tmem_slot = (uint32_t*)(bar_q + 7);
   float* xch = (float*)(smem + AF_XCH_OFF);            // [2][256]: per-block max (double-buffered by block parity)
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int mt = blockIdx.x, b = (blockIdx.y / p.heads) * p.pack, h = blockIdx.y % p.heads;   // b: first sample of the tile
+  const int mt = blockIdx.x, b = (int)blockIdx.z * p.pack, h = blockIdx.y;   // b: first sample of the tile; grid (tile, head, sample group): no prologue division
   const int qcol = p.new_order ? h * D : h * 3 * D;
   const int kcol = p.new_order ? p.C + h * D : h * 3 * D + D;
   const int vcol = p.new_order ? 2 * p.C + h * D : h * 3 * D + 2 * D;
@@ -273,7 +273,7 @@ attn_flash64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   uint64_t* bar_o = bar_q + 6;
   uint32_t* tmem_slot = (uint32_t*)(bar_q + 7);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
+  const int mt = blockIdx.x, b = blockIdx.z, h = blockIdx.y;      // grid (query tile, head, sample): no prologue division
   const int qcol = p.new_order ? h * D : h * 3 * D;
   const int kcol = p.new_order ? p.C + h * D : h * 3 * D + D;
   const int vcol = p.new_order ? 2 * p.C + h * D : h * 3 * D + 2 * D;
@@ -481,13 +481,15 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     }
     const int rowb = op.ch * 2;
     const size_t smem64 = (size_t)128 * rowb + 4 * 64 * rowb + 16384 + 128 + 1024;
-    LaunchCfg lc64(dim3((T + 127) / 128, B * op.heads), dim3(128), smem64, st, 1, pdl_enabled());
+    if (B > 65535) { e.err = "attn_flash64: batch too large for the grid"; return CFM_ERR_INVALID; }
+    LaunchCfg lc64(dim3((T + 127) / 128, op.heads, B), dim3(128), smem64, st, 1, pdl_enabled());
     cudaError_t ce64 = op.ch == 64 ? cudaLaunchKernelEx(&lc64.cfg, attn_flash64_kernel<64>, it->second, it64->second, p)
                                    : cudaLaunchKernelEx(&lc64.cfg, attn_flash64_kernel<32>, it->second, it64->second, p);
     if (ce64 != cudaSuccess) { e.err = std::string("attn_flash64_kernel launch failed: ") + cudaGetErrorString(ce64); return CFM_ERR_CUDA; }
     return 0;
   }
-  LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, ((B + p.pack - 1) / p.pack) * op.heads), dim3(256), AF_SMEM, st, 1, pdl_enabled());
+  if ((B + p.pack - 1) / p.pack > 65535) { e.err = "attn_flash: batch too large for the grid"; return CFM_ERR_INVALID; }
+  LaunchCfg lc(dim3((T + AF_M - 1) / AF_M, op.heads, (B + p.pack - 1) / p.pack), dim3(256), AF_SMEM, st, 1, pdl_enabled());
   cudaError_t ce = op.ch == 64 ? cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<64>, it->second, p)
                                : cudaLaunchKernelEx(&lc.cfg, attn_flash_kernel<32>, it->second, p);
   if (ce != cudaSuccess) { e.err = std::string("attn_flash_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1) attn_wide_kernel(const __grid_c
   uint64_t* bar_o = bar_s + 2;
   uint32_t* tmem_slot = (uint32_t*)(bar_s + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mt = blockIdx.x, b = blockIdx.y / p.heads, h = blockIdx.y % p.heads;
+  const int mt = blockIdx.x, b = blockIdx.z, h = blockIdx.y;      // grid (query tile, head, sample): no prologue division
   const int D = p.D, n_c = D >> 6;
   const int qcol = p.new_order ? h * D : h * 3 * D;
   const int kcol = p.new_order ? p.C + h * D : h * 3 * D + D;
@@ -244,7 +244,8 @@ int attn_wide_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.T = T; p.heads = op.heads; p.C = op.Cin; p.D = op.ch; p.new_order = e.cfg.use_new_attention_order;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
-  LaunchCfg lc(dim3((T + AW_M - 1) / AW_M, B * op.heads), dim3(AW_THREADS), AW_SMEM, st, 1, pdl_enabled());
+  if (B > 65535) { e.err = "attn_wide: batch too large for the grid"; return CFM_ERR_INVALID; }
+  LaunchCfg lc(dim3((T + AW_M - 1) / AW_M, op.heads, B), dim3(AW_THREADS), AW_SMEM, st, 1, pdl_enabled());
   cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, attn_wide_kernel, it->second, p);
   if (ce != cudaSuccess) { e.err = std::string("attn_wide_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
   return 0;

@@ -425,6 +425,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int nt = tc.nt;
       const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
       const EpiRow row1 = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
+      // (no L2 prefetch of the next tile's residual rows here: on the narrow MNIST layers this kernel serves, the extra
+      //  tile decode in a K = 32..96 tile's epilogue cost more than the latency it hid: proj_out 0.171 -> 0.187 ms)
       uint4 res_cur[4], res_nxt[4];
       if (sub < n_items) {
         const int half = sub >= chunks_per_half ? 1 : 0;          // mh <= 2
