@@ -7,8 +7,14 @@
 A "step" is one pass of the hot path over one batch: integrate `batch` synthetic noise images
 through `nfe` Euler steps of the CIFAR U-Net (cifar10/compute_fid.py:73-88) and produce the uint8
 images.  Prints ONE JSON line (contract in the task statement).  Multi-GPU: one process per GPU
-(torchrun), the batch is sharded with no collective inside the loop (weak scaling: every rank runs
-a full `batch`); NCCL only gathers the finished uint8 images in the end-to-end leg.
+(torchrun), the batch is sharded with no collective inside the loop.  N > 1 runs two legs: weak
+scaling (every rank integrates a full `batch`; the headline `value` unless --scaling strong) and
+strong scaling (`batch` samples in total, batch/N per rank; reported under "strong_scaling").
+In the end-to-end leg of N > 1 the finished uint8 shards are all-gathered over NCCL
+(`distributed.gather_uint8`) and rank 0 copies the whole set to the host inside the timed region.
+After the timed region rank 0 checks one NFE at the benchmarked batch against the reference's
+golden vector ("parity_check") and reports the final-sample drift of the 100-step sampler
+(bf16 engine vs fp32 engine vs CPU oracle, "drift").
 """
 from __future__ import annotations
 
@@ -41,6 +47,12 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--ref-nfe", type=int, default=2)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: which leg is the headline `value` (weak: --batch samples per GPU; strong: --batch samples in "
+                         "total, batch/N per GPU).  Both are measured and printed either way.")
+    ap.add_argument("--skip-drift", action="store_true")
+    ap.add_argument("--drift-batch", type=int, default=16, help="samples of the bf16-vs-fp32 100-step drift report")
+    ap.add_argument("--drift-oracle-batch", type=int, default=4, help="of which this many also run through the CPU oracle")
     return ap.parse_args()
 
 
@@ -148,6 +160,59 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
 
 
+def _drift_report(pkg, O, model_bf16, cfg, params, dev, nfe, batch, oracle_batch):
+    """Final-sample drift of the 100-step Euler sampler (north_star: "final-sample drift must be reported"):
+    the bf16 engine against the fp32 engine on `batch` samples and both against the CPU oracle on the first
+    `oracle_batch` of them (cifar10/compute_fid.py:73-88: same x0, same t_span, uint8 conversion included)."""
+    import torch
+    from oracle import ddpm as D
+    from oracle import integrators as I
+    t_span = torch.linspace(0, 1, nfe + 1)
+    x0 = torch.randn(batch, 3, 32, 32, generator=torch.Generator().manual_seed(2024))
+    m32 = pkg.UNetModelWrapper(dim=(3, 32, 32), num_res_blocks=2, num_channels=128, channel_mult=[1, 2, 2, 2], num_heads=4,
+                               num_head_channels=64, attention_resolutions="16", dropout=0.1, precision="fp32")
+    m32.load_state_dict(params)
+    m32 = m32.to(dev).eval()
+    xb, ib = pkg.sample_euler(model_bf16, x0.to(dev), t_span, return_uint8=True, use_graph=False)
+    xf, if_ = pkg.sample_euler(m32, x0.to(dev), t_span, return_uint8=True, use_graph=False)
+    m32.refresh()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    u8 = lambda a, b: {"mismatch_frac": float((a != b).float().mean()), "max_abs_diff": int((a.int() - b.int()).abs().max())}
+    rep = {"nfe": nfe, "batch": batch, "bf16_vs_fp32_engine": {"rel_l2": rel(xb.cpu(), xf.cpu()), "uint8": u8(ib.cpu(), if_.cpu())}}
+    if oracle_batch > 0:
+        t0 = time.perf_counter()
+        xo = I.euler_trajectory(lambda t, x: O.wrapper_forward(cfg, params, t, x), x0[:oracle_batch], t_span)[-1]
+        io = D.to_uint8(xo)
+        rep["oracle_batch"] = oracle_batch
+        rep["oracle_seconds"] = time.perf_counter() - t0
+        rep["bf16_vs_oracle"] = {"rel_l2": rel(xb[:oracle_batch].cpu(), xo), "uint8": u8(ib[:oracle_batch].cpu(), io)}
+        rep["fp32_engine_vs_oracle"] = {"rel_l2": rel(xf[:oracle_batch].cpu(), xo), "uint8": u8(if_[:oracle_batch].cpu(), io)}
+    return rep
+
+
+def _parity_check(model, dev, B):
+    """One NFE at the benchmarked batch with the reference's golden rows planted at both ends: bit-equality with the
+    batch-2 evaluation and rel-L2 against the reference's own output (tests/golden/unet_cifar.npz)."""
+    import numpy as np
+    import torch
+    g = np.load(os.path.join(ROOT, "tests", "golden", "unet_cifar.npz"))
+    gx, gt = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["t"]).to(dev)
+    eng = model.engine()
+    small = eng.forward(gx, gt)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(B, 3, 32, 32, device=dev, generator=gen)
+    t = torch.rand(B, device=dev, generator=gen)
+    spots = sorted({0, max(B - 2, 0)})
+    for s_ in spots:
+        x[s_:s_ + 2] = gx; t[s_:s_ + 2] = gt
+    out = eng.forward(x, t)
+    want = torch.from_numpy(g["out"])
+    rel = float((out[:2].cpu().double() - want.double()).norm() / want.double().norm())
+    return {"batch": B, "rel_l2_vs_reference_golden": rel, "tol": 2e-2, "within_tol": rel < 2e-2,
+            "bit_equal_vs_batch2": bool(all(torch.equal(out[s_:s_ + 2], small) for s_ in spots)),
+            "finite": bool(torch.isfinite(out).all())}
+
+
 def run_engine(args):
     import torch
     import torch.distributed as dist
@@ -171,12 +236,13 @@ def run_engine(args):
     pkg = g.load_package()
 
     cfg = cifar_config()
+    params = O.seeded_params(cfg, 0)
     model = pkg.UNetModelWrapper(dim=(3, 32, 32), num_res_blocks=2, num_channels=128, channel_mult=[1, 2, 2, 2], num_heads=4,
                                  num_head_channels=64, attention_resolutions="16", dropout=0.1, precision=args.precision)
-    model.load_state_dict(O.seeded_params(cfg, 0))
+    model.load_state_dict(params)
     model = model.to(dev).eval()
     eng = model.engine()
-    B, nfe = args.batch, args.nfe
+    nfe = args.nfe
     t_span = torch.linspace(0, 1, nfe + 1)
     use_graph = not args.no_graph
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -186,60 +252,86 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident leg: `value` ----------------
-    x_dev = [torch.randn(B, 3, 32, 32, device=dev, generator=gen) for _ in range(2)]
+    def max_over_ranks(ms):
+        v = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v)
 
-    def step_resident(i):
-        return pkg.sample_euler(model, x_dev[i % 2], t_span, return_uint8=True, use_graph=use_graph)
-
-    for i in range(args.warmup):
-        step_resident(i)
-    launches_per_step = eng.last_launches
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    def run_legs(Bper, total, steps, warmup, clocks_wanted):
+        """Device-resident leg and end-to-end leg at `Bper` samples on this rank (`total` over all ranks).
+        Returns (ms_resident, ms_e2e, launches_per_step, clock summary | None), times = max over ranks."""
+        x_dev = [torch.randn(Bper, 3, 32, 32, device=dev, generator=gen) for _ in range(2)]
+        for i in range(warmup):
+            pkg.sample_euler(model, x_dev[i % 2], t_span, return_uint8=True, use_graph=use_graph)
+        launches = eng.last_launches
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks = ClockSampler(local) if clocks_wanted else None
+        if clocks:
+            clocks.__enter__()
         ev0.record()
-        for i in range(args.steps):
-            step_resident(i)
+        for i in range(steps):
+            pkg.sample_euler(model, x_dev[i % 2], t_span, return_uint8=True, use_graph=use_graph)
         ev1.record()
         barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
-    value = B * world * args.steps / (ms_total / 1e3)
+        if clocks:
+            clocks.__exit__()
+        ms_res = max_over_ranks(ev0.elapsed_time(ev1))
 
-    # ---------------- end-to-end leg: host buffers in, uint8 images out ----------------
-    x_host = [torch.randn(B, 3, 32, 32).pin_memory() for _ in range(2)]
-    img_host = torch.empty(B, 3, 32, 32, dtype=torch.uint8).pin_memory()
+        # end to end: pinned host noise in, uint8 images of ALL ranks out on rank 0's host (N > 1: NCCL all-gather of the
+        # finished uint8 shards, cifar10/compute_fid.py:92-100 consumes the images on the host)
+        x_host = [torch.randn(Bper, 3, 32, 32).pin_memory() for _ in range(2)]
+        img_host = torch.empty(total if rank == 0 else 0, 3, 32, 32, dtype=torch.uint8).pin_memory()
 
-    def step_e2e(i):
-        xd = x_host[i % 2].to(dev, non_blocking=True)
-        _, img = pkg.sample_euler(model, xd, t_span, return_uint8=True, use_graph=use_graph)
-        img_host.copy_(img, non_blocking=True)
+        def step_e2e(i):
+            xd = x_host[i % 2].to(dev, non_blocking=True)
+            _, img = pkg.sample_euler(model, xd, t_span, return_uint8=True, use_graph=use_graph)
+            if world > 1:
+                img = pkg.gather_uint8(img, total)
+            if rank == 0:
+                img_host.copy_(img, non_blocking=True)
 
-    for i in range(min(args.warmup, 1)):
-        step_e2e(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step_e2e(i)
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * args.steps / (float(ms2) / 1e3)
+        for i in range(min(warmup, 1)):
+            step_e2e(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_e2e(i)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        return ms_res, ms_e2e, launches, (clocks.summary() if clocks else None)
+
+    B = args.batch
+    legs = {}
+    modes = ["weak"] if world == 1 else ["weak", "strong"]
+    if world > 1 and args.scaling == "strong":
+        modes = ["strong", "weak"]
+    for mode in modes:
+        if mode == "weak":
+            Bper, total = B, B * world
+        else:
+            lo, hi = pkg.shard_range(B, rank, world)
+            Bper, total = hi - lo, B
+        ms_res, ms_e2e, launches, clk = run_legs(Bper, total, args.steps, args.warmup, mode == modes[0])
+        legs[mode] = {"per_gpu_batch": Bper, "global_batch": total, "ms_per_step": ms_res / args.steps,
+                      "value": total * args.steps / (ms_res / 1e3), "e2e_value": total * args.steps / (ms_e2e / 1e3),
+                      "launches_per_step": launches, "clocks": clk,
+                      "h2d_bytes_per_step": total * 3 * 32 * 32 * 4, "d2h_bytes_per_step": total * 3 * 32 * 32}
+    head = legs[modes[0]]
+    Bper = head["per_gpu_batch"]
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel (conv_tc_kernel), measured live ----------------
+    # ---------------- roofline of the dominant kernel (tcgen05 conv), measured live ----------------
     peaks = measured_peaks()
-    rows = eng.profile_forward(x_dev[0], 0.5, repeats=3)
+    x_prof = torch.randn(Bper, 3, 32, 32, device=dev, generator=gen)
+    rows = eng.profile_forward(x_prof, 0.5, repeats=3)
     tc = [r for r in rows if r["kind"] == "conv_tcgen05"]
     roofline = None
     kernel_ms = {}
@@ -248,48 +340,78 @@ def run_engine(args):
     if tc:
         tc_ms = sum(r["ms"] for r in tc)
         tc_fl = sum(r["flops"] for r in tc)
+        tc_ex = sum(r["flops_executed"] for r in tc)
         achieved = tc_fl / (tc_ms * 1e-3) / 1e12
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
-        if os.path.isfile(tr_path):
-            try:
-                traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roofline = {"bound": "tensor", "kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv, all 64 launches of an NFE)", "achieved": achieved,
-                    "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"], "traffic": traffic,
-                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+        executed = tc_ex / (tc_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        for name in ("r02_conv_tc_traffic.json", "conv_tc_traffic.json"):
+            tr_path = os.path.join(ROOT, "profiles", name)
+            if os.path.isfile(tr_path):
+                try:
+                    traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+                    traffic_src = f"profiles/{name} (ncu --set full capture of an earlier run of this command, not this run)"
+                    break
+                except Exception:
+                    traffic = None
+        roofline = {"bound": "tensor", "kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of an NFE)",
+                    "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s", "frac": achieved / peaks["burst"],
+                    "achieved_algorithmic": achieved, "achieved_executed": executed,
+                    "frac_executed": executed / peaks["burst"],
+                    "frac_of_sustained": achieved / peaks["sustained"], "frac_executed_of_sustained": executed / peaks["sustained"],
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peaks["source"] + ", burst figure (per-launch CUDA-event timings, kernels timed alone)",
+                    "note": "algorithmic = 2*MAC of the reference's convs; executed = 2*MAC the kernels issue "
+                            "(the folded nearest-x2-upsample convs issue 4/9, the stem/head GEMMs run zero-padded K/N)",
                     "launches_per_nfe": len(tc), "flops_per_launch_avg": tc_fl / len(tc), "ms_per_launch_avg": tc_ms / len(tc),
                     "share_of_nfe": tc_ms / sum(kernel_ms.values())}
-    flops_step = eng.flops_per_sample * B * nfe
-    whole = {"achieved_tflops": value / world * nfe * eng.flops_per_sample / 1e12,
-             "frac_of_burst": value / world * nfe * eng.flops_per_sample / 1e12 / peaks["burst"],
-             "frac_of_sustained": value / world * nfe * eng.flops_per_sample / 1e12 / peaks["sustained"],
-             "ms_per_nfe": ms_total / args.steps / nfe, "kernel_ms_per_nfe": kernel_ms}
+    gn = [r for r in rows if r["kind"] == "groupnorm"]
+    hbm = None
+    if gn:
+        gn_ms = sum(r["ms"] for r in gn)
+        gn_b = sum(r["bytes"] for r in gn)
+        hbm = {"kernel": "GroupNorm(+FiLM)(+SiLU) pass, all launches of an NFE", "bound": "hbm", "achieved": gn_b / (gn_ms * 1e-3) / 1e9,
+               "peak": peaks["hbm"], "unit": "GB/s", "frac": gn_b / (gn_ms * 1e-3) / 1e9 / peaks["hbm"],
+               "launches_per_nfe": len(gn), "ms_per_nfe": gn_ms, "bytes_per_nfe": gn_b}
+    nfe_tf = head["value"] / world * nfe * eng.flops_per_sample / 1e12
+    whole = {"achieved_tflops": nfe_tf, "frac_of_burst": nfe_tf / peaks["burst"], "frac_of_sustained": nfe_tf / peaks["sustained"],
+             "ms_per_nfe": head["ms_per_step"] / nfe, "kernel_ms_per_nfe": kernel_ms}
 
+    parity = _parity_check(model, dev, Bper)
+    drift = None
     cpu = None
-    if world == 1 and not args.skip_cpu_baseline:
-        v, sec, cores = time_cpu_oracle(8, 2, 2, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "oracle port (torch CPU fp32), batch 8 x 2 Euler NFE per step, 1 warm-up + 2 timed, extrapolated to 100 NFE"}
+    if world == 1:
+        if not args.skip_drift:
+            drift = _drift_report(pkg, O, model, cfg, params, dev, nfe, args.drift_batch, args.drift_oracle_batch)
+        if not args.skip_cpu_baseline:
+            v, sec, cores = time_cpu_oracle(8, 2, 2, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "oracle port (torch CPU fp32), batch 8 x 2 Euler NFE per step, 1 warm-up + 2 timed, extrapolated to 100 NFE"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": modes[0], "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": "CIFAR-10 CFM UNetModel (num_channels=128, 2 res blocks, mult 1-2-2-2, attn@16x16, 4x64 heads), "
                                "100-step Euler, synthetic batch 1024 per GPU, random-init (seeded) weights",
-                   "per_gpu_batch": B, "global_batch": B * world, "nfe": nfe, "parallelism": f"dp{world} (batch sharded, no collective in loop)",
+                   "per_gpu_batch": Bper, "global_batch": head["global_batch"], "nfe": nfe,
+                   "parallelism": f"dp{world} (batch sharded, no collective in loop; NCCL all-gather of the uint8 images after it in the e2e leg)",
                    "cuda_graph": use_graph,
-                   "l2": f"activation working set {eng.workspace_bytes(B) / 2**30:.2f} GiB per NFE >> 126 MB L2 (no flush needed)"},
-        "nfe_per_sec": value * nfe / B, "sample_nfe_per_sec": value * nfe,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 32 * 32 * 4 * world,
-                "d2h_bytes_per_step": B * 3 * 32 * 32 * world},
-        "gpu_launches": launches_per_step * args.steps,
-        "clocks": clocks.summary(),
-        "roofline": roofline, "whole_step": whole, "flops_per_step": flops_step,
+                   "l2": f"activation working set {eng.workspace_bytes(Bper) / 2**30:.2f} GiB per NFE >> 126 MB L2 (no flush needed)"},
+        "nfe_per_sec": head["value"] * nfe / head["global_batch"] * world, "sample_nfe_per_sec": head["value"] * nfe,
+        "e2e": {"value": head["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": head["d2h_bytes_per_step"]},
+        "gpu_launches": head["launches_per_step"] * args.steps,
+        "clocks": head["clocks"],
+        "roofline": roofline, "hbm_roofline": hbm, "whole_step": whole, "flops_per_step": eng.flops_per_sample * Bper * nfe,
         "tensor_core_convs_per_nfe": eng.tensor_core_convs,
+        "parity_check": parity,
     }
+    for mode in modes[1:]:
+        o = legs[mode]
+        line[f"{mode}_scaling"] = {"value": o["value"], "unit": UNIT, "per_gpu_batch": o["per_gpu_batch"], "global_batch": o["global_batch"],
+                                   "ms_per_step": o["ms_per_step"], "e2e_value": o["e2e_value"]}
+    if drift is not None:
+        line["drift"] = drift
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "cfm_engine_profile_count": (C.c_int32, [C.c_void_p]),
     "cfm_engine_profile_get": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cfm_engine_op_info": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "cfm_sample_euler": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_uint32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1055,6 +1055,12 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   return 0;
 }
 
+double tc_conv_executed_flops(const Op& op) {
+  const TcConvPlan* pl = op.tc;
+  if (!pl) return op.flops;
+  return 2.0 * pl->Hg * pl->Wg * pl->n_phase * (double)pl->cout_pad * pl->total_k * pl->kc;
+}
+
 void tc_conv_release(Engine& e) {
   for (Op& op : e.ops)
     if (op.tc) op.tc->maps.clear();

@@ -886,6 +886,24 @@ int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t n
   return 0;
 }
 
+int cfm_engine_op_info(const cfm_engine* h, int32_t i, int32_t what, double* value) {
+  if (!h || !value || i < 0 || i >= (int32_t)h->impl.ops.size()) return CFM_ERR_INVALID;
+  const Engine& e = h->impl;
+  const Op& op = e.ops[i];
+  const double es = e.bf16 ? 2.0 : 4.0;
+  auto tb = [&](int id) { return id >= 0 ? (double)e.tensors[id].elems() * es : 0.0; };
+  if (what == 0) { *value = (op.kind == OP_CONV && op.tc) ? tc_conv_executed_flops(op) : op.flops; return 0; }
+  if (what == 1) {
+    double b = tb(op.src0) + tb(op.src1) + tb(op.skip0) + tb(op.skip1) + tb(op.res0) + tb(op.res1) + tb(op.out);
+    const int S = e.cfg.image_size;
+    if (op.src_is_input || op.kind == OP_IM2COL) b += 4.0 * e.cfg.in_channels * S * S;           // fp32 NCHW network input
+    if (op.out_is_output) b += 4.0 * e.cfg.out_channels * S * S;                                 // fp32 NCHW network output
+    *value = b;
+    return 0;
+  }
+  return CFM_ERR_INVALID;
+}
+
 static int sample_euler_impl(cfm_engine* h, int32_t batch, float* x_dev, float* cond_dev, const int64_t* y_dev,
                              bool guided, float guidance_w, const float* t_host, const float* dt_host, int32_t n_steps,
                              uint32_t flags, float* traj_dev, uint8_t* img_u8_dev, void* stream) {

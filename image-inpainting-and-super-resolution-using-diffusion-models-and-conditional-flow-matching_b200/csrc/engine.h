@@ -122,6 +122,7 @@ bool tc_conv_supported(const Engine& e, const Op& op);
 int  tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w_main_oihw, const std::vector<float>& w_skip_oi);
 int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_nchw = nullptr);
 void tc_conv_release(Engine& e);
+double tc_conv_executed_flops(const Op& op);   // 2*MAC per sample the tcgen05 kernel issues (padding and folding included)
 // bf16 fast kernels (kernels_bf16.cu)
 int  gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 // attn_tc.cu

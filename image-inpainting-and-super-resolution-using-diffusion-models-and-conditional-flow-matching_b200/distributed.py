@@ -29,6 +29,10 @@ def gather_uint8(local: torch.Tensor, total: int, group=None) -> Optional[torch.
     rank = dist.get_rank(group)
     sizes = [shard_range(total, r, world) for r in range(world)]
     max_n = max(hi - lo for lo, hi in sizes)
+    if total % world == 0:      # equal shards: one collective straight into the result, no padding or concatenation
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     bufs = [torch.empty_like(pad) for _ in range(world)]

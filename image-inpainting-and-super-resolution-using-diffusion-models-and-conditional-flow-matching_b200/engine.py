@@ -166,7 +166,8 @@ class Engine:
         return out
 
     def profile_forward(self, x: torch.Tensor, t: float = 0.5, y=None, cond=None, repeats: int = 3):
-        """Per-op device times of one NFE: list of dicts {name, kind, ms, flops} (flops for the whole batch)."""
+        """Per-op device times of one NFE: list of dicts {name, kind, ms, flops, flops_executed, bytes}, the last three
+        for the whole batch: algorithmic 2*MAC, the 2*MAC the kernel issues, algorithmic bytes (operands + result once)."""
         B = x.shape[0]
         xd = _as_f32_cuda(x, self.device)
         cd = None if cond is None else _as_f32_cuda(cond, self.device)
@@ -183,7 +184,11 @@ class Engine:
             name = C.create_string_buffer(128)
             kind, ms, fl = C.c_int32(), C.c_double(), C.c_double()
             _lib.check(self.lib.cfm_engine_profile_get(self._h, i, name, 128, C.byref(kind), C.byref(ms), C.byref(fl)), self._h)
-            rows.append({"name": name.value.decode(), "kind": kinds[kind.value], "ms": ms.value, "flops": fl.value * B})
+            ex, by = C.c_double(), C.c_double()
+            _lib.check(self.lib.cfm_engine_op_info(self._h, i, 0, C.byref(ex)), self._h)
+            _lib.check(self.lib.cfm_engine_op_info(self._h, i, 1, C.byref(by)), self._h)
+            rows.append({"name": name.value.decode(), "kind": kinds[kind.value], "ms": ms.value, "flops": fl.value * B,
+                         "flops_executed": ex.value * B, "bytes": by.value * B})
         return rows
 
     # --- fused fixed-step Euler loop ----------------------------------------------------------------

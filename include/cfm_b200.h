@@ -123,10 +123,16 @@ int cfm_engine_profile_forward(cfm_engine* e, int32_t batch, const float* x_dev,
 int32_t cfm_engine_profile_count(const cfm_engine* e);
 int cfm_engine_profile_get(const cfm_engine* e, int32_t i, char* name, int32_t name_cap, int32_t* kind,
                            double* ms, double* flops_per_sample);
+/* Static accounting of op i of the plan (same index space as cfm_engine_profile_get), per sample:
+ *   what = 0: EXECUTED flops (2*MAC the kernel issues: 4/9 of the algorithmic count for the folded
+ *             "nearest x2 upsample + 3x3 conv", more than it for zero-padded K / N of the stem and head GEMMs)
+ *   what = 1: algorithmic bytes (each operand read once + the result written once, at the storage width) */
+int cfm_engine_op_info(const cfm_engine* e, int32_t i, int32_t what, double* value);
 
 /* Flags for cfm_sample_euler. */
 #define CFM_EULER_COND_DRIFT   1u  /* conditioning is ODE state with d(con)/dt = con */
-#define CFM_EULER_USE_GRAPH    2u  /* capture the whole fixed-step loop into one CUDA graph      */
+#define CFM_EULER_USE_GRAPH    2u  /* capture ONE step (U-Net + update + counter bump) as a CUDA graph and replay it
+                                    * n_steps times; per-step scalars come from device tables indexed by a step counter */
 
 /* Fixed-step Euler: for k in [0, n_steps): x += dt[k] * model(t[k], x, y, cond).
  * t_host / dt_host: n_steps fp32 values each, in HOST memory (the torchdyn grid).

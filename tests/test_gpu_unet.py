@@ -234,3 +234,34 @@ def test_engines_on_two_devices_in_one_process(pkg):
                 per_dev.append(m(torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["t"]).to(dev)).cpu())
             assert torch.equal(per_dev[0], per_dev[1]), (name, precision)
             assert rel_l2(per_dev[1], torch.from_numpy(g["out"])) < TOL[precision]
+
+
+@pytest.mark.parametrize("B", [128, 1000, 1024])
+def test_cifar_nfe_at_benchmarked_batch(pkg, cuda, B):
+    # the shape bench.py times (CIFAR bf16, 1024 samples per NFE): multi-wave persistent tiling, stationary-weight pair
+    # counts, cluster GroupNorm and arena offsets beyond 2^31 bytes are only reached here.  The golden rows are planted
+    # at the start, in the middle and at the end of the batch (1000 is not a multiple of any tile count); every copy
+    # must equal the B = 2 result bit for bit and sit within the bf16 bar of the reference's own output.
+    cfg, _, _ = GOLDEN_CONFIGS["cifar"]
+    g = np.load(os.path.join(GOLD, "unet_cifar.npz"))
+    params = O.seeded_params(cfg, int(g["seed"]))
+    m = build(pkg, cfg, params, "bf16", cuda)
+    gx, gt = torch.from_numpy(g["x"]).to(cuda), torch.from_numpy(g["t"]).to(cuda)
+    small = m(gx, gt)
+    gen = torch.Generator(device=cuda).manual_seed(B)
+    x = torch.randn(B, 3, 32, 32, device=cuda, generator=gen)
+    t = torch.rand(B, device=cuda, generator=gen)
+    spots = [0, B // 2 - 1, B - 2]
+    for s in spots:
+        x[s:s + 2] = gx; t[s:s + 2] = gt
+    out = m(x, t)
+    assert torch.isfinite(out).all()
+    for s in spots:
+        assert torch.equal(out[s:s + 2], small), f"rows {s}..{s + 1} of a batch of {B} differ from the batch-2 result"
+    r = rel_l2(out[:2].cpu(), torch.from_numpy(g["out"]))
+    print(f"cifar[bf16, B={B}] rel-L2 vs reference golden = {r:.3e}")
+    assert r < TOL["bf16"], r
+    # uniform (scalar) t as the sampler uses it: the shared-row embedding path at the same batch
+    u = m(x, gt[0])
+    assert torch.equal(u[:1], m(gx[:1], gt[0]))
+    assert m.engine().workspace_bytes(B) == m.engine().workspace_bytes(1) * B
