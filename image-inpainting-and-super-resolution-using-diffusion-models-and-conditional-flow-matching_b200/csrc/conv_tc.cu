@@ -38,6 +38,10 @@ constexpr int TC_RING_BYTES = 216 * 1024;                 // A ring + B ring
 constexpr int TC_STAGE_BUF = 16 * 1024;                   // TMA-store epilogue: one 128-row x 64-channel bf16 box
 constexpr int TC_STAGE_BYTES = 4 * TC_STAGE_BUF;          // two per epilogue warp group, taken from the top of the rings
 constexpr int TC_STAGE_OFF = TC_RING_BYTES - TC_STAGE_BYTES;
+constexpr int TC_STAT_BYTES = 8 * 1024;                   // staged epilogue: GroupNorm-statistics scratch below the staging boxes
+constexpr int TC_STAT_OFF = TC_STAGE_OFF - TC_STAT_BYTES;
+constexpr int TC_STAT_MAX_COUT = 1024;                    // direct epilogue: its 4 KB scratch aliases the upper half of the bias array
+constexpr int TC_STAT_BIAS_OFF = TC_STAT_MAX_COUT;        // (floats)
 constexpr int TC_BAR_BYTES = 512;
 constexpr int TC_SMEM_BYTES = TC_RING_BYTES + TC_MAX_COUT * 4 + TC_BAR_BYTES + 1024 /*align*/;
 
@@ -89,6 +93,15 @@ struct TcParams {
   bf16* out;
   float* out_nchw; int cout_real;   // network head: fp32 NCHW output of the first cout_real channels
   float* out_f32;                   // fp32 NHWC output (head taps: 32 partial products per pixel)
+  // GroupNorm statistics of the OUTPUT, produced by the epilogue (pair kernel): per sample, per channel, stat_P partial
+  // (sum, sum of squares) pairs per granule of 4 channels, each over stat_R consecutive pixels of the sample - written once
+  // per partial in a fixed place (no atomics), summed in index order by the consumer (gn_apply_kernel).
+  // Layout [B][stat_P][Cout / 4] float2.
+  float2* stat_out;
+  int stat_P, stat_R;               // partials per sample; pixels (tile rows) per partial
+  int stat_seg;                     // rows of one warp that share a sample: 32, or 16 (4x4 maps)
+  int stat_sum_halves;              // kMH = 2 and a sample spans both 128-row halves of the CTA tile: summed in registers
+  FastDiv d_stat_R;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -172,9 +185,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   return v;
 }
 // accumulator chunk (32 fp32 from TMEM) + bias + embedding vector + residual -> bf16 NHWC (or fp32 NCHW for the head).
+// f[] returns the fp32 values before the rounding to bf16 (what the GroupNorm statistics are taken from).
 __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, int lane, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
-                                           uint32_t s_bias_addr) {
-  float f[32];
+                                           uint32_t s_bias_addr, float (&f)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 b4 = lds_f4(s_bias_addr + (uint32_t)(cg + j) * 4u);
@@ -231,8 +244,7 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
 // row go to the staging box in shared memory - 128-byte rows, 16-byte chunks XOR-swizzled with the row (SWIZZLE_128B) -
 // `chunk0` = first of the four chunks (0 or 4).  Rows that are not pixels are written too: TMA clips them.
 __device__ __forceinline__ void epi_finish_smem(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
-                                                uint32_t s_bias_addr, uint32_t stage_row_addr, int row, int chunk0) {
-  float f[32];
+                                                uint32_t s_bias_addr, uint32_t stage_row_addr, int row, int chunk0, float (&f)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 b4 = lds_f4(s_bias_addr + (uint32_t)(cg + j) * 4u);
@@ -263,6 +275,55 @@ __device__ __forceinline__ void epi_finish_smem(const TcParams& p, const EpiRow&
     for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
     sts_u4(stage_row_addr + (uint32_t)(((chunk0 + j) ^ (row & 7)) << 4), o);
   }
+}
+
+// GroupNorm statistics are kept per GRANULE of TC_STAT_G = 4 consecutive channels (every consumer's groups are whole
+// granules, engine.cu checks), which lets each lane fold its row's 32 columns to 8 (sum, sum of squares) pairs in
+// registers before anything crosses lanes.
+__device__ __forceinline__ void epi_granules(const float (&f)[32], float (&gs)[8], float (&gq)[8], bool accumulate) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float a = f[4 * g], b = f[4 * g + 1], c = f[4 * g + 2], d = f[4 * g + 3];
+    const float s = (a + b) + (c + d);
+    const float q = fmaf(a, a, fmaf(b, b, fmaf(c, c, d * d)));
+    gs[g] = accumulate ? gs[g] + s : s;
+    gq[g] = accumulate ? gq[g] + q : q;
+  }
+}
+// Sum the 8 granule pairs over the rows of a warp: reduce-scatter butterfly (4 + 2 + 1 exchanges per quantity), then
+// plain butterflies over the lanes that hold the same granule.  kSeg32: the 32 rows are one sample; lane l ends with
+// granule l >> 2 in gs[0], gq[0] (4 copies).  Otherwise each half-warp is a sample (16 pixels per sample, 4x4 maps):
+// lane l ends with granule (l >> 1) & 7 of its half-warp's rows (2 copies).
+template <bool kSeg32>
+__device__ __forceinline__ void epi_granule_reduce(float (&gs)[8], float (&gq)[8], int lane) {
+  constexpr int H0 = kSeg32 ? 16 : 8;
+#pragma unroll
+  for (int st = 0, H = H0, n = 4; st < 3; ++st, H >>= 1, n >>= 1) {
+    const bool up = (lane & H) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < n) {
+        const float ss = up ? gs[j] : gs[j + n], ks = up ? gs[j + n] : gs[j];
+        const float sq = up ? gq[j] : gq[j + n], kq = up ? gq[j + n] : gq[j];
+        gs[j] = ks + __shfl_xor_sync(0xffffffffu, ss, H);
+        gq[j] = kq + __shfl_xor_sync(0xffffffffu, sq, H);
+      }
+    }
+  }
+#pragma unroll
+  for (int H = kSeg32 ? 2 : 1; H >= 1; H >>= 1) {
+    gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], H);
+    gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], H);
+  }
+}
+// (sample, partial index) of the statistics unit whose first tile row is `row`; n >= B for rows past the batch
+__device__ __forceinline__ void epi_stat_unit(const TcParams& p, const TileCoord& c, int row, int* n, int* part) {
+  int wi, hi, ni, t;
+  p.d_bw.divmod(row, &t, &wi);
+  p.d_bh.divmod(t, &ni, &hi);
+  *n = c.tb * p.bn + ni;
+  const int pix = (c.th * p.bh + hi) * p.W + c.tw * p.bw + wi;       // index on the grid the tiles walk
+  *part = p.d_stat_R.div(pix) * p.n_phase + c.ph;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,7 +509,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
-        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
+        float f[32];
+        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr, f);
       }
       tc_fence_before();
       __syncwarp();
@@ -659,13 +721,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           uint4 res[2][4];
           epi_load_res(p, rr, lane, nt * p.block_n + (cb << 6), res[0]);
           epi_load_res(p, rr, lane, nt * p.block_n + (cb << 6) + 32, res[1]);
+          // statistics scratch [unit parity][32-column chunk][quadrant][granule]: written before the unit's barrier, read
+          // after it; the parity keeps a fast warp's next unit out of the buffer a slow warp is still reading
+          float2* scr = (float2*)(smem + TC_STAT_OFF) + (sub * 2 + (int)(n_store & 1u)) * 64;
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
             const int c0 = (cb << 6) + (it << 5);
             uint32_t v[32];
             tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
             tmem_ld_wait();
-            epi_finish_smem(p, rr, nt * p.block_n + c0, v, res[it], s_bias_addr, buf + (uint32_t)row * 128u, row, it * 4);
+            float f[32];
+            epi_finish_smem(p, rr, nt * p.block_n + c0, v, res[it], s_bias_addr, buf + (uint32_t)row * 128u, row, it * 4, f);
+            if (p.stat_out) {
+              float gs[8], gq[8];
+              if (!rr.valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = 0.f;
+              }
+              epi_granules(f, gs, gq, false);
+              epi_granule_reduce<true>(gs, gq, lane);
+              if ((lane & 3) == 0) scr[(it * 4 + quad) * 8 + (lane >> 2)] = make_float2(gs[0], gq[0]);
+            }
           }
           fence_proxy_async();                      // generic-proxy writes of this thread -> visible to the TMA engine
           if (issuer) bulk_wait_group_read0();      // the box stored one unit ago has been read: free after the barrier
@@ -675,6 +751,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                          tc.tw * p.bw, tc.th * p.bh + half * p.st_dh, tc.tb * p.bn + half * p.st_dn);
             bulk_commit_group();
           }
+          if (p.stat_out) {
+            // one partial per (unit of stat_R rows, granule): the quadrants of a unit are summed in a fixed order
+            const int bpu = p.stat_R >> 5, n_out = (4 / bpu) * 16;
+            if (row < n_out) {
+              const int u = row >> 4, gg = row & 15;
+              float ts = 0.f, tq = 0.f;
+              for (int b = 0; b < bpu; ++b) { const float2 t2 = scr[((gg >> 3) * 4 + u * bpu + b) * 8 + (gg & 7)]; ts += t2.x; tq += t2.y; }
+              int sn, sp;
+              epi_stat_unit(p, tc, half * 128 + u * p.stat_R, &sn, &sp);
+              if (sn < p.B) p.stat_out[((long long)sn * p.stat_P + sp) * (p.Cout >> 2) + ((nt * p.block_n + (cb << 6)) >> 2) + gg] = make_float2(ts, tq);
+            }
+          }
           ++n_store;
         }
         tc_fence_before();
@@ -683,7 +771,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (issuer) bulk_wait_group0();               // shared memory stays valid until every box has left
-    } else
+    } else {
+    // items of this warp, chunk-major: 32-column chunks sub, sub + 2, ...; for each, the kMH 128-row halves - so the
+    // statistics of a chunk are complete (and can be combined across the four quadrant warps) after its last half
+    const int n_mine = chunks_per_half > sub ? ((chunks_per_half - sub + 1) >> 1) * kMH : 0;
+    uint32_t n_stat = 0;
+    float2* scr0 = (float2*)(s_bias + TC_STAT_BIAS_OFF) + sub * 128;     // [chunk parity][block of stat_seg rows (<= 8)][8 granules]
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
@@ -695,32 +788,75 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (kMH == 2) epi_prefetch_res(p, epi_decode_row(p, tn, 128 + quad * 32 + lane), tn.nt * p.block_n, p.block_n);
       }
       uint4 res_cur[4], res_nxt[4];
-      if (sub < n_items) {
-        const int half = (kMH == 2 && sub >= chunks_per_half) ? 1 : 0;
-        epi_load_res(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
-      }
+      if (n_mine > 0) epi_load_res(p, row0, lane, nt * p.block_n + (sub << 5), res_nxt);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
-      for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
-        const int half = (kMH == 2 && item >= chunks_per_half) ? 1 : 0;
-        const int c0 = (item - half * chunks_per_half) << 5;
+      float run_s[8], run_q[8];
+      for (int k = 0; k < n_mine; ++k) {
+        const int half = kMH == 2 ? (k & 1) : 0;
+        const int c0 = (sub + 2 * (kMH == 2 ? (k >> 1) : k)) << 5;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
-        const int nxt = item + TC_EPI_WARPS / 4;
-        if (nxt < n_items) {
-          const int nh = (kMH == 2 && nxt >= chunks_per_half) ? 1 : 0;
-          epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
+        if (k + 1 < n_mine) {
+          const int nh = kMH == 2 ? ((k + 1) & 1) : 0;
+          const int nc0 = (sub + 2 * (kMH == 2 ? ((k + 1) >> 1) : (k + 1))) << 5;
+          epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + nc0, res_nxt);
         }
         tmem_ld_wait();
-        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
+        if (k == n_mine - 1) {       // last read of this accumulator stage: hand it back before the stores and the statistics
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        }
+        const EpiRow rr = epi_pick(row0, row1, half != 0);
+        float f[32];
+        epi_finish(p, rr, lane, nt * p.block_n + c0, v, res_cur, s_bias_addr, f);
+        if (p.stat_out) {
+          if (!rr.valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          const bool acc_halves = kMH == 2 && p.stat_sum_halves && half == 1;
+          epi_granules(f, run_s, run_q, acc_halves);
+          float2* scr = scr0 + (n_stat & 1u) * 64;       // parity: the next chunk never touches the buffer being combined
+          if (!(kMH == 2 && p.stat_sum_halves && half == 0)) {
+            if (p.stat_seg == 32) {
+              epi_granule_reduce<true>(run_s, run_q, lane);
+              const int blk = p.stat_sum_halves ? quad : half * 4 + quad;
+              if ((lane & 3) == 0) scr[blk * 8 + (lane >> 2)] = make_float2(run_s[0], run_q[0]);
+            } else {                 // 16 pixels per sample (kMH = 1): each half-warp is a sample
+              epi_granule_reduce<false>(run_s, run_q, lane);
+              if ((lane & 1) == 0) scr[(quad * 2 + (lane >> 4)) * 8 + ((lane >> 1) & 7)] = make_float2(run_s[0], run_q[0]);
+            }
+          }
+          if (half == kMH - 1) {
+            ++n_stat;
+            named_bar_sync(3 + sub, 128);
+            const int rows_blk = p.stat_sum_halves ? 64 : p.stat_seg;      // tile rows one scratch block stands for
+            const int bpu = p.stat_sum_halves ? 4 : p.stat_R / rows_blk;   // blocks per partial
+            const int n_blk = p.stat_sum_halves ? 4 : (128 * kMH) / rows_blk;
+            const int o = quad * 32 + lane;
+            if (o < (n_blk / bpu) * 8) {
+              const int u = o >> 3, gi = o & 7;
+              float ts = 0.f, tq = 0.f;
+              for (int b = 0; b < bpu; ++b) { const float2 t2 = scr[(u * bpu + b) * 8 + gi]; ts += t2.x; tq += t2.y; }
+              int sn, sp;
+              epi_stat_unit(p, tc, u * p.stat_R, &sn, &sp);
+              if (sn < p.B) p.stat_out[((long long)sn * p.stat_P + sp) * (p.Cout >> 2) + ((nt * p.block_n + c0) >> 2) + gi] = make_float2(ts, tq);
+            }
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // report to the leader
+      if (n_mine == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
   }
 
@@ -753,6 +889,8 @@ struct TcConvPlan {
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
 };
+
+static bool stats_geometry(const TcConvPlan* pl, int* R_out, int* seg_out, int* sum_halves_out);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -861,7 +999,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
     if (pl->pair && !op.out_is_output && !op.out_f32 && !op.ups && pl->block_n % 64 == 0 && Cout % 64 == 0 && tk_all <= max_k &&
         pl->valid_rows == rows && pl->bw == Wg && halves_ok && !env_off("CFM_DISABLE_TC_TMA_STORE")) {
       pl->tma_store = true;
-      pl->ring_bytes = TC_STAGE_OFF;
+      pl->ring_bytes = TC_STAT_OFF;          // staging boxes + statistics scratch sit above the rings
       if (pl->mh == 1) { pl->st_bh = pl->bh; pl->st_bn = pl->bn; }
       else if (pl->bn % 2 == 0) { pl->st_bh = pl->bh; pl->st_bn = pl->bn / 2; pl->st_dn = pl->bn / 2; }
       else { pl->st_bh = pl->bh / 2; pl->st_bn = 1; pl->st_dh = pl->bh / 2; }
@@ -1032,6 +1170,13 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.out = (bf16*)tensor_ptr(e, op.out, B);
   if (op.out_f32) p.out_f32 = (float*)tensor_ptr(e, op.out, B);
   if (op.out_is_output) { p.out_nchw = out_nchw; p.cout_real = op.Cout; }
+  if (op.emit_stats) {
+    int R, seg, sh;
+    if (!stats_geometry(pl, &R, &seg, &sh) || e.tensors[op.out].stat_off < 0 || !e.stats) { e.err = "internal: statistics requested from a conv that cannot emit them: " + op.name; return CFM_ERR_INTERNAL; }
+    p.stat_out = e.stats + (size_t)e.tensors[op.out].stat_off * B;
+    p.stat_P = e.tensors[op.out].stat_P; p.stat_R = R; p.stat_seg = seg; p.stat_sum_halves = sh;
+    p.d_stat_R.init(R);
+  }
   if (pl->pair) {
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
@@ -1053,6 +1198,31 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
   if (ce != cudaSuccess) { e.err = std::string("conv_tc_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
   return 0;
+}
+
+// GroupNorm statistics from the epilogue (pair kernel only): tiles of whole image rows without padding, and every group of
+// stat_seg consecutive tile rows inside one sample.  A partial covers R = min(HW, rows of the tile one warp group sums) rows.
+static bool stats_geometry(const TcConvPlan* pl, int* R_out, int* seg_out, int* sum_halves_out) {
+  if (!pl || !pl->pair || pl->cout_pad > TC_STAT_MAX_COUT) return false;
+  const int rows = 128 * pl->mh, HW = pl->Hg * pl->Wg;
+  if (pl->valid_rows != rows || pl->bw != pl->Wg) return false;
+  const int span = (pl->tma_store || pl->mh == 1) ? 128 : 256;     // staged epilogue: one 128-row half per unit
+  const int R = std::min(HW, span);
+  if (HW % R || span % R) return false;
+  if (R > 128 && rows % R) return false;
+  int seg;
+  if (R % 32 == 0) seg = 32;
+  else if (R == 16 && pl->mh == 1 && !pl->tma_store) seg = 16;
+  else return false;
+  *R_out = R; *seg_out = seg; *sum_halves_out = (R == 256) ? 1 : 0;
+  return true;
+}
+
+int tc_conv_stats_parts(const Engine& e, const Op& op) {
+  if (!e.bf16 || op.kind != OP_CONV || !op.tc || op.out_is_output || op.out_f32 || env_off("CFM_DISABLE_GN_STATS")) return 0;
+  int R, seg, sh;
+  if (!stats_geometry(op.tc, &R, &seg, &sh)) return 0;
+  return (op.tc->Hg * op.tc->Wg / R) * op.tc->n_phase;
 }
 
 double tc_conv_executed_flops(const Op& op) {

@@ -408,6 +408,29 @@ static int build_plan(Engine& e) {
   e.flops_per_sample = 2.0 * ((double)mc * e.ted + (double)e.ted * e.ted + (double)e.emb_total * e.ted);
   for (auto& op : e.ops) e.flops_per_sample += op.flops;
 
+  // ---- GroupNorm statistics from the producing convs' epilogues: a GroupNorm whose every source is written by a conv that
+  // can emit per-channel partial sums becomes one streaming pass (no reduction of its own) ----
+  {
+    std::vector<int> producer(e.tensors.size(), -1);
+    for (int i = 0; i < (int)e.ops.size(); ++i) if (e.ops[i].out >= 0) producer[e.ops[i].out] = i;
+    for (Op& gn : e.ops) {
+      if (gn.kind != OP_GN || !e.bf16 || !gn_apply_supported(e, gn)) continue;
+      bool ok = true;
+      for (int id : {gn.src0, gn.src1})
+        if (id >= 0) ok = ok && producer[id] >= 0 && tc_conv_stats_parts(e, e.ops[producer[id]]) > 0 && e.tensors[id].C % 8 == 0;
+      if (!ok) continue;
+      gn.use_stats = true;
+      for (int id : {gn.src0, gn.src1}) {
+        if (id < 0 || e.tensors[id].stat_P > 0) continue;
+        Op& pr = e.ops[producer[id]];
+        pr.emit_stats = true;
+        e.tensors[id].stat_P = tc_conv_stats_parts(e, pr);
+        e.tensors[id].stat_off = e.stats_per_sample;
+        e.stats_per_sample += (long long)e.tensors[id].stat_P * (e.tensors[id].C / 4);   // one pair per granule of 4 channels
+      }
+    }
+  }
+
   // ---- liveness + first-fit arena assignment (per-sample element offsets, 64-element aligned) ----
   for (int i = 0; i < (int)e.ops.size(); ++i) {
     const Op& op = e.ops[i];
@@ -460,6 +483,7 @@ static void drop_graphs(Engine& e) {
 static int ensure_batch(Engine& e, int B) {
   if (B > e.arena_batch) {
     if (e.arena) { cudaFree(e.arena); e.arena = nullptr; }
+    if (e.stats) { cudaFree(e.stats); e.stats = nullptr; }
     tc_conv_release(e);   // tensor maps hold arena addresses
     attn_tc_release(e);
     attn_flash_release(e);
@@ -468,6 +492,7 @@ static int ensure_batch(Engine& e, int B) {
     drop_graphs(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
     CU_CHECK(e, cudaMalloc(&e.arena, bytes));
+    if (e.stats_per_sample > 0) CU_CHECK(e, cudaMalloc((void**)&e.stats, sizeof(float2) * (size_t)e.stats_per_sample * B));
     e.arena_batch = B;
   }
   const int rows_needed = std::max(B, std::max(1, e.cfg.num_classes));
@@ -554,6 +579,12 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_GN: {
+        if (op.use_stats) {                                 // statistics already written by the producing convs
+          int rc = gn_apply_launch(e, op, B, st);
+          if (rc) return rc;
+          e.launches++;
+          break;
+        }
         if (e.bf16 && gn_stream_supported(e, op)) {       // large maps: persistent TMA-pipelined kernel
           int rc = gn_stream_launch(e, op, B, st);
           if (rc) return rc;
@@ -818,7 +849,7 @@ void cfm_engine_destroy(cfm_engine* h) {
     if (p) cudaFree(p);
   for (void* p : e.owned) cudaFree(p);
   for (cudaEvent_t ev : e.prof_events) cudaEventDestroy(ev);
-  for (void* p : {(void*)e.arena, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf, (void*)e.v2_buf})
+  for (void* p : {(void*)e.arena, (void*)e.stats, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf, (void*)e.v2_buf})
     if (p) cudaFree(p);
   delete h;
 }

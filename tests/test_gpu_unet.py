@@ -265,3 +265,33 @@ def test_cifar_nfe_at_benchmarked_batch(pkg, cuda, B):
     u = m(x, gt[0])
     assert torch.equal(u[:1], m(gx[:1], gt[0]))
     assert m.engine().workspace_bytes(B) == m.engine().workspace_bytes(1) * B
+
+
+@pytest.mark.parametrize("name,batch", [("cifar", 5), ("flowers_ddpm", 2), ("tiny_neworder", 7)])
+def test_groupnorm_statistics_from_conv_epilogues(pkg, cuda, monkeypatch, name, batch):
+    # default path: the convs' epilogues write per-channel partial sums and GroupNorm is one streaming pass
+    # (gn_apply_kernel); CFM_DISABLE_GN_STATS=1 keeps the self-contained GroupNorm kernel.  Same arithmetic up to the
+    # summation order of the statistics (fp32 accumulators before rounding vs the stored bf16 values): both must sit
+    # within the bf16 bar of the reference golden, and close to each other.  Concat-straddling groups (cifar 384 = 256 +
+    # 128), FiLM (flowers), 4x4 maps (16 pixels per sample) and ragged batches are all on this path.
+    cfg, _, _ = GOLDEN_CONFIGS[name]
+    g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
+    params = O.seeded_params(cfg, int(g["seed"]))
+    gx, gt = torch.from_numpy(g["x"]), torch.from_numpy(g["t"])
+    reps = (batch + gx.shape[0] - 1) // gx.shape[0]
+    x = torch.cat([gx] * reps)[:batch].to(cuda)
+    t = torch.cat([gt] * reps)[:batch].to(cuda)
+    m = build(pkg, cfg, params, "bf16", cuda)
+    fused = m(x, t).cpu()
+    names = [r["name"] for r in m.engine().profile_forward(x, 0.5, repeats=1)]
+    monkeypatch.setenv("CFM_DISABLE_GN_STATS", "1")
+    m2 = build(pkg, cfg, params, "bf16", cuda)
+    plain = m2(x, t).cpu()
+    monkeypatch.delenv("CFM_DISABLE_GN_STATS")
+    want = torch.from_numpy(g["out"])
+    n = want.shape[0]
+    r_f, r_p, d = rel_l2(fused[:n], want), rel_l2(plain[:n], want), rel_l2(fused, plain)
+    print(f"{name}: fused-statistics rel-L2 {r_f:.3e}, self-contained GroupNorm {r_p:.3e}, between them {d:.3e}")
+    assert r_f < TOL["bf16"] and r_p < TOL["bf16"] and d < TOL["bf16"]
+    for k in range(n, batch):                       # repeated golden rows: batch position must not matter
+        assert torch.equal(fused[k], fused[k % n])
