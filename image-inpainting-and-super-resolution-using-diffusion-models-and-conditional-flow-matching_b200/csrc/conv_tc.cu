@@ -38,10 +38,14 @@ constexpr int TC_RING_BYTES = 216 * 1024;                 // A ring + B ring
 constexpr int TC_STAGE_BUF = 16 * 1024;                   // TMA-store epilogue: one 128-row x 64-channel bf16 box
 constexpr int TC_STAGE_BYTES = 4 * TC_STAGE_BUF;          // two per epilogue warp group, taken from the top of the rings
 constexpr int TC_STAGE_OFF = TC_RING_BYTES - TC_STAGE_BYTES;
-constexpr int TC_STAT_BYTES = 8 * 1024;                   // staged epilogue: GroupNorm-statistics scratch below the staging boxes
-constexpr int TC_STAT_OFF = TC_STAGE_OFF - TC_STAT_BYTES;
-constexpr int TC_STAT_MAX_COUT = 1024;                    // direct epilogue: its 4 KB scratch aliases the upper half of the bias array
-constexpr int TC_STAT_BIAS_OFF = TC_STAT_MAX_COUT;        // (floats)
+// Fused GroupNorm epilogue (kGN): 12 KB taken from the top of the rings -
+//   [0, 2K)   mean / rstd per (sample of the tile, group): float2 [8][32]
+//   [2K, 4K)  gamma [256] | beta [256]
+//   [4K, 8K)  per-warp partial sums: float2 [chunk <= 8][block of rows <= 8][granule 8]
+//   [8K, 12K) per-(sample of the tile, channel) scale / shift of pass 2: float2 [2][256] (tiles of at most two samples)
+constexpr int TC_GN_BYTES = 12 * 1024;
+constexpr int TC_GN_OFF = TC_RING_BYTES - TC_GN_BYTES;
+constexpr int TC_GN_MAX_COUT = 256;
 constexpr int TC_BAR_BYTES = 512;
 constexpr int TC_SMEM_BYTES = TC_RING_BYTES + TC_MAX_COUT * 4 + TC_BAR_BYTES + 1024 /*align*/;
 
@@ -93,15 +97,16 @@ struct TcParams {
   bf16* out;
   float* out_nchw; int cout_real;   // network head: fp32 NCHW output of the first cout_real channels
   float* out_f32;                   // fp32 NHWC output (head taps: 32 partial products per pixel)
-  // GroupNorm statistics of the OUTPUT, produced by the epilogue (pair kernel): per sample, per channel, stat_P partial
-  // (sum, sum of squares) pairs per granule of 4 channels, each over stat_R consecutive pixels of the sample - written once
-  // per partial in a fixed place (no atomics), summed in index order by the consumer (gn_apply_kernel).
-  // Layout [B][stat_P][Cout / 4] float2.
-  float2* stat_out;
-  int stat_P, stat_R;               // partials per sample; pixels (tile rows) per partial
-  int stat_seg;                     // rows of one warp that share a sample: 32, or 16 (4x4 maps)
-  int stat_sum_halves;              // kMH = 2 and a sample spans both 128-row halves of the CTA tile: summed in registers
-  FastDiv d_stat_R;
+  // kGN: GroupNorm32 (+ SiLU) of the OUTPUT applied in the epilogue - the ResBlock's `out_layers.0` folded into its first
+  // conv (unet.py:307-308), so the un-normalised h is never written and the separate GroupNorm pass disappears.
+  const float* gn_gamma; const float* gn_beta; float gn_eps; int gn_cpg;
+  int gn_R, gn_R_log2, gn_cpg_log2; // rows of a CTA tile that belong to one sample: min(H * W, 128 * mh); powers of two
+  int gn_seg;                       // rows of one warp that share a sample: 32, or 16 (4x4 maps: a half-warp per sample)
+  int gn_ctas;                      // CTA tiles per sample (> 1: partial sums are exchanged through L2, see the kernel)
+  int gn_hw;                        // pixels per sample
+  int gn_silu;
+  uint2* gn_exch;                   // [B][gn_ctas][32][2]: {sum | sum of squares, epoch} of every group over one CTA tile
+  const unsigned* gn_epoch;         // device counter, bumped once per NFE (setup_rows_kernel): marks the words of this NFE
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -184,10 +189,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
-// accumulator chunk (32 fp32 from TMEM) + bias + embedding vector + residual -> bf16 NHWC (or fp32 NCHW for the head).
-// f[] returns the fp32 values before the rounding to bf16 (what the GroupNorm statistics are taken from).
-__device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, int lane, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
-                                           uint32_t s_bias_addr, float (&f)[32]) {
+// accumulator chunk (32 fp32 from TMEM) + bias + embedding vector, in fp32
+__device__ __forceinline__ void epi_bias_emb(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], uint32_t s_bias_addr,
+                                             float (&f)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 b4 = lds_f4(s_bias_addr + (uint32_t)(cg + j) * 4u);
@@ -202,6 +206,25 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
       f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
     }
   }
+}
+// 32 fp32 -> bf16, this lane's 64 B of its output row: two full 32 B sectors per store instruction
+__device__ __forceinline__ void epi_store_bf16(const TcParams& p, const EpiRow& r, int cg, const float (&f)[32]) {
+  uint4 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162* ob = (__nv_bfloat162*)&o[j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+  }
+  bf16* op = p.out + r.pix * p.Cout + cg;
+  stg256(op, o[0], o[1]);
+  stg256(op + 16, o[2], o[3]);
+}
+// accumulator chunk (32 fp32 from TMEM) + bias + embedding vector + residual -> bf16 NHWC (or fp32 NCHW for the head).
+__device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, int lane, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
+                                           uint32_t s_bias_addr) {
+  float f[32];
+  epi_bias_emb(p, r, cg, v, s_bias_addr, f);
   if (p.out_nchw) {
     // head conv: channel-planar fp32; lanes are consecutive pixels -> coalesced per channel
     if (!r.valid) return;
@@ -229,57 +252,11 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
       for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
     }
   }
-  uint4 o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __nv_bfloat162* ob = (__nv_bfloat162*)&o[j];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-  }
-  bf16* op = p.out + r.pix * p.Cout + cg;      // 64 B of this row: two full 32 B sectors per store instruction
-  stg256(op, o[0], o[1]);
-  stg256(op + 16, o[2], o[3]);
+  epi_store_bf16(p, r, cg, f);
 }
-// TMA-store variant: the same arithmetic (bias + embedding + residual, one rounding to bf16), but the 64 bytes of this
-// row go to the staging box in shared memory - 128-byte rows, 16-byte chunks XOR-swizzled with the row (SWIZZLE_128B) -
-// `chunk0` = first of the four chunks (0 or 4).  Rows that are not pixels are written too: TMA clips them.
-__device__ __forceinline__ void epi_finish_smem(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
-                                                uint32_t s_bias_addr, uint32_t stage_row_addr, int row, int chunk0, float (&f)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 b4 = lds_f4(s_bias_addr + (uint32_t)(cg + j) * 4u);
-    f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-  }
-  if (p.emb && r.valid) {
-    const float* embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 e4 = __ldg((const float4*)(embp + cg + j));
-      f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
-    }
-  }
-  if (p.res0 && r.valid) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 o;
-    __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-    sts_u4(stage_row_addr + (uint32_t)(((chunk0 + j) ^ (row & 7)) << 4), o);
-  }
-}
-
-// GroupNorm statistics are kept per GRANULE of TC_STAT_G = 4 consecutive channels (every consumer's groups are whole
-// granules, engine.cu checks), which lets each lane fold its row's 32 columns to 8 (sum, sum of squares) pairs in
-// registers before anything crosses lanes.
+// ---- fused GroupNorm epilogue helpers ----
+// Statistics are kept per GRANULE of 4 consecutive channels (a group is a whole number of granules: cpg % 4 == 0), so each
+// lane folds its row's 32 columns to 8 (sum, sum of squares) pairs in registers before anything crosses lanes.
 __device__ __forceinline__ void epi_granules(const float (&f)[32], float (&gs)[8], float (&gq)[8], bool accumulate) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
@@ -316,14 +293,48 @@ __device__ __forceinline__ void epi_granule_reduce(float (&gs)[8], float (&gq)[8
     gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], H);
   }
 }
-// (sample, partial index) of the statistics unit whose first tile row is `row`; n >= B for rows past the batch
-__device__ __forceinline__ void epi_stat_unit(const TcParams& p, const TileCoord& c, int row, int* n, int* part) {
-  int wi, hi, ni, t;
-  p.d_bw.divmod(row, &t, &wi);
-  p.d_bh.divmod(t, &ni, &hi);
-  *n = c.tb * p.bn + ni;
-  const int pix = (c.th * p.bh + hi) * p.W + c.tw * p.bw + wi;       // index on the grid the tiles walk
-  *part = p.d_stat_R.div(pix) * p.n_phase + c.ph;
+__device__ __forceinline__ void st_relaxed_gpu_v2(uint2* p, unsigned x, unsigned y) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_relaxed_gpu_v2(const uint2* p) {
+  uint2 v; asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory"); return v;
+}
+// TMA-store variant: the same arithmetic (bias + embedding + residual, one rounding to bf16), but the 64 bytes of this
+// row go to the staging box in shared memory - 128-byte rows, 16-byte chunks XOR-swizzled with the row (SWIZZLE_128B) -
+// `chunk0` = first of the four chunks (0 or 4).  Rows that are not pixels are written too: TMA clips them.
+__device__ __forceinline__ void epi_finish_smem(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], uint4 (&res)[4],
+                                                uint32_t s_bias_addr, uint32_t stage_row_addr, int row, int chunk0) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = lds_f4(s_bias_addr + (uint32_t)(cg + j) * 4u);
+    f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+  }
+  if (p.emb && r.valid) {
+    const float* embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 e4 = __ldg((const float4*)(embp + cg + j));
+      f[j] += e4.x; f[j + 1] += e4.y; f[j + 2] += e4.z; f[j + 3] += e4.w;
+    }
+  }
+  if (p.res0 && r.valid) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 o;
+    __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+    sts_u4(stage_row_addr + (uint32_t)(((chunk0 + j) ^ (row & 7)) << 4), o);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,8 +520,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
-        float f[32];
-        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr, f);
+        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
       tc_fence_before();
       __syncwarp();
@@ -534,7 +544,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // kMH: 128-row M-halves per CTA, a compile-time constant so that the kMH = 1 instances (N >= 192 layers, most of
 // them short-K and epilogue-bound) carry none of the two-half bookkeeping
-template <int kMH>
+// kGN: the epilogue also applies GroupNorm32 (+ SiLU) to the tile (see the epilogue branch below).
+template <int kMH, bool kGN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -574,6 +585,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
+  if (kGN) {
+    float* s_gb = (float*)(smem + TC_GN_OFF + 2048);
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) { s_gb[i] = p.gn_gamma[i]; s_gb[TC_GN_MAX_COUT + i] = p.gn_beta[i]; }
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                 // peer barriers initialised before any remote arrive / multicast commit
@@ -689,7 +704,163 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int acc_cols = p.block_n * kMH;
     const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
-    if (p.tma_store) {
+    if (kGN) {
+      // ---- fused GroupNorm epilogue (ResBlock conv1 + out_layers.0/1): two passes over the accumulator stage.
+      // Pass 1: every warp folds its rows to per-granule (sum, sum of squares), the eight warps combine them in a fixed
+      //   order through shared memory into per-(sample, group) partial sums of this CTA tile.  When a sample spans
+      //   several CTA tiles (32x32 maps: four 256-row tiles on two CTA pairs) the partials are exchanged through L2:
+      //   each CTA stores its 32 pairs, publishes an epoch flag (st.release) and spins on the flags of the sample's
+      //   other tiles.  Those CTAs are co-resident (persistent grid, one CTA per SM, consecutive pair tiles go to
+      //   consecutive pairs) and never wait on a LATER tile, so the wait cannot deadlock.  Totals are summed in tile
+      //   order: bit-reproducible, no atomics.
+      // Pass 2: the accumulators are read again, normalised, SiLU-activated and stored as bf16.  The second TMEM stage
+      //   keeps the MMAs of the next tile running underneath.
+      float2* s_mr = (float2*)(smem + TC_GN_OFF);                   // [unit][group]
+      const float* s_gamma = (const float*)(smem + TC_GN_OFF + 2048);
+      const float* s_beta = s_gamma + TC_GN_MAX_COUT;
+      float2* s_scr = (float2*)(smem + TC_GN_OFF + 4096);           // [chunk][block][granule]
+      float2* s_tab = (float2*)(smem + TC_GN_OFF + 8192);           // [unit <= 2][channel]: (scale, shift) of pass 2
+      const int n_mine = chunks_per_half > sub ? ((chunks_per_half - sub + 1) >> 1) * kMH : 0;
+      const bool sum_halves = kMH == 2 && p.gn_R == 256;            // both 128-row halves belong to the same sample
+      const int rows_blk = sum_halves ? 64 : p.gn_seg;              // tile rows one scratch block stands for
+      const int n_blk = sum_halves ? 4 : (128 * kMH) / rows_blk;    // scratch blocks per chunk (<= 8)
+      const int bpu = sum_halves ? 4 : p.gn_R / rows_blk;           // blocks per sample ("unit") of the tile
+      const int n_units = n_blk / bpu;
+      const int gpg = p.gn_cpg >> 2;                                // granules per group
+      const int et = (warp - 2) * 32 + lane;                        // epilogue thread 0..255
+      const unsigned epoch = p.gn_ctas > 1 ? *p.gn_epoch : 0u;
+      for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+        const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
+        const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+        const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
+        // ---------------- pass 1: statistics ----------------
+        float run_s[8], run_q[8];
+        for (int k = 0; k < n_mine; ++k) {
+          const int half = kMH == 2 ? (k & 1) : 0;
+          const int ci = sub + 2 * (kMH == 2 ? (k >> 1) : k);
+          const EpiRow rr = epi_pick(row0, row1, half != 0);
+          uint32_t v[32];
+          tmem_ld32(t_addr + (uint32_t)(half * p.block_n + (ci << 5)), v);
+          tmem_ld_wait();
+          float f[32];
+          epi_bias_emb(p, rr, ci << 5, v, s_bias_addr, f);
+          if (!rr.valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          epi_granules(f, run_s, run_q, sum_halves && half == 1);
+          if (sum_halves && half == 0) continue;
+          float2* sc = s_scr + ci * 64;
+          if (p.gn_seg == 32) {
+            epi_granule_reduce<true>(run_s, run_q, lane);
+            const int blk = sum_halves ? quad : half * 4 + quad;
+            if ((lane & 3) == 0) sc[blk * 8 + (lane >> 2)] = make_float2(run_s[0], run_q[0]);
+          } else {
+            epi_granule_reduce<false>(run_s, run_q, lane);
+            if ((lane & 1) == 0) sc[(quad * 2 + (lane >> 4)) * 8 + ((lane >> 1) & 7)] = make_float2(run_s[0], run_q[0]);
+          }
+        }
+        named_bar_sync(5, 32 * TC_EPI_WARPS);
+        // ---------------- per-(sample, group) statistics of the tile ----------------
+        if (et < n_units * 32) {
+          const int u = et >> 5, g = et & 31;                   // a warp per unit, a lane per group
+          const int g0 = g * gpg;                                // first granule of the group; groups never straddle chunks
+          const float2* sc = s_scr + (g0 >> 3) * 64 + (g0 & 7);
+          float ts = 0.f, tq = 0.f;
+          for (int b = 0; b < bpu; ++b)
+            for (int j = 0; j < gpg; ++j) { const float2 t2 = sc[(u * bpu + b) * 8 + j]; ts += t2.x; tq += t2.y; }
+          if (p.gn_ctas > 1) {
+            // u == 0: the whole CTA tile lies inside sample n; `my` = its index among the sample's tiles.  Every partial
+            // travels as two 8-byte words {value, epoch}: an aligned 8-byte store is single-copy atomic, so the word itself
+            // says when it is valid - no fence, no release / acquire pair (and no L1 invalidation) on either side.
+            const int n = tc.tb * p.bn;
+            const int my = (tc.th * p.bh * p.W) / (128 * kMH);
+            if (n < p.B) {
+              uint2* ex = p.gn_exch + ((long long)n * p.gn_ctas) * 64;
+              st_relaxed_gpu_v2(ex + (my * 32 + g) * 2, __float_as_uint(ts), epoch);
+              st_relaxed_gpu_v2(ex + (my * 32 + g) * 2 + 1, __float_as_uint(tq), epoch);
+              ts = 0.f; tq = 0.f;
+              for (int j = 0; j < p.gn_ctas; ++j) {        // fixed order over the sample's tiles: bit-reproducible
+                uint2 a, b;
+                do { a = ld_relaxed_gpu_v2(ex + (j * 32 + g) * 2); } while (a.y != epoch);
+                do { b = ld_relaxed_gpu_v2(ex + (j * 32 + g) * 2 + 1); } while (b.y != epoch);
+                ts += __uint_as_float(a.x); tq += __uint_as_float(b.x);
+              }
+            }
+          }
+          const float inv_n = 1.0f / (float)(p.gn_cpg * p.gn_hw);
+          const float mean = ts * inv_n;
+          const float var = fmaxf(tq * inv_n - mean * mean, 0.f);
+          s_mr[u * 32 + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
+        }
+        named_bar_sync(5, 32 * TC_EPI_WARPS);
+        const float hs = p.gn_silu ? 0.5f : 1.0f;                   // silu(y) = h * tanh(h) + h with h = y / 2
+        const bool table = n_units <= 2;
+        if (table) {
+          // per-(sample, channel) scale / shift with everything folded in: y = acc * sc + sh,
+          //   sc = rstd * gamma * hs,  sh = ((bias + emb - mean) * rstd * gamma + beta) * hs
+          for (int i = et; i < n_units * p.Cout; i += 32 * TC_EPI_WARPS) {
+            const int u = i >= p.Cout ? 1 : 0, c = i - u * p.Cout;
+            const float2 m = s_mr[u * 32 + (c >> p.gn_cpg_log2)];
+            float add = s_bias[c];
+            const int n = epi_decode_row(p, tc, u * p.gn_R).n;
+            if (p.emb && n < p.B) add += __ldg(p.emb + (long long)p.emb_row[n] * p.emb_stride + c);
+            const float sc = m.y * s_gamma[c] * hs;
+            s_tab[u * TC_GN_MAX_COUT + c] = make_float2(sc, fmaf(add - m.x, sc, s_beta[c] * hs));
+          }
+          named_bar_sync(5, 32 * TC_EPI_WARPS);
+        }
+        // ---------------- pass 2: normalise, activate, store ----------------
+        for (int k = 0; k < n_mine; ++k) {
+          const int half = kMH == 2 ? (k & 1) : 0;
+          const int c0 = (sub + 2 * (kMH == 2 ? (k >> 1) : k)) << 5;
+          const EpiRow rr = epi_pick(row0, row1, half != 0);
+          uint32_t v[32];
+          tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
+          tmem_ld_wait();
+          if (k == n_mine - 1) {       // last read of this accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+          }
+          const int trow = half * 128 + quad * 32 + lane;
+          float f[32];
+          if (table) {
+            const float2* tb = s_tab + (trow >> p.gn_R_log2) * TC_GN_MAX_COUT + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float4 t4 = *(const float4*)(tb + j);
+              f[j] = fmaf(__uint_as_float(v[j]), t4.x, t4.y); f[j + 1] = fmaf(__uint_as_float(v[j + 1]), t4.z, t4.w);
+            }
+          } else {
+            epi_bias_emb(p, rr, c0, v, s_bias_addr, f);
+            const float2* mr = s_mr + (trow >> p.gn_R_log2) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float2 m = mr[(c0 + j) >> p.gn_cpg_log2];       // 4 | cpg: the four channels share a group
+              const float4 ga = *(const float4*)(s_gamma + c0 + j), be = *(const float4*)(s_beta + c0 + j);
+              const float r = m.y * hs;
+              f[j] = fmaf((f[j] - m.x) * r, ga.x, be.x * hs); f[j + 1] = fmaf((f[j + 1] - m.x) * r, ga.y, be.y * hs);
+              f[j + 2] = fmaf((f[j + 2] - m.x) * r, ga.z, be.z * hs); f[j + 3] = fmaf((f[j + 3] - m.x) * r, ga.w, be.w * hs);
+            }
+          }
+          if (p.gn_silu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = silu_from_half(f[j]);
+          }
+          if (rr.valid) epi_store_bf16(p, rr, c0, f);
+        }
+        if (n_mine == 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else if (p.tma_store) {
       // ---- staged epilogue: each group of four warps (one per TMEM lane quadrant) owns two 16 KB staging boxes.  A unit
       // is one 128-row x 64-channel box of the output: two 32-column TMEM chunks per thread, written as bf16 into the
       // swizzled box, then ONE thread hands the box to TMA (full 128-byte lines, no per-lane sector stores).
@@ -721,27 +892,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           uint4 res[2][4];
           epi_load_res(p, rr, lane, nt * p.block_n + (cb << 6), res[0]);
           epi_load_res(p, rr, lane, nt * p.block_n + (cb << 6) + 32, res[1]);
-          // statistics scratch [unit parity][32-column chunk][quadrant][granule]: written before the unit's barrier, read
-          // after it; the parity keeps a fast warp's next unit out of the buffer a slow warp is still reading
-          float2* scr = (float2*)(smem + TC_STAT_OFF) + (sub * 2 + (int)(n_store & 1u)) * 64;
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
             const int c0 = (cb << 6) + (it << 5);
             uint32_t v[32];
             tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
             tmem_ld_wait();
-            float f[32];
-            epi_finish_smem(p, rr, nt * p.block_n + c0, v, res[it], s_bias_addr, buf + (uint32_t)row * 128u, row, it * 4, f);
-            if (p.stat_out) {
-              float gs[8], gq[8];
-              if (!rr.valid) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = 0.f;
-              }
-              epi_granules(f, gs, gq, false);
-              epi_granule_reduce<true>(gs, gq, lane);
-              if ((lane & 3) == 0) scr[(it * 4 + quad) * 8 + (lane >> 2)] = make_float2(gs[0], gq[0]);
-            }
+            epi_finish_smem(p, rr, nt * p.block_n + c0, v, res[it], s_bias_addr, buf + (uint32_t)row * 128u, row, it * 4);
           }
           fence_proxy_async();                      // generic-proxy writes of this thread -> visible to the TMA engine
           if (issuer) bulk_wait_group_read0();      // the box stored one unit ago has been read: free after the barrier
@@ -751,18 +908,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                          tc.tw * p.bw, tc.th * p.bh + half * p.st_dh, tc.tb * p.bn + half * p.st_dn);
             bulk_commit_group();
           }
-          if (p.stat_out) {
-            // one partial per (unit of stat_R rows, granule): the quadrants of a unit are summed in a fixed order
-            const int bpu = p.stat_R >> 5, n_out = (4 / bpu) * 16;
-            if (row < n_out) {
-              const int u = row >> 4, gg = row & 15;
-              float ts = 0.f, tq = 0.f;
-              for (int b = 0; b < bpu; ++b) { const float2 t2 = scr[((gg >> 3) * 4 + u * bpu + b) * 8 + (gg & 7)]; ts += t2.x; tq += t2.y; }
-              int sn, sp;
-              epi_stat_unit(p, tc, half * 128 + u * p.stat_R, &sn, &sp);
-              if (sn < p.B) p.stat_out[((long long)sn * p.stat_P + sp) * (p.Cout >> 2) + ((nt * p.block_n + (cb << 6)) >> 2) + gg] = make_float2(ts, tq);
-            }
-          }
           ++n_store;
         }
         tc_fence_before();
@@ -771,12 +916,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (issuer) bulk_wait_group0();               // shared memory stays valid until every box has left
-    } else {
-    // items of this warp, chunk-major: 32-column chunks sub, sub + 2, ...; for each, the kMH 128-row halves - so the
-    // statistics of a chunk are complete (and can be combined across the four quadrant warps) after its last half
-    const int n_mine = chunks_per_half > sub ? ((chunks_per_half - sub + 1) >> 1) * kMH : 0;
-    uint32_t n_stat = 0;
-    float2* scr0 = (float2*)(s_bias + TC_STAT_BIAS_OFF) + sub * 128;     // [chunk parity][block of stat_seg rows (<= 8)][8 granules]
+    } else
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
@@ -788,75 +928,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (kMH == 2) epi_prefetch_res(p, epi_decode_row(p, tn, 128 + quad * 32 + lane), tn.nt * p.block_n, p.block_n);
       }
       uint4 res_cur[4], res_nxt[4];
-      if (n_mine > 0) epi_load_res(p, row0, lane, nt * p.block_n + (sub << 5), res_nxt);
+      if (sub < n_items) {
+        const int half = (kMH == 2 && sub >= chunks_per_half) ? 1 : 0;
+        epi_load_res(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + ((sub - half * chunks_per_half) << 5), res_nxt);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
-      float run_s[8], run_q[8];
-      for (int k = 0; k < n_mine; ++k) {
-        const int half = kMH == 2 ? (k & 1) : 0;
-        const int c0 = (sub + 2 * (kMH == 2 ? (k >> 1) : k)) << 5;
+      for (int item = sub; item < n_items; item += TC_EPI_WARPS / 4) {
+        const int half = (kMH == 2 && item >= chunks_per_half) ? 1 : 0;
+        const int c0 = (item - half * chunks_per_half) << 5;
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(half * p.block_n + c0), v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
-        if (k + 1 < n_mine) {
-          const int nh = kMH == 2 ? ((k + 1) & 1) : 0;
-          const int nc0 = (sub + 2 * (kMH == 2 ? ((k + 1) >> 1) : (k + 1))) << 5;
-          epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + nc0, res_nxt);
+        const int nxt = item + TC_EPI_WARPS / 4;
+        if (nxt < n_items) {
+          const int nh = (kMH == 2 && nxt >= chunks_per_half) ? 1 : 0;
+          epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nt * p.block_n + ((nxt - nh * chunks_per_half) << 5), res_nxt);
         }
         tmem_ld_wait();
-        if (k == n_mine - 1) {       // last read of this accumulator stage: hand it back before the stores and the statistics
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-        }
-        const EpiRow rr = epi_pick(row0, row1, half != 0);
-        float f[32];
-        epi_finish(p, rr, lane, nt * p.block_n + c0, v, res_cur, s_bias_addr, f);
-        if (p.stat_out) {
-          if (!rr.valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = 0.f;
-          }
-          const bool acc_halves = kMH == 2 && p.stat_sum_halves && half == 1;
-          epi_granules(f, run_s, run_q, acc_halves);
-          float2* scr = scr0 + (n_stat & 1u) * 64;       // parity: the next chunk never touches the buffer being combined
-          if (!(kMH == 2 && p.stat_sum_halves && half == 0)) {
-            if (p.stat_seg == 32) {
-              epi_granule_reduce<true>(run_s, run_q, lane);
-              const int blk = p.stat_sum_halves ? quad : half * 4 + quad;
-              if ((lane & 3) == 0) scr[blk * 8 + (lane >> 2)] = make_float2(run_s[0], run_q[0]);
-            } else {                 // 16 pixels per sample (kMH = 1): each half-warp is a sample
-              epi_granule_reduce<false>(run_s, run_q, lane);
-              if ((lane & 1) == 0) scr[(quad * 2 + (lane >> 4)) * 8 + ((lane >> 1) & 7)] = make_float2(run_s[0], run_q[0]);
-            }
-          }
-          if (half == kMH - 1) {
-            ++n_stat;
-            named_bar_sync(3 + sub, 128);
-            const int rows_blk = p.stat_sum_halves ? 64 : p.stat_seg;      // tile rows one scratch block stands for
-            const int bpu = p.stat_sum_halves ? 4 : p.stat_R / rows_blk;   // blocks per partial
-            const int n_blk = p.stat_sum_halves ? 4 : (128 * kMH) / rows_blk;
-            const int o = quad * 32 + lane;
-            if (o < (n_blk / bpu) * 8) {
-              const int u = o >> 3, gi = o & 7;
-              float ts = 0.f, tq = 0.f;
-              for (int b = 0; b < bpu; ++b) { const float2 t2 = scr[(u * bpu + b) * 8 + gi]; ts += t2.x; tq += t2.y; }
-              int sn, sp;
-              epi_stat_unit(p, tc, u * p.stat_R, &sn, &sp);
-              if (sn < p.B) p.stat_out[((long long)sn * p.stat_P + sp) * (p.Cout >> 2) + ((nt * p.block_n + c0) >> 2) + gi] = make_float2(ts, tq);
-            }
-          }
-        }
+        epi_finish(p, epi_pick(row0, row1, half != 0), lane, nt * p.block_n + c0, v, res_cur, s_bias_addr);
       }
-      if (n_mine == 0) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // report to the leader
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
     }
   }
 
@@ -885,12 +982,12 @@ struct TcConvPlan {
   int st_bh = 0, st_bn = 0, st_dh = 0, st_dn = 0;   // store box (128 rows) and the origin shift of the second half
   int ring_bytes = TC_RING_BYTES;
   bool b_stat = false;          // weights resident in shared memory across the M tiles of a pair (n_b == total_k)
+  // fused GroupNorm epilogue (conv_tc2_kernel<.., true>)
+  bool gn = false; int gn_R = 0, gn_seg = 32, gn_ctas = 1, gn_cpg = 0;
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
 };
-
-static bool stats_geometry(const TcConvPlan* pl, int* R_out, int* seg_out, int* sum_halves_out);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -907,8 +1004,10 @@ static int get_encode(Engine& e) {
   return 0;
 }
 
-static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 static bool env_off(const char* name) { const char* v = getenv(name); return v && v[0] == '1'; }
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 static int pick_block_n(int Cout) {
   for (int n : {256, 192, 128, 96, 64, 32})
@@ -999,10 +1098,34 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
     if (pl->pair && !op.out_is_output && !op.out_f32 && !op.ups && pl->block_n % 64 == 0 && Cout % 64 == 0 && tk_all <= max_k &&
         pl->valid_rows == rows && pl->bw == Wg && halves_ok && !env_off("CFM_DISABLE_TC_TMA_STORE")) {
       pl->tma_store = true;
-      pl->ring_bytes = TC_STAT_OFF;          // staging boxes + statistics scratch sit above the rings
+      pl->ring_bytes = TC_STAGE_OFF;
       if (pl->mh == 1) { pl->st_bh = pl->bh; pl->st_bn = pl->bn; }
       else if (pl->bn % 2 == 0) { pl->st_bh = pl->bh; pl->st_bn = pl->bn / 2; pl->st_dn = pl->bn / 2; }
       else { pl->st_bh = pl->bh / 2; pl->st_bn = 1; pl->st_dh = pl->bh / 2; }
+    }
+  }
+  // GroupNorm of the output applied in the epilogue (requested by the plan for a ResBlock's first conv): the CTA tile must
+  // hold whole samples or a whole number of tiles must make up a sample, every warp's rows (or half-warp's: 4x4 maps) must
+  // lie in one sample, one N tile must span all channels and a group must be 4, 8, 16 or 32 channels.
+  // the two-pass epilogue holds an accumulator stage ~2x longer: it only pays where the K loop of a tile is long enough to
+  // cover it (measured: wins from 36 K-iterations, loses at 18)
+  static const int gn_min_k = [] { const char* v = getenv("CFM_TC_GN_MIN_K"); return v ? atoi(v) : 0; }();
+  op.gn_fused = false;
+  if (op.gn_request && pl->pair && !pl->tma_store && !op.ups && !op.out_is_output && !op.out_f32 && op.res0 < 0 && Cout == op.Cout &&
+      pl->block_n == Cout && Cout <= TC_GN_MAX_COUT && pl->valid_rows == rows && pl->bw == Wg && !env_off("CFM_DISABLE_TC_GN") &&
+      eks * eks * (Cin / kc) + op.Cskip / kc >= gn_min_k) {
+    const int cpg = Cout / 32, HW = Hg * Wg;
+    const bool cpg_ok = cpg >= 4 && pow2(cpg) && cpg <= 32;
+    int R = 0, seg = 32, ctas = 1;
+    if (HW >= rows) { if (HW % rows == 0) { R = rows; ctas = HW / rows; } }
+    else if (rows % HW == 0 && pow2(HW)) {
+      R = HW;
+      if (HW % 32) { if (HW == 16 && pl->mh == 1) seg = 16; else R = 0; }
+    }
+    if (cpg_ok && R > 0 && ctas <= 32 && (ctas == 1 || pl->bn == 1)) {
+      pl->gn = true; pl->gn_R = R; pl->gn_seg = seg; pl->gn_ctas = ctas; pl->gn_cpg = cpg;
+      pl->ring_bytes = TC_GN_OFF;
+      op.gn_fused = true; op.gn_ctas = ctas;
     }
   }
   // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous), fill its rows exactly and
@@ -1089,8 +1212,10 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   static DeviceOnce attr_set;
   if (attr_set.pending(e.device)) {
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+        cudaFuncSetAttribute(conv_tc2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
       e.err = "cudaFuncSetAttribute(conv_tc_kernel, smem) failed"; return CFM_ERR_CUDA;
     }
     attr_set.done(e.device);
@@ -1170,13 +1295,6 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.out = (bf16*)tensor_ptr(e, op.out, B);
   if (op.out_f32) p.out_f32 = (float*)tensor_ptr(e, op.out, B);
   if (op.out_is_output) { p.out_nchw = out_nchw; p.cout_real = op.Cout; }
-  if (op.emit_stats) {
-    int R, seg, sh;
-    if (!stats_geometry(pl, &R, &seg, &sh) || e.tensors[op.out].stat_off < 0 || !e.stats) { e.err = "internal: statistics requested from a conv that cannot emit them: " + op.name; return CFM_ERR_INTERNAL; }
-    p.stat_out = e.stats + (size_t)e.tensors[op.out].stat_off * B;
-    p.stat_P = e.tensors[op.out].stat_P; p.stat_R = R; p.stat_seg = seg; p.stat_sum_halves = sh;
-    p.d_stat_R.init(R);
-  }
   if (pl->pair) {
     const int tiles128 = p.tiles_w * p.tiles_h * p.tiles_b;
     const int pair_tiles = ((tiles128 + 1) / 2) * p.tiles_n * p.n_phase;
@@ -1187,7 +1305,18 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
       if (!p.b_stat) n_pairs = std::min(pair_tiles, e.sm_count / 2);
     }
     LaunchCfg lc(dim3(2 * n_pairs), dim3(TC_THREADS), TC_SMEM_BYTES, st, 2, pdl_enabled());
-    auto kern = pl->mh == 2 ? conv_tc2_kernel<2> : conv_tc2_kernel<1>;
+    auto kern = pl->mh == 2 ? (pl->gn ? conv_tc2_kernel<2, true> : conv_tc2_kernel<2, false>)
+                            : (pl->gn ? conv_tc2_kernel<1, true> : conv_tc2_kernel<1, false>);
+    if (pl->gn) {
+      p.gn_gamma = op.gamma; p.gn_beta = op.beta; p.gn_eps = 1e-5f; p.gn_cpg = pl->gn_cpg; p.gn_cpg_log2 = ilog2(pl->gn_cpg);
+      p.gn_R = pl->gn_R; p.gn_R_log2 = ilog2(pl->gn_R); p.gn_seg = pl->gn_seg; p.gn_ctas = pl->gn_ctas; p.gn_hw = pl->Hg * pl->Wg;
+      p.gn_silu = op.silu;
+      if (pl->gn_ctas > 1) {
+        if (!e.gn_exch || !e.gn_epoch || op.gn_exch_off < 0) { e.err = "internal: GroupNorm exchange buffers missing for " + op.name; return CFM_ERR_INTERNAL; }
+        p.gn_exch = e.gn_exch + (size_t)op.gn_exch_off * B * 64;
+        p.gn_epoch = e.gn_epoch;
+      }
+    }
     p.tma_store = pl->tma_store ? 1 : 0; p.st_dh = pl->st_dh; p.st_dn = pl->st_dn;
     cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, kern, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, it->second.out, p);
     if (ce != cudaSuccess) { e.err = std::string("conv_tc2_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
@@ -1198,31 +1327,6 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
   if (ce != cudaSuccess) { e.err = std::string("conv_tc_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
   return 0;
-}
-
-// GroupNorm statistics from the epilogue (pair kernel only): tiles of whole image rows without padding, and every group of
-// stat_seg consecutive tile rows inside one sample.  A partial covers R = min(HW, rows of the tile one warp group sums) rows.
-static bool stats_geometry(const TcConvPlan* pl, int* R_out, int* seg_out, int* sum_halves_out) {
-  if (!pl || !pl->pair || pl->cout_pad > TC_STAT_MAX_COUT) return false;
-  const int rows = 128 * pl->mh, HW = pl->Hg * pl->Wg;
-  if (pl->valid_rows != rows || pl->bw != pl->Wg) return false;
-  const int span = (pl->tma_store || pl->mh == 1) ? 128 : 256;     // staged epilogue: one 128-row half per unit
-  const int R = std::min(HW, span);
-  if (HW % R || span % R) return false;
-  if (R > 128 && rows % R) return false;
-  int seg;
-  if (R % 32 == 0) seg = 32;
-  else if (R == 16 && pl->mh == 1 && !pl->tma_store) seg = 16;
-  else return false;
-  *R_out = R; *seg_out = seg; *sum_halves_out = (R == 256) ? 1 : 0;
-  return true;
-}
-
-int tc_conv_stats_parts(const Engine& e, const Op& op) {
-  if (!e.bf16 || op.kind != OP_CONV || !op.tc || op.out_is_output || op.out_f32 || env_off("CFM_DISABLE_GN_STATS")) return 0;
-  int R, seg, sh;
-  if (!stats_geometry(op.tc, &R, &seg, &sh)) return 0;
-  return (op.tc->Hg * op.tc->Wg / R) * op.tc->n_phase;
 }
 
 double tc_conv_executed_flops(const Op& op) {

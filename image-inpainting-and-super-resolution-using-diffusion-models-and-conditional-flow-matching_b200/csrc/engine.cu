@@ -91,7 +91,7 @@ static int heads_for(const cfm_unet_config& c, int channels, bool upsample_side)
 static int add_conv(Engine& e, const std::string& name, const std::string& wname, int ks, int stride, int ups,
                     int src0, int src1, bool src_is_input, int Cin, int Hin, int Win, int Cout,
                     const std::string& skip_wname, int skip0, int skip1, int Cskip,
-                    int res0, int res1, int emb_off, int out, bool out_is_output) {
+                    int res0, int res1, int emb_off, int out, bool out_is_output, const std::string& gn_name = "") {
   Op op; op.kind = OP_CONV; op.name = name;
   op.ks = ks; op.stride = stride; op.ups = ups; op.src0 = src0; op.src1 = src1; op.src_is_input = src_is_input;
   op.Cin = Cin; op.Hin = Hin; op.Win = Win; op.Cout = Cout;
@@ -118,8 +118,23 @@ static int add_conv(Engine& e, const std::string& name, const std::string& wname
   if ((rc = upload(e, bias.data(), bias.size(), &op.bias))) return rc;
   op.flops = 2.0 * op.Hout * op.Wout * Cout * ((double)ks * ks * Cin + Cskip);
   if (e.bf16 && tc_conv_supported(e, op)) {
+    if (!gn_name.empty()) {     // ask the tensor-core kernel to apply the GroupNorm (+SiLU) that follows in its epilogue
+      const int64_t before = e.param_count;
+      const float *g = nullptr, *b2 = nullptr;
+      if ((rc = fetch(e, gn_name + ".weight", Cout, &g))) return rc;
+      if ((rc = fetch(e, gn_name + ".bias", Cout, &b2))) return rc;
+      if ((rc = upload(e, g, Cout, &op.gamma))) return rc;
+      if ((rc = upload(e, b2, Cout, &op.beta))) return rc;
+      op.gn_request = true; op.silu = 1;
+      e.param_count = before;   // counted when the GroupNorm is really folded in (below) or by add_gn
+    }
     if ((rc = tc_conv_prepare(e, op, w_oihw, ws_oi))) return rc;
     e.n_tc_convs++;
+    if (op.gn_fused) {
+      e.param_count += 2 * Cout;
+      op.name += "+" + gn_name.substr(gn_name.rfind("out_layers") == std::string::npos ? 0 : gn_name.rfind("out_layers"));
+      if (op.gn_ctas > 1) { op.gn_exch_off = e.gn_tiles_per_sample; e.gn_tiles_per_sample += op.gn_ctas; }
+    }
   }
   e.ops.push_back(op);
   return 0;
@@ -170,10 +185,15 @@ static int add_resblock(Engine& e, const std::string& p, Cur xa, Cur xb, int cou
   emb_pieces.push_back({p + ".emb_layers.1", ew});
   e.emb_total += ew;
   const int h1 = new_tensor(e, cout, H, W);
+  // out_layers.0/1 (GroupNorm + SiLU of h) is folded into this conv's epilogue when the tensor-core kernel can hold whole
+  // samples' statistics (no FiLM): h1 then already IS the normalised, activated tensor and no GroupNorm op is emitted
   if ((rc = add_conv(e, p + ".in_layers.2", p + ".in_layers.2", 3, 1, 0, conv_src, -1, false, cin, H, W, cout,
-                     "", -1, -1, 0, -1, -1, film ? -1 : emb_off, h1, false))) return rc;
-  const int a2 = new_tensor(e, cout, H, W);
-  if ((rc = add_gn(e, p + ".out_layers.0", p + ".out_layers.0", h1, -1, cout, 1, film, film ? emb_off : -1, a2))) return rc;
+                     "", -1, -1, 0, -1, -1, film ? -1 : emb_off, h1, false, film ? "" : p + ".out_layers.0"))) return rc;
+  int a2 = h1;
+  if (!e.ops.back().gn_fused) {
+    a2 = new_tensor(e, cout, H, W);
+    if ((rc = add_gn(e, p + ".out_layers.0", p + ".out_layers.0", h1, -1, cout, 1, film, film ? emb_off : -1, a2))) return rc;
+  }
   const int o = new_tensor(e, cout, H, W);
   if (cin != cout) {
     if ((rc = add_conv(e, p + ".out_layers.3", p + ".out_layers.3", 3, 1, 0, a2, -1, false, cout, H, W, cout,
@@ -408,29 +428,6 @@ static int build_plan(Engine& e) {
   e.flops_per_sample = 2.0 * ((double)mc * e.ted + (double)e.ted * e.ted + (double)e.emb_total * e.ted);
   for (auto& op : e.ops) e.flops_per_sample += op.flops;
 
-  // ---- GroupNorm statistics from the producing convs' epilogues: a GroupNorm whose every source is written by a conv that
-  // can emit per-channel partial sums becomes one streaming pass (no reduction of its own) ----
-  {
-    std::vector<int> producer(e.tensors.size(), -1);
-    for (int i = 0; i < (int)e.ops.size(); ++i) if (e.ops[i].out >= 0) producer[e.ops[i].out] = i;
-    for (Op& gn : e.ops) {
-      if (gn.kind != OP_GN || !e.bf16 || !gn_apply_supported(e, gn)) continue;
-      bool ok = true;
-      for (int id : {gn.src0, gn.src1})
-        if (id >= 0) ok = ok && producer[id] >= 0 && tc_conv_stats_parts(e, e.ops[producer[id]]) > 0 && e.tensors[id].C % 8 == 0;
-      if (!ok) continue;
-      gn.use_stats = true;
-      for (int id : {gn.src0, gn.src1}) {
-        if (id < 0 || e.tensors[id].stat_P > 0) continue;
-        Op& pr = e.ops[producer[id]];
-        pr.emit_stats = true;
-        e.tensors[id].stat_P = tc_conv_stats_parts(e, pr);
-        e.tensors[id].stat_off = e.stats_per_sample;
-        e.stats_per_sample += (long long)e.tensors[id].stat_P * (e.tensors[id].C / 4);   // one pair per granule of 4 channels
-      }
-    }
-  }
-
   // ---- liveness + first-fit arena assignment (per-sample element offsets, 64-element aligned) ----
   for (int i = 0; i < (int)e.ops.size(); ++i) {
     const Op& op = e.ops[i];
@@ -483,7 +480,7 @@ static void drop_graphs(Engine& e) {
 static int ensure_batch(Engine& e, int B) {
   if (B > e.arena_batch) {
     if (e.arena) { cudaFree(e.arena); e.arena = nullptr; }
-    if (e.stats) { cudaFree(e.stats); e.stats = nullptr; }
+    if (e.gn_exch) { cudaFree(e.gn_exch); e.gn_exch = nullptr; }
     tc_conv_release(e);   // tensor maps hold arena addresses
     attn_tc_release(e);
     attn_flash_release(e);
@@ -492,7 +489,11 @@ static int ensure_batch(Engine& e, int B) {
     drop_graphs(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
     CU_CHECK(e, cudaMalloc(&e.arena, bytes));
-    if (e.stats_per_sample > 0) CU_CHECK(e, cudaMalloc((void**)&e.stats, sizeof(float2) * (size_t)e.stats_per_sample * B));
+    if (e.gn_tiles_per_sample > 0) {
+      CU_CHECK(e, cudaMalloc((void**)&e.gn_exch, sizeof(uint2) * 64 * (size_t)e.gn_tiles_per_sample * B));
+      CU_CHECK(e, cudaMemset(e.gn_exch, 0, sizeof(uint2) * 64 * (size_t)e.gn_tiles_per_sample * B));      // epoch 0 = never written
+      if (!e.gn_epoch) { CU_CHECK(e, cudaMalloc((void**)&e.gn_epoch, sizeof(unsigned))); CU_CHECK(e, cudaMemset(e.gn_epoch, 0, sizeof(unsigned))); }
+    }
     e.arena_batch = B;
   }
   const int rows_needed = std::max(B, std::max(1, e.cfg.num_classes));
@@ -519,8 +520,9 @@ void* tensor_ptr(const Engine& e, int id, int B) {
 // rows of the embedding table: uniform t -> one row (or one per class); per-sample t -> one per sample
 __global__ void setup_rows_kernel(int B, int rows, int uniform, float t_scalar, const float* t_dev,
                                   const float* t_table, const int* step_counter,
-                                  const long long* y, float* t_rows, long long* label_idx, int* row_of_sample) {
+                                  const long long* y, float* t_rows, long long* label_idx, int* row_of_sample, unsigned* epoch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && epoch) *epoch += 1u;                   // one U-Net evaluation = one epoch of the fused-GroupNorm exchange flags
   if (t_table) t_scalar = t_table[*step_counter];      // sampler loops: time of the current step lives on the device
   if (i < rows) {
     t_rows[i] = uniform ? t_scalar : t_dev[i];
@@ -579,12 +581,6 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_GN: {
-        if (op.use_stats) {                                 // statistics already written by the producing convs
-          int rc = gn_apply_launch(e, op, B, st);
-          if (rc) return rc;
-          e.launches++;
-          break;
-        }
         if (e.bf16 && gn_stream_supported(e, op)) {       // large maps: persistent TMA-pipelined kernel
           int rc = gn_stream_launch(e, op, B, st);
           if (rc) return rc;
@@ -707,7 +703,7 @@ static int forward_impl(Engine& e, int B, const float* x, const float* cond, con
   const int uniform = t_dev == nullptr;
   const int rows = uniform ? std::max(1, e.cfg.num_classes) : B;
   const int n = std::max(rows, B);
-  setup_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, rows, uniform, t_scalar, t_dev, t_table, step_counter, (const long long*)y, e.t_rows, e.label_idx, e.row_of_sample);
+  setup_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(B, rows, uniform, t_scalar, t_dev, t_table, step_counter, (const long long*)y, e.t_rows, e.label_idx, e.row_of_sample, e.gn_epoch);
   time_hidden_kernel<<<dim3(rows, (e.ted + 7) / 8), 256, sizeof(float) * e.cfg.model_channels, st>>>(e.t_rows, e.cfg.model_channels, e.ted, e.w_t1, e.b_t1, e.hidden);
   linear_rows_kernel<<<dim3((e.ted + 7) / 8, rows), 256, 0, st>>>(e.hidden, e.ted, e.w_t2, e.b_t2, e.ted, drop_labels ? nullptr : e.label_emb, e.label_idx, 1, e.semb);
   linear_rows_kernel<<<dim3((e.emb_total + 7) / 8, rows), 256, 0, st>>>(e.semb, e.ted, e.w_emb_cat, e.b_emb_cat, e.emb_total, nullptr, nullptr, 0, e.emb_out);
@@ -849,7 +845,7 @@ void cfm_engine_destroy(cfm_engine* h) {
     if (p) cudaFree(p);
   for (void* p : e.owned) cudaFree(p);
   for (cudaEvent_t ev : e.prof_events) cudaEventDestroy(ev);
-  for (void* p : {(void*)e.arena, (void*)e.stats, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf, (void*)e.v2_buf})
+  for (void* p : {(void*)e.arena, (void*)e.gn_exch, (void*)e.gn_epoch, (void*)e.t_rows, (void*)e.hidden, (void*)e.semb, (void*)e.emb_out, (void*)e.label_idx, (void*)e.row_of_sample, (void*)e.v_buf, (void*)e.v2_buf})
     if (p) cudaFree(p);
   delete h;
 }

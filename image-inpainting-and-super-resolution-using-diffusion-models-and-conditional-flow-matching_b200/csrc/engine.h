@@ -18,10 +18,6 @@ struct TensorDesc {
   int C = 0, H = 0, W = 0;
   long long off = -1;
   int first_use = -1, last_use = -1;
-  // GroupNorm statistics of this tensor, written by the conv that produces it (conv_tc.cu) when a GroupNorm reads it:
-  // stat_P partial (sum, sum of squares) pairs per (sample, channel); stat_off = per-sample float2 offset in Engine::stats
-  int stat_P = 0;
-  long long stat_off = -1;
   long long elems() const { return (long long)C * H * W; }
 };
 
@@ -51,8 +47,11 @@ struct Op {
   TcConvPlan* tc = nullptr;
   AttnQkvPlan* fq = nullptr;   // attention op that takes the GroupNorm output and projects q, k, v itself
   double flops = 0;        // 2*MAC per sample
-  bool emit_stats = false; // conv: the epilogue also writes the GroupNorm statistics of `out`
-  bool use_stats = false;  // groupnorm: statistics come from the producers' epilogues -> one streaming pass (gn_apply_kernel)
+  // conv with the following GroupNorm (+SiLU) applied in its epilogue (ResBlock conv1 + out_layers.0; conv_tc.cu, kGN):
+  // gn_request is set by the plan (gamma / beta / silu then describe that GroupNorm), gn_fused by tc_conv_prepare.
+  bool gn_request = false, gn_fused = false;
+  int gn_ctas = 1;              // CTA tiles per sample; > 1: partial sums are exchanged through Engine::gn_exch
+  long long gn_exch_off = -1;   // offset of this op's exchange slots, in tiles per sample
 };
 
 struct Engine {
@@ -66,7 +65,8 @@ struct Engine {
   std::vector<Op> ops;
   long long arena_elems_per_sample = 0;
   void* arena = nullptr; int arena_batch = 0;
-  float2* stats = nullptr; long long stats_per_sample = 0;   // GroupNorm partial statistics, [B * stats_per_sample] float2
+  // fused GroupNorm epilogues whose samples span several CTA tiles: per-(sample, tile) partial sums and epoch flags
+  uint2* gn_exch = nullptr; unsigned* gn_epoch = nullptr; long long gn_tiles_per_sample = 0;
   // embedding path
   int ted = 0, emb_total = 0;
   float *w_t1 = nullptr, *b_t1 = nullptr, *w_t2 = nullptr, *b_t2 = nullptr, *label_emb = nullptr;
@@ -129,11 +129,7 @@ bool tc_conv_supported(const Engine& e, const Op& op);
 int  tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w_main_oihw, const std::vector<float>& w_skip_oi);
 int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_nchw = nullptr);
 void tc_conv_release(Engine& e);
-double tc_conv_executed_flops(const Op& op);
-int  tc_conv_stats_parts(const Engine& e, const Op& op);   // partial sums per sample the epilogue can emit for op.out (0: it cannot)
-// GroupNorm as one streaming pass over statistics produced by the convs (kernels_bf16.cu)
-bool gn_apply_supported(const Engine& e, const Op& op);
-int  gn_apply_launch(Engine& e, const Op& op, int B, cudaStream_t st);   // 2*MAC per sample the tcgen05 kernel issues (padding and folding included)
+double tc_conv_executed_flops(const Op& op);   // 2*MAC per sample the tcgen05 kernel issues (padding and folding included)
 // bf16 fast kernels (kernels_bf16.cu)
 int  gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 // attn_tc.cu

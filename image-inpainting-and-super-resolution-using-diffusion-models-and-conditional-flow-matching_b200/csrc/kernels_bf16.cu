@@ -279,156 +279,6 @@ int gn_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm32 as ONE streaming pass.  The per-(sample, channel) sums and sums of squares were written by the epilogues
-// of the convs that produced the source tensors (conv_tc.cu: stat_P partials per channel, fixed slots, no atomics), so
-// this kernel has no reduction over pixels: a CTA sums the partials of its sample in index order, folds the channels
-// of each group (which may straddle the two sources of a concat: 384 = 256 + 128 channels, 12 per group), turns them
-// into a per-channel scale / shift (gamma, beta, FiLM and the 1/2 of the one-MUFU SiLU folded in) and then streams
-// its pixels: 16-byte loads, 8 FMAs + 8 tanh.approx, 16-byte stores, no shared-memory staging of the data, no barrier
-// after the prologue.  Algorithmic bytes = 4 B per element; bound = HBM.
-// ------------------------------------------------------------------------------------------------
-struct GnApplyArgs {
-  const bf16* src0; const bf16* src1; int C0, C1;
-  const float2* part0; const float2* part1; int P0, P1;   // [B][P][C_src / 4] (sum, sum of squares) per granule of 4 channels
-  int HW, cpg, ppc, chunks;                               // pixels per CTA, CTAs per sample
-  const float* gamma; const float* beta; float eps; int silu;
-  const float* film; int film_stride; const int* film_row;
-  bf16* out;
-};
-constexpr int GNA_MAX_C = 1024;
-constexpr int GNA_UNROLL = 4;
-
-__global__ void __launch_bounds__(512) gn_apply_kernel(GnApplyArgs a) {
-  __shared__ float2 s_gran[GNA_MAX_C / 4];
-  __shared__ float s_mean[32], s_rstd[32];
-  const int T = blockDim.x, tid = threadIdx.x;
-  const int C = a.C0 + a.C1;
-  const int vpp = C >> 3;                               // T % vpp == 0: every thread keeps one 8-channel slot
-  const int q = tid % vpp, cq = q * 8;
-  pdl_launch_dependents();
-  // affine parameters of this thread's 8 channels: weights, not written by a predecessor -> loaded before the wait
-  float ga[8], be[8];
-  {
-    const float4 g0 = __ldg((const float4*)(a.gamma + cq)), g1 = __ldg((const float4*)(a.gamma + cq + 4));
-    const float4 b0 = __ldg((const float4*)(a.beta + cq)), b1 = __ldg((const float4*)(a.beta + cq + 4));
-    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
-    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
-  }
-  pdl_wait();
-  const int b = blockIdx.x / a.chunks, chunk = blockIdx.x - b * a.chunks;
-  // 1. per-granule totals of this sample: the partials of a granule are summed in index order (8 loads in flight)
-  const int nG0 = a.C0 >> 2, nG = C >> 2;
-  for (int g = tid; g < nG; g += T) {
-    const float2* pp; int P, nGs;
-    if (g < nG0) { pp = a.part0 + (long long)b * a.P0 * nG0 + g; P = a.P0; nGs = nG0; }
-    else { nGs = nG - nG0; pp = a.part1 + (long long)b * a.P1 * nGs + (g - nG0); P = a.P1; }
-    float ts = 0.f, tq = 0.f;
-    for (int i0 = 0; i0 < P; i0 += 8) {
-      float2 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (i0 + i < P) ? __ldg(pp + (long long)(i0 + i) * nGs) : make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { ts += v[i].x; tq += v[i].y; }
-    }
-    s_gran[g] = make_float2(ts, tq);
-  }
-  __syncthreads();
-  // 2. the 32 groups: cpg / 4 granules each (a group may straddle the two sources of a concat)
-  if (tid < 32) {
-    const int gpg = a.cpg >> 2;
-    float gs = 0.f, gq = 0.f;
-    for (int j = 0; j < gpg; ++j) { const float2 v = s_gran[tid * gpg + j]; gs += v.x; gq += v.y; }
-    const float inv_n = 1.0f / (float)(a.cpg * a.HW);
-    const float mean = gs * inv_n;
-    const float var = fmaxf(gq * inv_n - mean * mean, 0.f);
-    s_mean[tid] = mean; s_rstd[tid] = rsqrtf(var + a.eps);
-  }
-  __syncthreads();
-  // 3. scale / shift of this thread's 8 channels (gamma, beta, FiLM and the 1/2 of the one-MUFU SiLU folded in)
-  float sc8[8], sh8[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cq + j, gi = c / a.cpg;
-    float sc_ = s_rstd[gi] * ga[j];
-    float sh_ = be[j] - s_mean[gi] * sc_;
-    if (a.film) {
-      const float* f = a.film + (long long)a.film_row[b] * a.film_stride;
-      const float m = 1.0f + f[c];
-      sc_ *= m; sh_ = sh_ * m + f[C + c];
-    }
-    if (a.silu) { sc_ *= 0.5f; sh_ *= 0.5f; }          // silu(y) = h * tanh(h) + h with h = y / 2
-    sc8[j] = sc_; sh8[j] = sh_;
-  }
-  const bf16* sp; int sC, sc;
-  if (cq < a.C0) { sp = a.src0; sC = a.C0; sc = cq; } else { sp = a.src1; sC = a.C1; sc = cq - a.C0; }
-  const int pstep = T / vpp;
-  const int p_begin = chunk * a.ppc, p_end = min(a.HW, p_begin + a.ppc);
-  const long long pix0 = (long long)b * a.HW;
-  for (int pb = p_begin + tid / vpp; pb < p_end; pb += pstep * GNA_UNROLL) {
-    uint4 r[GNA_UNROLL];
-#pragma unroll
-    for (int u = 0; u < GNA_UNROLL; ++u) {
-      const int px = pb + u * pstep;
-      if (px < p_end) r[u] = __ldg((const uint4*)(sp + (pix0 + px) * sC + sc));
-    }
-#pragma unroll
-    for (int u = 0; u < GNA_UNROLL; ++u) {
-      const int px = pb + u * pstep;
-      if (px >= p_end) continue;
-      const __nv_bfloat162* h2 = (const __nv_bfloat162*)&r[u];
-      uint4 o4;
-      __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h2[j]);
-        float y0 = fmaf(f.x, sc8[2 * j], sh8[2 * j]), y1 = fmaf(f.y, sc8[2 * j + 1], sh8[2 * j + 1]);
-        if (a.silu) { y0 = silu_from_half(y0); y1 = silu_from_half(y1); }
-        o2[j] = __floats2bfloat162_rn(y0, y1);
-      }
-      *(uint4*)(a.out + (pix0 + px) * C + cq) = o4;
-    }
-  }
-}
-
-static int gn_apply_threads(int C) {
-  const int vpp = C / 8;
-  const int unit = 32 / gcd_i(32, vpp) * vpp;
-  if (C % 8 || C > GNA_MAX_C || unit > 512) return 0;
-  return std::max(unit, 256 / unit * unit);
-}
-
-bool gn_apply_supported(const Engine& e, const Op& op) {
-  if (!e.bf16 || op.kind != OP_GN) return false;
-  if ((op.Cin / 32) % 4) return false;                  // statistics come per granule of 4 channels: groups must be whole granules
-  if (e.tensors[op.src0].C % 8 || (op.src1 >= 0 && e.tensors[op.src1].C % 8)) return false;
-  return gn_apply_threads(op.Cin) > 0;
-}
-
-int gn_apply_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
-  GnApplyArgs a{};
-  const TensorDesc& t0 = e.tensors[op.src0];
-  a.src0 = (const bf16*)tensor_ptr(e, op.src0, B); a.C0 = t0.C;
-  a.part0 = e.stats + (size_t)t0.stat_off * B; a.P0 = t0.stat_P;
-  if (op.src1 >= 0) {
-    const TensorDesc& t1 = e.tensors[op.src1];
-    a.src1 = (const bf16*)tensor_ptr(e, op.src1, B); a.C1 = t1.C;
-    a.part1 = e.stats + (size_t)t1.stat_off * B; a.P1 = t1.stat_P;
-  }
-  a.HW = op.Hin * op.Win; a.cpg = op.Cin / 32;
-  const int T = gn_apply_threads(op.Cin);
-  const int pstep = T / (op.Cin / 8);
-  static const int vec_per_thread = [] { const char* v = getenv("CFM_GNA_VEC"); return v ? atoi(v) : 16; }();
-  a.ppc = std::min(a.HW, pstep * vec_per_thread);
-  a.chunks = (a.HW + a.ppc - 1) / a.ppc;
-  a.gamma = op.gamma; a.beta = op.beta; a.eps = 1e-5f; a.silu = op.silu;
-  if (op.film) { a.film = e.emb_out + op.emb_off; a.film_stride = e.emb_total; a.film_row = e.row_of_sample; }
-  a.out = (bf16*)tensor_ptr(e, op.out, B);
-  LaunchCfg lc(dim3((unsigned)(B * a.chunks)), dim3(T), 0, st, 1, pdl_enabled());
-  if (cudaLaunchKernelEx(&lc.cfg, gn_apply_kernel, a) != cudaSuccess) { e.err = "gn_apply_kernel launch failed"; return CFM_ERR_CUDA; }
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
 // nearest x2 upsample / 2x2 average pool, 8 channels (16 B) per thread
 // ------------------------------------------------------------------------------------------------
 __global__ void resample_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ out, int B, int Hin, int Win, int C, int up) {

@@ -268,12 +268,12 @@ def test_cifar_nfe_at_benchmarked_batch(pkg, cuda, B):
 
 
 @pytest.mark.parametrize("name,batch", [("cifar", 5), ("flowers_ddpm", 2), ("tiny_neworder", 7)])
-def test_groupnorm_statistics_from_conv_epilogues(pkg, cuda, monkeypatch, name, batch):
-    # default path: the convs' epilogues write per-channel partial sums and GroupNorm is one streaming pass
-    # (gn_apply_kernel); CFM_DISABLE_GN_STATS=1 keeps the self-contained GroupNorm kernel.  Same arithmetic up to the
-    # summation order of the statistics (fp32 accumulators before rounding vs the stored bf16 values): both must sit
-    # within the bf16 bar of the reference golden, and close to each other.  Concat-straddling groups (cifar 384 = 256 +
-    # 128), FiLM (flowers), 4x4 maps (16 pixels per sample) and ragged batches are all on this path.
+def test_groupnorm_folded_into_conv_epilogue(pkg, cuda, monkeypatch, name, batch):
+    # default path: a ResBlock's out_layers.0/1 (GroupNorm + SiLU) runs in the epilogue of its first conv (conv_tc2_kernel
+    # <.., true>: statistics from the fp32 accumulators, samples that span several CTA tiles exchange partial sums through
+    # L2); CFM_DISABLE_TC_GN=1 keeps the separate GroupNorm pass.  Both must sit within the bf16 bar of the reference
+    # golden and close to each other.  cifar covers 32x32 (4 tiles per sample), 16x16 (2), 8x8 and 4x4 maps (2 / 8 samples
+    # per tile); flowers uses FiLM and must NOT fold; batch position must not matter (ragged tail tiles included).
     cfg, _, _ = GOLDEN_CONFIGS[name]
     g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
     params = O.seeded_params(cfg, int(g["seed"]))
@@ -284,14 +284,22 @@ def test_groupnorm_statistics_from_conv_epilogues(pkg, cuda, monkeypatch, name, 
     m = build(pkg, cfg, params, "bf16", cuda)
     fused = m(x, t).cpu()
     names = [r["name"] for r in m.engine().profile_forward(x, 0.5, repeats=1)]
-    monkeypatch.setenv("CFM_DISABLE_GN_STATS", "1")
+    n_folded = sum("+out_layers.0" in n for n in names)
+    assert torch.equal(m(x, t).cpu(), fused)             # a second evaluation (next epoch of the exchange flags): same bits
+    monkeypatch.setenv("CFM_DISABLE_TC_GN", "1")
     m2 = build(pkg, cfg, params, "bf16", cuda)
     plain = m2(x, t).cpu()
-    monkeypatch.delenv("CFM_DISABLE_GN_STATS")
+    monkeypatch.delenv("CFM_DISABLE_TC_GN")
+    names2 = [r["name"] for r in m2.engine().profile_forward(x, 0.5, repeats=1)]
+    assert not any("+out_layers.0" in n for n in names2) and len(names2) == len(names) + n_folded
+    if name == "cifar":
+        assert n_folded == 22, names
+    if name == "flowers_ddpm":
+        assert n_folded == 0
     want = torch.from_numpy(g["out"])
     n = want.shape[0]
     r_f, r_p, d = rel_l2(fused[:n], want), rel_l2(plain[:n], want), rel_l2(fused, plain)
-    print(f"{name}: fused-statistics rel-L2 {r_f:.3e}, self-contained GroupNorm {r_p:.3e}, between them {d:.3e}")
+    print(f"{name}: {n_folded} GroupNorms folded; rel-L2 folded {r_f:.3e}, separate pass {r_p:.3e}, between them {d:.3e}")
     assert r_f < TOL["bf16"] and r_p < TOL["bf16"] and d < TOL["bf16"]
     for k in range(n, batch):                       # repeated golden rows: batch position must not matter
         assert torch.equal(fused[k], fused[k % n])
