@@ -9,10 +9,11 @@ from ._lib import EngineError, LIB_PATH
 from .engine import Engine, UNetConfig
 from .models import (UNetModel, UNetModelWrapper, InPaintModelWrapper, SuperResModelWrapper, create_model,
                      load_checkpoint, parameter_layout, default_channel_mult)
-from .integrators import NeuralODE, odeint, sample_euler, euler_time_grid, rk_combine, rk_error_sumsq
+from .integrators import NeuralODE, odeint, sample_euler, sample_sde, euler_time_grid, rk_combine, rk_error_sumsq
 from .diffusion import (DDPM, EpsModel, Amortized, Replacement, ReconstructionGuidance, InPainting, OutPainting,
                         HyperResolution, get_conditioning, get_likelihood, get_prior_sample_fn,
-                        get_conditional_sample_fn, downsample_images, extract)
+                        get_conditional_sample_fn, downsample_images, resize_bilinear, extract)
+from .fid import FIDStatistics, frechet_distance, compute_fid
 from .distributed import shard_range, sample_euler_sharded, gather_uint8, odeint_sharded
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -58,6 +58,7 @@ SIGNATURES = {
     "cfm_engine_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
     "cfm_engine_kernel_launches": (C.c_int32, [C.c_void_p]),
     "cfm_engine_tensor_core_convs": (C.c_int32, [C.c_void_p]),
+    "cfm_engine_cached_graphs": (C.c_int32, [C.c_void_p]),
     "cfm_engine_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cfm_engine_profile_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
@@ -82,6 +83,17 @@ SIGNATURES = {
     "cfm_make_box_condition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "cfm_quantize_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cfm_ddpm_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(DdpmTablesC), C.POINTER(DdpmOptionsC),
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p]),
+    "cfm_sde_em_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_uint64,
+                                  C.c_uint32, C.c_int64, C.c_void_p]),
+    "cfm_ddpm_em_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_double, C.c_void_p, C.c_uint64,
+                                   C.c_uint32, C.c_int64, C.c_void_p]),
+    "cfm_sample_sde": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float), C.c_int32, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "cfm_resize_bilinear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p]),
+    "cfm_fid_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

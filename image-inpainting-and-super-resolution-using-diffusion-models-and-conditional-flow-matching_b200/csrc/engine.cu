@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include "engine.h"
 #include "kernels_generic.cuh"
 #include "steps.cuh"
@@ -475,6 +476,8 @@ static size_t esize(const Engine& e) { return e.bf16 ? 2 : 4; }
 static void drop_graphs(Engine& e) {
   for (auto& kv : e.graphs) cudaGraphExecDestroy(kv.second);
   e.graphs.clear();
+  e.graph_nodes.clear();
+  e.graph_lru.clear();
 }
 
 static int ensure_batch(Engine& e, int B) {
@@ -742,6 +745,14 @@ static int ensure_sampler(Engine& e, long long n, long long n_cond, int B, int n
   if ((rc = grow(e, &e.dt_table, &e.dt_cap, (long long)std::max(n_steps, 1)))) return rc;
   if ((rc = grow(e, &e.ddpm_table, &e.ddpm_cap, (long long)std::max(n_steps, 1)))) return rc;
   if (!e.step_counter) CU_CHECK(e, cudaMalloc((void**)&e.step_counter, sizeof(int)));
+  if (!e.sampler_params) CU_CHECK(e, cudaMalloc((void**)&e.sampler_params, sizeof(SamplerParams)));
+  return 0;
+}
+
+// Per-call pointers / seed of the sampler kernels go through device memory, never through captured launch arguments.
+static int set_sampler_params(Engine& e, const float* noise, unsigned long long seed, float* traj, cudaStream_t st) {
+  const SamplerParams h{noise, seed, traj};
+  CU_CHECK(e, cudaMemcpyAsync(e.sampler_params, &h, sizeof(h), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
   return 0;
 }
 
@@ -775,9 +786,18 @@ static int run_steps(Engine& e, const std::string& key, bool use_graph, int n_st
     cudaGraphGetNodes(graph, nullptr, &n_nodes);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) return fail(e, CFM_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+    if ((int)e.graphs.size() >= Engine::kMaxGraphs && !e.graph_lru.empty()) {     // evict the least recently used graph
+      const std::string old = e.graph_lru.front();
+      e.graph_lru.erase(e.graph_lru.begin());
+      auto io = e.graphs.find(old);
+      if (io != e.graphs.end()) { cudaGraphExecDestroy(io->second); e.graphs.erase(io); }
+      e.graph_nodes.erase(old);
+    }
     e.graph_nodes[key] = (int)n_nodes;
     it = e.graphs.emplace(key, exec).first;
   }
+  e.graph_lru.erase(std::remove(e.graph_lru.begin(), e.graph_lru.end(), key), e.graph_lru.end());
+  e.graph_lru.push_back(key);
   for (int k = 0; k < n_steps; ++k) {
     cudaError_t ce = cudaGraphLaunch(it->second, st);
     if (ce != cudaSuccess) return fail(e, CFM_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(ce));
@@ -841,7 +861,7 @@ void cfm_engine_destroy(cfm_engine* h) {
   attn_wide_forget(e);
   drop_graphs(e);
   for (void* p : {(void*)e.x_work, (void*)e.cond_work, (void*)e.img_work, (void*)e.y_work, (void*)e.t_table, (void*)e.dt_table,
-                  (void*)e.ddpm_table, (void*)e.step_counter})
+                  (void*)e.ddpm_table, (void*)e.step_counter, (void*)e.sampler_params})
     if (p) cudaFree(p);
   for (void* p : e.owned) cudaFree(p);
   for (cudaEvent_t ev : e.prof_events) cudaEventDestroy(ev);
@@ -857,6 +877,7 @@ int64_t cfm_engine_workspace_bytes(const cfm_engine* e, int32_t batch) {
 }
 int32_t cfm_engine_kernel_launches(const cfm_engine* e) { return e ? e->impl.launches : 0; }
 int32_t cfm_engine_tensor_core_convs(const cfm_engine* e) { return e ? e->impl.n_tc_convs : 0; }
+int32_t cfm_engine_cached_graphs(const cfm_engine* e) { return e ? (int32_t)e->impl.graphs.size() : 0; }
 
 int cfm_engine_forward(cfm_engine* h, int32_t batch, const float* x_dev, const float* cond_dev, const float* t_dev,
                        float t_scalar, const int64_t* y_dev, float* out_dev, void* stream) {
@@ -956,6 +977,7 @@ static int sample_euler_impl(cfm_engine* h, int32_t batch, float* x_dev, float* 
     CU_CHECK(e, cudaMemcpyAsync(e.dt_table, dt_host, sizeof(float) * n_steps, cudaMemcpyHostToDevice, st));
   }
   CU_CHECK(e, cudaMemsetAsync(e.step_counter, 0, sizeof(int), st));
+  if ((rc = set_sampler_params(e, nullptr, 0ull, traj_dev, st))) return rc;
   if (traj_dev) CU_CHECK(e, cudaMemcpyAsync(traj_dev, x_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   if (n_steps == 0 && img_u8_dev) { quantize_u8_kernel<<<ew_blocks(e, n), 256, 0, st>>>(img_u8_dev, x_dev, n); e.launches++; }
 
@@ -973,7 +995,7 @@ static int sample_euler_impl(cfm_engine* h, int32_t batch, float* x_dev, float* 
       e.launches++;
     }
     euler_step_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.dt_table, e.step_counter, n_steps, n,
-                                                      drift ? e.cond_work : nullptr, n_cond, traj_dev,
+                                                      drift ? e.cond_work : nullptr, n_cond, e.sampler_params,
                                                       img_u8_dev ? e.img_work : nullptr);
     counter_add_kernel<<<1, 1, 0, s2>>>(e.step_counter);
     e.launches += 2;
@@ -981,8 +1003,8 @@ static int sample_euler_impl(cfm_engine* h, int32_t batch, float* x_dev, float* 
   };
   char key[160];
   uint32_t w_bits; std::memcpy(&w_bits, &guidance_w, 4);
-  snprintf(key, sizeof(key), "euler:%d:%d:%d:%d:%d:%p:%d:%d:%08x", batch, n_steps, cond_dev != nullptr, y_dev != nullptr, (int)drift,
-           (void*)traj_dev, img_u8_dev != nullptr, (int)guided, guided ? w_bits : 0u);
+  snprintf(key, sizeof(key), "euler:%d:%d:%d:%d:%d:%d:%d:%08x", batch, n_steps, cond_dev != nullptr, y_dev != nullptr, (int)drift,
+           img_u8_dev != nullptr, (int)guided, guided ? w_bits : 0u);
   const bool use_graph = (flags & CFM_EULER_USE_GRAPH) != 0;
   if (use_graph && n_steps > 0 && !e.graphs.count(key)) {
     // un-captured dry run first: all lazy host-side setup (tensor maps, kernel attributes) happens outside capture
@@ -1006,6 +1028,36 @@ int cfm_sample_euler_cfg(cfm_engine* h, int32_t batch, float* x_dev, float* cond
                          float guidance_w, const float* t_host, const float* dt_host, int32_t n_steps, uint32_t flags,
                          float* traj_dev, uint8_t* img_u8_dev, void* stream) {
   return sample_euler_impl(h, batch, x_dev, cond_dev, y_dev, true, guidance_w, t_host, dt_host, n_steps, flags, traj_dev, img_u8_dev, stream);
+}
+
+// Scalars of chain step i.  unfused = false: the posterior kernel of step i also applies the mask blend of step i - 1
+// (one launch per step); unfused = true: the blend of step i runs on its own before the U-Net call (chains with
+// corrector steps, and the stepwise API where a Python-level eps network sits between the launches).
+static DdpmStepScalars ddpm_scalars(const cfm_ddpm_tables* tb, const cfm_ddpm_options* opt, int i, bool unfused) {
+  const int Ns = tb->Ns, n_corr = (int)opt->n_corrector;
+  const bool repl = opt->mode == CFM_DDPM_REPLACEMENT;
+  auto blend_at = [&](int j) { return repl && j >= 0 && j < opt->replace_below_step; };
+  DdpmStepScalars s{};
+  s.a = tb->sqrt_recip_alphas_cumprod[i]; s.b = tb->sqrt_recipm1_alphas_cumprod[i];
+  s.c1 = tb->posterior_mean_coef1[i]; s.c2 = tb->posterior_mean_coef2[i];
+  s.sigma = expf(0.5f * tb->posterior_log_variance_clipped[i]);
+  s.add_noise = i > 0;
+  s.blend_next = blend_at(i - 1);
+  s.noise_condition = opt->noise_condition; s.pad_value = opt->pad_value;
+  if (s.blend_next) { s.sa = tb->sqrt_alphas_cumprod[i - 1]; s.sb = tb->sqrt_one_minus_alphas_cumprod[i - 1]; }
+  s.final_clip = i == 0 && n_corr == 0;      // with correctors the last corrector of step 0 clips
+  s.chain_index = i;
+  s.n_slots = 2 + n_corr;
+  if (unfused) {
+    // un-fused order: [blend i] -> U-Net -> posterior draw -> n_corr x (U-Net -> Langevin step)
+    s.blend_cur = blend_at(i); s.blend_next = 0;
+    s.sa_cur = tb->sqrt_alphas_cumprod[i]; s.sb_cur = tb->sqrt_one_minus_alphas_cumprod[i];
+    s.corr_r = 1.0f / tb->sqrt_one_minus_alphas_cumprod[i];
+    const double dt = (1.0 - 0.00001) / Ns;            // (tmax - tmin) / Ns, sde_diffusion.py:130-132
+    s.corr_cd = (float)(0.5 * dt * (double)opt->corrector_delta);
+    s.corr_cn = (float)std::sqrt(dt * (double)opt->corrector_delta);
+  }
+  return s;
 }
 
 int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* condition_dev,
@@ -1040,27 +1092,7 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   std::vector<float> tt(Ns);
   for (int k = 0; k < Ns; ++k) {
     const int i = Ns - 1 - k;
-    DdpmStepScalars s{};
-    s.a = tb->sqrt_recip_alphas_cumprod[i]; s.b = tb->sqrt_recipm1_alphas_cumprod[i];
-    s.c1 = tb->posterior_mean_coef1[i]; s.c2 = tb->posterior_mean_coef2[i];
-    s.sigma = expf(0.5f * tb->posterior_log_variance_clipped[i]);
-    s.add_noise = i > 0;
-    s.blend_next = blend_at(i - 1);
-    s.noise_condition = opt->noise_condition; s.pad_value = opt->pad_value;
-    if (s.blend_next) { s.sa = tb->sqrt_alphas_cumprod[i - 1]; s.sb = tb->sqrt_one_minus_alphas_cumprod[i - 1]; }
-    s.final_clip = i == 0 && n_corr == 0;      // with correctors the last corrector of step 0 clips
-    s.chain_index = i;
-    s.n_slots = n_slots;
-    if (n_corr > 0) {
-      // un-fused order: [blend i] -> U-Net -> posterior draw -> n_corr x (U-Net -> Langevin step)
-      s.blend_cur = blend_at(i); s.blend_next = 0;
-      s.sa_cur = tb->sqrt_alphas_cumprod[i]; s.sb_cur = tb->sqrt_one_minus_alphas_cumprod[i];
-      s.corr_r = 1.0f / tb->sqrt_one_minus_alphas_cumprod[i];
-      const double dt = (1.0 - 0.00001) / Ns;            // (tmax - tmin) / Ns, sde_diffusion.py:130-132
-      s.corr_cd = (float)(0.5 * dt * (double)opt->corrector_delta);
-      s.corr_cn = (float)std::sqrt(dt * (double)opt->corrector_delta);
-    }
-    tab[k] = s;
+    tab[k] = ddpm_scalars(tb, opt, i, n_corr > 0);
     tt[k] = tb->model_time[i];
   }
   CU_CHECK(e, cudaMemcpyAsync(e.x_work, x_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
@@ -1068,6 +1100,7 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   CU_CHECK(e, cudaMemcpyAsync(e.ddpm_table, tab.data(), sizeof(DdpmStepScalars) * Ns, cudaMemcpyHostToDevice, st));
   CU_CHECK(e, cudaMemcpyAsync(e.t_table, tt.data(), sizeof(float) * Ns, cudaMemcpyHostToDevice, st));
   CU_CHECK(e, cudaMemsetAsync(e.step_counter, 0, sizeof(int), st));
+  if ((rc = set_sampler_params(e, noise_dev, seed, nullptr, st))) return rc;
   if (corr_cond) { fill_f32_kernel<<<ew_blocks(e, n), 256, 0, st>>>(e.v2_buf, opt->pad_value, n); e.launches++; }
   CU_CHECK(e, cudaStreamSynchronize(st));   // host staging vectors go out of scope below
   if (n_corr == 0 && blend_at(Ns - 1)) {
@@ -1077,15 +1110,15 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
     e.launches++;
   }
   auto body = [&](cudaStream_t s2) -> int {
-    if (n_corr > 0 && repl) { ddpm_blend_table_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.cond_work, e.ddpm_table, e.step_counter, noise_dev, seed, n); e.launches++; }
+    if (n_corr > 0 && repl) { ddpm_blend_table_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.cond_work, e.ddpm_table, e.step_counter, e.sampler_params, n); e.launches++; }
     int r = forward_impl(e, batch, e.x_work, amort ? e.cond_work : nullptr, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
     if (r) return r;
     ddpm_step_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter,
-                                                     condition_dev ? e.cond_work : nullptr, noise_dev, seed, n);
+                                                     condition_dev ? e.cond_work : nullptr, e.sampler_params, n);
     for (int c = 0; c < n_corr; ++c) {
       r = forward_impl(e, batch, e.x_work, corr_cond, nullptr, 0.f, nullptr, e.v_buf, s2, e.t_table, e.step_counter);
       if (r) return r;
-      ddpm_corrector_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter, noise_dev, seed, 2 + c, c == n_corr - 1, n);
+      ddpm_corrector_kernel<<<ew_blocks(e, n), 256, 0, s2>>>(e.x_work, e.v_buf, e.ddpm_table, e.step_counter, e.sampler_params, 2 + c, c == n_corr - 1, n);
       e.launches++;
     }
     counter_add_kernel<<<1, 1, 0, s2>>>(e.step_counter);
@@ -1094,7 +1127,7 @@ int cfm_sample_ddpm(cfm_engine* h, int32_t batch, float* x_dev, const float* con
   };
   char key[160];
   uint32_t d_bits; std::memcpy(&d_bits, &opt->corrector_delta, 4);
-  snprintf(key, sizeof(key), "ddpm:%d:%d:%d:%p:%llu:%d:%08x", batch, opt->mode, condition_dev != nullptr, (const void*)noise_dev, (unsigned long long)seed, n_corr, d_bits);
+  snprintf(key, sizeof(key), "ddpm:%d:%d:%d:%d:%08x", batch, opt->mode, condition_dev != nullptr, n_corr, d_bits);
   if (opt->use_graph && !e.graphs.count(key)) {
     if ((rc = forward_impl(e, batch, e.x_work, amort ? e.cond_work : nullptr, nullptr, 0.f, nullptr, e.v_buf, st, e.t_table, e.step_counter))) return rc;
   }
@@ -1120,13 +1153,134 @@ int cfm_rk_combine(float* out_dev, const float* y_dev, const float* const* k_dev
   return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
 }
 
+// scratch of the deterministic error norm: per device, block partials + the ticket counter (zeroed once; the kernel
+// leaves the ticket at zero)
+static int rk_scratch(int blocks, double** partial, unsigned** ticket) {
+  static std::mutex mu;
+  static std::map<int, std::pair<double*, unsigned*>> per_dev;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return CFM_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = per_dev.find(dev);
+  if (it == per_dev.end()) {
+    double* p = nullptr; unsigned* t = nullptr;
+    if (cudaMalloc((void**)&p, sizeof(double) * 148 * 8) != cudaSuccess || cudaMalloc((void**)&t, sizeof(unsigned)) != cudaSuccess) return CFM_ERR_OOM;
+    if (cudaMemset(t, 0, sizeof(unsigned)) != cudaSuccess) return CFM_ERR_CUDA;
+    it = per_dev.emplace(dev, std::make_pair(p, t)).first;
+  }
+  if (blocks > 148 * 8) return CFM_ERR_INTERNAL;
+  *partial = it->second.first; *ticket = it->second.second;
+  return 0;
+}
+
 int cfm_rk_error_sumsq(double* sumsq_dev, const float* y0_dev, const float* y1_dev, const float* const* k_dev,
                        const float* coef_host, int32_t n_k, float dt, float rtol, float atol, int64_t n, void* stream) {
   RkPtrs p; if (rk_pack(&p, k_dev, coef_host, n_k) || !sumsq_dev || !y0_dev || !y1_dev || n < 0) return CFM_ERR_INVALID;
   if (cudaMemsetAsync(sumsq_dev, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return CFM_ERR_CUDA;
   if (n == 0) return 0;
   const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-  rk_error_sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sumsq_dev, y0_dev, y1_dev, p, dt, rtol, atol, n);
+  double* partial = nullptr; unsigned* ticket = nullptr;
+  if (int rc = rk_scratch(blocks, &partial, &ticket)) return rc;
+  rk_error_sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sumsq_dev, partial, ticket, y0_dev, y1_dev, p, dt, rtol, atol, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+// One launch of a DDPM reverse-chain step for a caller that evaluates the eps network itself (a plain Python callable:
+// AD/experiments/main.py:140 passes `lambda xi, i: ema_network(xi, 1.0 * i / ddpm.Ns)`).
+//   phase 0: mask blend of step i (Replacement; before the network call)   phase 1: posterior draw from eps
+//   phase 2 + c: Langevin corrector c from eps (the network re-evaluated on the current x)
+int cfm_ddpm_step(float* x_dev, const float* eps_dev, const float* condition_dev, const cfm_ddpm_tables* tb,
+                  const cfm_ddpm_options* opt, int32_t chain_index, int32_t phase, const float* noise_dev, uint64_t seed,
+                  int64_t n, void* stream) {
+  if (!x_dev || !tb || !opt || tb->Ns <= 0 || chain_index < 0 || chain_index >= tb->Ns || n < 0 || phase < 0 ||
+      phase > 1 + (int)opt->n_corrector || (int)opt->n_corrector > 16) return CFM_ERR_INVALID;
+  if (phase >= 1 && !eps_dev) return CFM_ERR_INVALID;
+  if (opt->mode == CFM_DDPM_REPLACEMENT && !condition_dev) return CFM_ERR_INVALID;
+  if (n == 0) return 0;
+  const DdpmStepScalars s = ddpm_scalars(tb, opt, chain_index, true);
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (phase == 0) { if (s.blend_cur) ddpm_blend_value_kernel<<<blocks, 256, 0, st>>>(x_dev, condition_dev, s, noise_dev, seed, n); }
+  else if (phase == 1) ddpm_step_value_kernel<<<blocks, 256, 0, st>>>(x_dev, eps_dev, s, condition_dev, noise_dev, seed, n);
+  else ddpm_corrector_value_kernel<<<blocks, 256, 0, st>>>(x_dev, eps_dev, s, noise_dev, seed, phase, phase == 1 + (int)opt->n_corrector, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+int cfm_sde_em_step(float* x_dev, const float* drift_dev, const float* score_dev, float dt, float sigma,
+                    const float* noise_dev, uint64_t seed, uint32_t stream_id, int64_t n, void* stream) {
+  if (!x_dev || !drift_dev || n < 0 || !(dt > 0.f)) return CFM_ERR_INVALID;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  sde_em_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, drift_dev, score_dev, dt, sigma, sqrtf(dt), noise_dev, seed, stream_id, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+int cfm_ddpm_em_step(float* x_dev, const float* eps_dev, float beta_t, float sigma_t, double dt, const float* noise_dev,
+                     uint64_t seed, uint32_t stream_id, int64_t n, void* stream) {
+  if (!x_dev || !eps_dev || n < 0 || !(dt > 0.0) || !(sigma_t > 0.f) || beta_t < 0.f) return CFM_ERR_INVALID;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  // dt = 1 / Ns and np.sqrt(dt) are Python doubles in the reference, rounded to fp32 when they meet a tensor
+  ddpm_em_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, eps_dev, beta_t, sigma_t, sqrtf(beta_t), (float)dt, (float)std::sqrt(dt), noise_dev, seed, stream_id, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+// Euler-Maruyama sampling of dx = (drift(t, x, y) + score(t, x, y)) dt + sigma dW over the fixed grid t_host / dt_host
+// (conditional_mnist.ipynb cells 11-12: torchsde.sdeint(SDE(model, score_model), ..., dt=0.01)).  Both engines evaluate
+// the same state; score may be NULL.  noise_dev: [n_steps, B*C*H*W] injected normals, else Philox(seed), stream = step.
+int cfm_sample_sde(cfm_engine* drift, cfm_engine* score, int32_t batch, float* x_dev, const int64_t* y_dev,
+                   const float* t_host, const float* dt_host, int32_t n_steps, float sigma, const float* noise_dev,
+                   uint64_t seed, void* stream) {
+  if (!drift) return CFM_ERR_INVALID;
+  Engine& e = drift->impl;
+  if (!x_dev || batch <= 0 || n_steps < 0 || (n_steps > 0 && (!t_host || !dt_host))) return fail(e, CFM_ERR_INVALID, "bad argument to cfm_sample_sde");
+  if (score && (score->impl.device != e.device || score->impl.cfg.image_size != e.cfg.image_size || score->impl.cfg.in_channels != e.cfg.in_channels ||
+                score->impl.cfg.out_channels != e.cfg.out_channels || (score->impl.cfg.num_classes > 0) != (e.cfg.num_classes > 0)))
+    return fail(e, CFM_ERR_INVALID, "drift and score networks must share device, image shape and class conditioning");
+  if ((y_dev != nullptr) != (e.cfg.num_classes > 0)) return fail(e, CFM_ERR_INVALID, "must specify y if and only if the model is class-conditional");
+  if (e.cfg.in_channels != e.x_channels()) return fail(e, CFM_ERR_INVALID, "cfm_sample_sde takes unconditional or class-conditional networks");
+  cudaSetDevice(e.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = e.cfg.image_size;
+  const long long n = (long long)batch * e.x_channels() * S * S;
+  int rc = ensure_batch(e, batch); if (rc) return rc;
+  if ((rc = grow(e, &e.v_buf, &e.v_cap, n))) return rc;
+  if (score) {
+    if ((rc = ensure_batch(score->impl, batch))) { e.err = score->impl.err; return rc; }
+    if ((rc = grow(score->impl, &score->impl.v_buf, &score->impl.v_cap, n))) { e.err = score->impl.err; return rc; }
+  }
+  e.launches = 0;
+  for (int k = 0; k < n_steps; ++k) {
+    if ((rc = forward_impl(e, batch, x_dev, nullptr, nullptr, t_host[k], y_dev, e.v_buf, st))) return rc;
+    if (score) {
+      score->impl.launches = 0;
+      if ((rc = forward_impl(score->impl, batch, x_dev, nullptr, nullptr, t_host[k], y_dev, score->impl.v_buf, st))) { e.err = score->impl.err; return rc; }
+      e.launches += score->impl.launches;
+    }
+    sde_em_step_kernel<<<ew_blocks(e, n), 256, 0, st>>>(x_dev, e.v_buf, score ? score->impl.v_buf : nullptr, dt_host[k], sigma, sqrtf(dt_host[k]),
+                                                       noise_dev ? noise_dev + (long long)k * n : nullptr, seed, (unsigned)k, n);
+    e.launches++;
+  }
+  CU_CHECK(e, cudaGetLastError());
+  return 0;
+}
+
+int cfm_resize_bilinear(float* out_dev, const float* in_dev, int64_t planes, int32_t h_in, int32_t w_in, int32_t h_out,
+                        int32_t w_out, void* stream) {
+  if (!out_dev || !in_dev || planes < 0 || h_in <= 0 || w_in <= 0 || h_out <= 0 || w_out <= 0) return CFM_ERR_INVALID;
+  const long long n = (long long)planes * h_out * w_out;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  resize_bilinear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, in_dev, planes, h_in, w_in, h_out, w_out,
+                                                                  (float)h_in / (float)h_out, (float)w_in / (float)w_out);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+int cfm_fid_accumulate(double* sum_dev, double* outer_dev, const float* feats_dev, int64_t n, int32_t dim, void* stream) {
+  if (!sum_dev || !outer_dev || !feats_dev || n < 0 || dim <= 0) return CFM_ERR_INVALID;
+  if (n == 0) return 0;
+  const unsigned t = (unsigned)((dim + 31) / 32);
+  fid_accumulate_kernel<<<dim3(t, t), 256, 0, (cudaStream_t)stream>>>(sum_dev, outer_dev, feats_dev, n, dim);
   return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
 }
 

@@ -84,8 +84,11 @@ struct Engine {
   float* dt_table = nullptr; long long dt_cap = 0;
   struct DdpmStepScalars* ddpm_table = nullptr; long long ddpm_cap = 0;
   int* step_counter = nullptr;
-  std::map<std::string, cudaGraphExec_t> graphs;      // one captured step per sampler configuration
+  struct SamplerParams* sampler_params = nullptr;     // device: noise pointer, seed, trajectory buffer of the running loop
+  std::map<std::string, cudaGraphExec_t> graphs;      // one captured step per sampler configuration (LRU, <= kMaxGraphs)
   std::map<std::string, int> graph_nodes;
+  std::vector<std::string> graph_lru;                 // least recently used first
+  static constexpr int kMaxGraphs = 8;
   int64_t param_count = 0;
   double flops_per_sample = 0;
   int launches = 0;

@@ -7,10 +7,17 @@ Mirrors the reference's operator surface for this path:
 * ``InPainting`` / ``OutPainting`` / ``HyperResolution`` ... AD/image_diffusion/likelihoods.py:39-146
 * ``get_prior_sample_fn`` / ``get_conditional_sample_fn(eps_model, ddpm, conditioning, likelihood)``
   ........................................ AD/image_diffusion/sampling.py:50-75, 80-133, 209-260
-* ``EpsModel(network, ddpm)`` is the object form of ``lambda xi, i: network(xi, 1.0 * i / ddpm.Ns)``
-  (AD/experiments/main.py:140) that lets the sampler see the engine and run the whole chain
-  in one native call.  ``ReconstructionGuidance`` needs the U-Net's backward pass and is out
-  of scope for this inference engine (raises NotImplementedError).
+* The eps network is ANY callable ``eps_model(xi, i)`` (type ``Network``, sde_diffusion.py:11), as in the
+  reference: ``lambda xi, i: ema_network(xi, 1.0 * i / ddpm.Ns)`` (AD/experiments/main.py:140) works
+  unchanged.  When the callable turns out to be an engine-backed U-Net evaluated at ``t = i / Ns`` (an
+  ``EpsModel``, or a closure over one that a two-point probe confirms), the whole chain runs as one
+  native call (``cfm_sample_ddpm``); otherwise the chain runs step by step with the native step
+  kernels (``cfm_ddpm_step``) around the Python callable.  ``ReconstructionGuidance`` needs the U-Net's
+  backward pass and is out of scope for this inference engine (raises NotImplementedError).
+* Noise: the reference draws fresh ``torch.randn_like`` noise on every call.  Here every call of a
+  returned ``sample()`` draws a new Philox seed from torch's global CPU generator (mixed with the
+  rank under ``torch.distributed``), so successive calls and different ranks get independent noise;
+  ``seed=`` / ``noise=`` pin it for reproducibility.
 
 The multiple-dispatch on (conditioning, likelihood) types that the reference does with ``plum``
 is done with ``isinstance`` here.
@@ -34,6 +41,10 @@ bd = 20
 
 def beta(t):
     return bm + (bd - bm) * t
+
+
+def int_b(t):
+    return bm * t + (bd - bm) * t ** 2 / 2
 
 
 def extract(a, t, x_shape):
@@ -91,6 +102,28 @@ class DDPM(nn.Module):
     def p_mean_variance(self, x_start, x, i):
         m, v, lv = self.q_posterior(x0=x_start, x_i=x, i=i)
         return m, v, lv, x_start
+
+    def em_step(self, xi: torch.Tensor, noise_hat: torch.Tensor, i: int, z: Optional[torch.Tensor] = None, seed: int = 0):
+        """One reverse-time Euler-Maruyama step of the VP SDE from a noise prediction (sampling.py:100-111 ``em_step`` with
+        backward_drift / backward_diffusion / score_from_noise, sde_diffusion.py:170-205), as one native launch:
+        ``x = xi - dt*drift + g*z*sqrt(dt)``, ``drift = -0.5*xi*xi - g^2*score`` (sic: the reference's ``drift`` multiplies by x,
+        not beta_t - see oracle/ddpm.py), ``score = -noise_hat/sigma_t``,
+        ``t = ts[i]``, ``dt = 1/Ns``.  ``z``: injected normals (else Philox(seed), stream i).  Returns a new tensor."""
+        t = self.ts[int(i)]
+        beta_t = beta(t)
+        sigma_t = torch.sqrt(1 - torch.exp(-int_b(t)))
+        x = xi.detach().to(torch.float32).contiguous().clone()
+        eps = noise_hat.detach().to(torch.float32).contiguous()
+        if x.device.type != "cuda" or eps.device != x.device or eps.shape != x.shape:
+            raise ValueError("xi and noise_hat must be CUDA tensors of the same shape")
+        zd = None if z is None else z.to(device=x.device, dtype=torch.float32).contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            rc = lib.cfm_ddpm_em_step(C.c_void_p(x.data_ptr()), C.c_void_p(eps.data_ptr()), float(beta_t), float(sigma_t),
+                                      1 / self.Ns, None if zd is None else C.c_void_p(zd.data_ptr()), C.c_uint64(seed),
+                                      int(i), x.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _lib.check(rc)
+        return x
 
     def q_sample(self, x_start, i):
         noise = torch.randn_like(x_start)
@@ -159,8 +192,13 @@ class Painting(Likelihood):
         return h, w
 
     def sample_boxes(self, batch: int, image_size: int) -> torch.Tensor:
-        return torch.tensor([[int(v) for v in self.get_random_patch(image_size)] for _ in range(batch)],
-                            dtype=torch.int32).reshape(batch, 2)
+        """All (h, w) pairs in ONE call.  torch's CPU generator fills a tensor element by element in memory order, so
+        ``randint(lo, hi, (B, 2))`` consumes the global stream exactly like the reference's per-sample loop of two scalar
+        draws, h before w (likelihoods.py:49-53, 78-87; tests/test_host_logic.py pins this against the loop)."""
+        lo, hi = 5, image_size - self.patch_size - 5
+        if batch == 0:
+            return torch.empty((0, 2), dtype=torch.int32)
+        return torch.randint(lo, hi, size=(batch, 2)).to(torch.int32)
 
     def sample(self, x: torch.Tensor, boxes: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Per-sample random box; the fill is one native kernel instead of an O(B) Python loop."""
@@ -192,6 +230,24 @@ class OutPainting(Painting):
     mode = 1
 
 
+def resize_bilinear(images: torch.Tensor, size) -> torch.Tensor:
+    """``F.interpolate(images, size, mode="bilinear", align_corners=False)`` as one native kernel (cfm_resize_bilinear)."""
+    if images.device.type != "cuda":
+        raise RuntimeError("images must be on a CUDA device")
+    if images.dim() != 4:
+        raise ValueError("images must be [B, C, H, W]")
+    h, w = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    src = images.detach().to(torch.float32).contiguous()
+    B, Cc, H, W = src.shape
+    out = torch.empty((B, Cc, h, w), device=src.device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(src.device):
+        rc = lib.cfm_resize_bilinear(C.c_void_p(out.data_ptr()), C.c_void_p(src.data_ptr()), B * Cc, H, W, h, w,
+                                     C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream))
+    _lib.check(rc)
+    return out
+
+
 class HyperResolution(Likelihood):
     @classmethod
     def from_configdict(cls, config):
@@ -201,8 +257,8 @@ class HyperResolution(Likelihood):
         self.target_height, self.target_width = target_height, target_width
 
     def sample(self, images: torch.Tensor) -> torch.Tensor:
-        lo = F.interpolate(images, size=(self.target_height, self.target_width), mode="bilinear", align_corners=False)
-        return F.interpolate(lo, (images.shape[2], images.shape[3]), mode="bilinear")
+        lo = resize_bilinear(images, (self.target_height, self.target_width))
+        return resize_bilinear(lo, (images.shape[2], images.shape[3]))
 
     def none_like(self, x):
         return torch.zeros_like(x)
@@ -214,7 +270,7 @@ def get_likelihood(type_: str):
 
 def downsample_images(images, target_size):
     """mnist/utils_mnist_hy.py:18-28."""
-    return F.interpolate(images, size=target_size, mode="bilinear", align_corners=False)
+    return resize_bilinear(images, target_size)
 
 
 # --- eps network + sampler factories ----------------------------------------------------------------
@@ -234,37 +290,183 @@ def _noise_tensor(noise, Ns, x):
     raise TypeError("noise must be a [Ns, 2 + n_corrector, B*C*H*W] tensor or None")
 
 
-def get_prior_sample_fn(eps_model, ddpm: DDPM, conditioning=None, likelihood=None, *, noise=None, seed: int = 0,
+def _fresh_seed(seed: Optional[int]) -> int:
+    """Explicit seed: reproducible.  None: a new seed per call from torch's global CPU generator (advances it, as the
+    reference's randn_like calls advance the global generator), mixed with the rank under torch.distributed."""
+    if seed is not None:
+        return int(seed)
+    s_ = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            s_ ^= (dist.get_rank() + 1) * 0x9E3779B97F4A7C15 & (2 ** 63 - 1)
+    except Exception:
+        pass
+    return s_
+
+
+def _find_unet(obj, depth: int = 0):
+    """An engine-backed U-Net reachable from a callable: itself, its ``ema_model`` / ``module`` / ``network`` attribute
+    (EMA and DataParallel wrappers), or a cell of its closure."""
+    if isinstance(obj, UNetModel):
+        return obj
+    if depth > 2:
+        return None
+    for name in ("network", "ema_model", "module", "model"):
+        sub = getattr(obj, name, None)
+        if sub is not None and sub is not obj:
+            r = _find_unet(sub, depth + 1)
+            if r is not None:
+                return r
+    for cell in getattr(obj, "__closure__", None) or ():
+        try:
+            r = _find_unet(cell.cell_contents, depth + 1)
+        except ValueError:
+            r = None
+        if r is not None:
+            return r
+    return None
+
+
+def _engine_behind(eps_model, ddpm: DDPM, in_channels_needed: Optional[int] = None):
+    """The U-Net whose engine can run the whole chain natively, or None.  A plain callable qualifies only if it is
+    observably ``xi, i -> unet(xi, i / Ns)``: it is probed at two chain indices on a random input and must reproduce
+    the engine's own forward bit for bit (the engine is deterministic)."""
+    if isinstance(eps_model, EpsModel):
+        return eps_model.network if isinstance(eps_model.network, UNetModel) else None
+    net = _find_unet(eps_model)
+    if net is None or net.num_classes is not None:
+        return None
+    try:
+        p = next(net.parameters())
+        if p.device.type != "cuda":
+            return None
+        cfg = net.config
+        g = torch.Generator(device="cpu").manual_seed(12345)
+        x = torch.randn(2, cfg.in_channels, cfg.image_size, cfg.image_size, generator=g).to(p.device)
+        for idx in (0, ddpm.Ns - 1):
+            i = torch.full((2,), idx, device=p.device, dtype=torch.long)
+            got = eps_model(x, i)
+            want = net.engine().forward(x, 1.0 * i / ddpm.Ns)
+            if got.shape != want.shape or not torch.equal(got.to(torch.float32), want):
+                return None
+        return net
+    except Exception:
+        return None
+
+
+def _check_condition(xT: torch.Tensor, condition: torch.Tensor) -> torch.Tensor:
+    """The reference's ``torch.where`` / ``concat`` broadcast a [1, C, H, W] condition; the native chain indexes it
+    element by element, so it is expanded here and anything else is rejected."""
+    if condition.dim() != xT.dim() or tuple(condition.shape[1:]) != tuple(xT.shape[1:]) or condition.shape[0] not in (1, xT.shape[0]):
+        raise ValueError(f"condition must be {tuple(xT.shape)} (or batch 1), got {tuple(condition.shape)}")
+    if condition.device != xT.device:
+        raise ValueError("condition and xT must live on the same device")
+    return condition.expand_as(xT) if condition.shape[0] != xT.shape[0] else condition
+
+
+def _tables_c(ddpm: DDPM):
+    keep = []
+    tb = _lib.DdpmTablesC()
+    tb.Ns = ddpm.Ns
+    for name, t in ddpm.tables().items():
+        h = t.detach().to("cpu", torch.float32).contiguous()
+        keep.append(h)
+        setattr(tb, name, C.cast(h.data_ptr(), C.POINTER(C.c_float)))
+    return tb, keep
+
+
+def _stepwise_chain(eps_model, ddpm: DDPM, xT, mode: str, condition=None, pad_value=-2.0, replace_below_step=None,
+                    noise_condition=True, noise=None, seed=0, n_corrector=0, corrector_delta=0.1, none_value=0.0):
+    """The reverse chains of sampling.py:50-75 / 80-133 / 209-260 around an arbitrary Python eps network: every
+    elementwise step is one native launch (cfm_ddpm_step), the network call stays with the caller's callable."""
+    lib = _lib.load()
+    if xT.device.type != "cuda":
+        raise RuntimeError("xT must be on a CUDA device (no CPU fallback)")
+    x = xT.detach().to(torch.float32).contiguous().clone()
+    B = x.shape[0]
+    Ns = ddpm.Ns
+    cd = None if condition is None else condition.detach().to(torch.float32).contiguous()
+    tb, keep = _tables_c(ddpm)
+    opt = _lib.DdpmOptionsC()
+    opt.mode = {"prior": _lib.DDPM_PRIOR, "replacement": _lib.DDPM_REPLACEMENT, "amortized": _lib.DDPM_AMORTIZED}[mode]
+    opt.pad_value = float(pad_value)
+    opt.replace_below_step = Ns if replace_below_step is None else int(replace_below_step)
+    opt.noise_condition = int(noise_condition)
+    opt.n_corrector = int(n_corrector)
+    opt.corrector_delta = float(corrector_delta)
+    nd = None
+    if noise is not None:
+        nd = noise.to(device=x.device, dtype=torch.float32).contiguous()
+        assert nd.numel() == Ns * (2 + int(n_corrector)) * x.numel(), "noise must be [Ns, 2 + n_corrector, B*C*H*W]"
+    if B == 0:
+        return x
+    none_cond = torch.full_like(x, none_value) if (mode == "amortized" and n_corrector) else None
+    stream = lambda: C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+
+    def launch(i, phase, eps):
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cfm_ddpm_step(ptr(x), ptr(eps), ptr(cd) if mode == "replacement" else None, C.byref(tb), C.byref(opt),
+                                         i, phase, ptr(nd), C.c_uint64(seed), x.numel(), stream()))
+
+    def net(i, cond_for_net):
+        idx = torch.full((B,), i, device=x.device, dtype=torch.long)
+        inp = x if cond_for_net is None else torch.cat((x, cond_for_net), dim=-3)
+        return eps_model(inp, idx).to(torch.float32).contiguous()
+
+    for i in reversed(range(Ns)):
+        if mode == "replacement":
+            launch(i, 0, None)
+        launch(i, 1, net(i, cd if mode == "amortized" else None))
+        for c in range(int(n_corrector)):
+            launch(i, 2 + c, net(i, none_cond if mode == "amortized" else None))
+    del keep
+    return x
+
+
+def get_prior_sample_fn(eps_model, ddpm: DDPM, conditioning=None, likelihood=None, *, noise=None, seed: Optional[int] = None,
                         use_graph: bool = False) -> Callable:
-    if not isinstance(eps_model, EpsModel):
-        raise TypeError("wrap the network as EpsModel(network, ddpm) so the sampler can run on the engine")
+    if not callable(eps_model):
+        raise TypeError("eps_model must be callable as eps_model(xi, i)")
     amortized = isinstance(conditioning, Amortized)
+    state = {}
 
     @torch.no_grad()
     def sample(xT):
-        eng = eps_model.network.engine()
-        if amortized:      # x0_model substitutes likelihood.none_like(xi) for the condition (sampling.py:36-37)
-            return eng.sample_ddpm(xT, ddpm.tables(), mode="amortized", condition=likelihood.none_like(xT),
-                                   noise=_noise_tensor(noise, ddpm.Ns, xT), seed=seed, use_graph=use_graph)
-        return eng.sample_ddpm(xT, ddpm.tables(), mode="prior", noise=_noise_tensor(noise, ddpm.Ns, xT), seed=seed,
-                               use_graph=use_graph)
+        if "net" not in state:
+            state["net"] = _engine_behind(eps_model, ddpm)
+        net, s_ = state["net"], _fresh_seed(seed)
+        cond = likelihood.none_like(xT) if amortized else None      # x0_model's stand-in condition (sampling.py:36-37)
+        if net is None:
+            return _stepwise_chain(eps_model, ddpm, xT, "amortized" if amortized else "prior", condition=cond,
+                                   noise=_noise_tensor(noise, ddpm.Ns, xT), seed=s_)
+        return net.engine().sample_ddpm(xT, ddpm.tables(), mode="amortized" if amortized else "prior", condition=cond,
+                                        noise=_noise_tensor(noise, ddpm.Ns, xT), seed=s_, use_graph=use_graph)
 
     return sample
 
 
-def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *, noise=None, seed: int = 0,
+def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *, noise=None, seed: Optional[int] = None,
                               use_graph: bool = False) -> Callable:
-    if not isinstance(eps_model, EpsModel):
-        raise TypeError("wrap the network as EpsModel(network, ddpm) so the sampler can run on the engine")
+    if not callable(eps_model):
+        raise TypeError("eps_model must be callable as eps_model(xi, i)")
     if getattr(conditioning, "n_corrector", 0) and not isinstance(conditioning, (Replacement, Amortized)):
         raise NotImplementedError("Langevin corrector steps (n_corrector > 0) run on the engine for Replacement and "
                                   "Amortized conditioning only")
+    state = {}
+
+    def backend():
+        if "net" not in state:
+            state["net"] = _engine_behind(eps_model, ddpm)
+        return state["net"]
 
     if isinstance(conditioning, Amortized):
         n_corr = int(getattr(conditioning, "n_corrector", 0))
 
         @torch.no_grad()
         def sample(xT, condition):
+            condition = _check_condition(xT, condition)
             none_value = 0.0
             if n_corr:
                 # the corrector's x0_model call has no condition -> likelihood.none_like(xi) (sampling.py:36-37, 116);
@@ -273,11 +475,12 @@ def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *
                 none_value = float(none.flatten()[0])
                 if not bool((none == none_value).all()):
                     raise NotImplementedError("Amortized corrector steps need a constant likelihood.none_like()")
-            return eps_model.network.engine().sample_ddpm(xT, ddpm.tables(), mode="amortized", condition=condition,
-                                                          pad_value=none_value,
-                                                          noise=_noise_tensor(noise, ddpm.Ns, xT), seed=seed,
-                                                          use_graph=use_graph, n_corrector=n_corr,
-                                                          corrector_delta=float(conditioning.delta))
+            kw = dict(mode="amortized", condition=condition, pad_value=none_value, noise=_noise_tensor(noise, ddpm.Ns, xT),
+                      seed=_fresh_seed(seed), n_corrector=n_corr, corrector_delta=float(conditioning.delta))
+            net = backend()
+            if net is None:
+                return _stepwise_chain(eps_model, ddpm, xT, none_value=none_value, **kw)
+            return net.engine().sample_ddpm(xT, ddpm.tables(), use_graph=use_graph, **kw)
         return sample
 
     if isinstance(conditioning, Replacement):
@@ -287,11 +490,15 @@ def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *
 
         @torch.no_grad()
         def sample(xT, condition):
-            return eps_model.network.engine().sample_ddpm(
-                xT, ddpm.tables(), mode="replacement", condition=condition, pad_value=float(pad),
-                replace_below_step=int(ddpm.Ns * conditioning.start_fraction), noise_condition=bool(conditioning.noise),
-                noise=_noise_tensor(noise, ddpm.Ns, xT), seed=seed, use_graph=use_graph,
-                n_corrector=int(getattr(conditioning, "n_corrector", 0)), corrector_delta=float(conditioning.delta))
+            condition = _check_condition(xT, condition)
+            kw = dict(mode="replacement", condition=condition, pad_value=float(pad),
+                      replace_below_step=int(ddpm.Ns * conditioning.start_fraction), noise_condition=bool(conditioning.noise),
+                      noise=_noise_tensor(noise, ddpm.Ns, xT), seed=_fresh_seed(seed),
+                      n_corrector=int(getattr(conditioning, "n_corrector", 0)), corrector_delta=float(conditioning.delta))
+            net = backend()
+            if net is None:
+                return _stepwise_chain(eps_model, ddpm, xT, **kw)
+            return net.engine().sample_ddpm(xT, ddpm.tables(), use_graph=use_graph, **kw)
         return sample
 
     raise NotImplementedError(f"no engine sampler for conditioning {type(conditioning).__name__}")

@@ -88,7 +88,8 @@ class Engine:
         numel = (C.c_int64 * n)(*[v.numel() for _, v in items])
         handle = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        rc = self.lib.cfm_engine_create(C.byref(cfg), n, names, ptrs, numel, idx, C.byref(handle))
+        with torch.cuda.device(self.device):      # cfm_engine_create selects the device: keep the caller's current one
+            rc = self.lib.cfm_engine_create(C.byref(cfg), n, names, ptrs, numel, idx, C.byref(handle))
         _lib.check(rc, None)
         self._h = handle
         self.x_channels = config.out_channels
@@ -96,8 +97,22 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
-            self.lib.cfm_engine_destroy(self._h)
+            with torch.cuda.device(self.device):
+                self.lib.cfm_engine_destroy(self._h)
             self._h = None
+
+    def _labels(self, y: Optional[torch.Tensor], B: int) -> Optional[torch.Tensor]:
+        """int64 labels on the device, range-checked (an out-of-range label would index past the embedding table)."""
+        assert (y is not None) == (self.config.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        if y is None:
+            return None
+        if tuple(y.shape) != (B,):
+            raise ValueError(f"y must have shape ({B},), got {tuple(y.shape)}")
+        yd = y.to(device=self.device, dtype=torch.int64).contiguous()
+        if B and (int(yd.min()) < 0 or int(yd.max()) >= self.config.num_classes):
+            raise IndexError(f"class labels must lie in [0, {self.config.num_classes})")
+        return yd
 
     def __del__(self):
         try:
@@ -122,6 +137,10 @@ class Engine:
     def tensor_core_convs(self) -> int:
         return int(self.lib.cfm_engine_tensor_core_convs(self._h))
 
+    @property
+    def cached_graphs(self) -> int:
+        return int(self.lib.cfm_engine_cached_graphs(self._h))
+
     def workspace_bytes(self, batch: int) -> int:
         return int(self.lib.cfm_engine_workspace_bytes(self._h, batch))
 
@@ -136,14 +155,9 @@ class Engine:
             raise ValueError(f"x must be [B,{cx},{S},{S}], got {tuple(x.shape)}")
         if cond is not None and tuple(cond.shape) != (B, self.config.in_channels - cx, S, S):
             raise ValueError(f"cond must be [B,{self.config.in_channels - cx},{S},{S}], got {tuple(cond.shape)}")
-        assert (y is not None) == (self.config.num_classes is not None), \
-            "must specify y if and only if the model is class-conditional"
         xd = _as_f32_cuda(x, self.device)
         cd = None if cond is None else _as_f32_cuda(cond, self.device)
-        yd = None
-        if y is not None:
-            assert tuple(y.shape) == (B,)
-            yd = y.to(device=self.device, dtype=torch.int64).contiguous()
+        yd = self._labels(y, B)
         t_dev, t_scalar = None, 0.0
         if torch.is_tensor(t):
             while t.dim() > 1:
@@ -203,11 +217,17 @@ class Engine:
         n_steps = len(t_grid)
         assert len(dt_grid) == n_steps
         B = x0.shape[0]
-        x = _as_f32_cuda(x0, self.device).clone()
-        cd = None if cond is None else _as_f32_cuda(cond, self.device).clone()
-        yd = None if y is None else y.to(device=self.device, dtype=torch.int64).contiguous()
-        assert (y is not None) == (self.config.num_classes is not None), \
-            "must specify y if and only if the model is class-conditional"
+        S = self.config.image_size
+        cx = self.config.in_channels if cond is None else self.x_channels
+        if tuple(x0.shape[1:]) != (cx, S, S):
+            raise ValueError(f"x0 must be [B,{cx},{S},{S}], got {tuple(x0.shape)}")
+        if cond is not None and tuple(cond.shape) != (B, self.config.in_channels - cx, S, S):
+            raise ValueError(f"cond must be [B,{self.config.in_channels - cx},{S},{S}], got {tuple(cond.shape)}")
+        x = _as_f32_cuda(x0, self.device).clone()        # the native loop integrates in place: keep the caller's x0
+        cd = None if cond is None else _as_f32_cuda(cond, self.device)
+        if cond_drift and cd is not None and cd.data_ptr() == cond.data_ptr():
+            cd = cd.clone()                               # COND_DRIFT writes the drifted conditioning back
+        yd = self._labels(y, B)
         traj = torch.empty((n_steps + 1,) + tuple(x.shape), device=self.device, dtype=torch.float32) if return_trajectory else None
         img = torch.empty(tuple(x.shape), device=self.device, dtype=torch.uint8) if return_uint8 else None
         tg = (C.c_float * max(n_steps, 1))(*[float(v) for v in t_grid])
@@ -232,6 +252,20 @@ class Engine:
                     noise: Optional[torch.Tensor] = None, seed: int = 0, use_graph: bool = False,
                     n_corrector: int = 0, corrector_delta: float = 0.1) -> torch.Tensor:
         Ns = int(tables["sqrt_alphas_cumprod"].numel())
+        S = self.config.image_size
+        if tuple(xT.shape[1:]) != (self.x_channels, S, S):
+            raise ValueError(f"xT must be [B,{self.x_channels},{S},{S}], got {tuple(xT.shape)}")
+        if mode != "prior" and condition is None:
+            raise ValueError("conditional sampling needs a condition")
+        if condition is not None:
+            # the native chain reads batch * C * S * S floats of it: a broadcastable or differently shaped condition
+            # (which torch.where / concat would accept or reject later) must match xT exactly here
+            if condition.dim() == xT.dim() and condition.shape[0] == 1 and tuple(condition.shape[1:]) == tuple(xT.shape[1:]):
+                condition = condition.expand_as(xT)
+            if tuple(condition.shape) != tuple(xT.shape):
+                raise ValueError(f"condition must have the shape of xT {tuple(xT.shape)}, got {tuple(condition.shape)}")
+            if mode == "amortized" and self.cond_channels != self.x_channels:
+                raise ValueError("amortized conditioning needs a network with 2 * C input channels")
         x = _as_f32_cuda(xT, self.device).clone()
         cd = None if condition is None else _as_f32_cuda(condition, self.device)
         keep = []

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import inspect
+import math
 from typing import Callable, List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -55,12 +56,23 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _check_state(*tensors):
+    """The native state kernels take raw pointers: fp32, contiguous, one CUDA device, one element count."""
+    ref = tensors[0]
+    for t in tensors:
+        if not torch.is_tensor(t) or t.device.type != "cuda" or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("state tensors must be contiguous fp32 CUDA tensors")
+        if t.device != ref.device or t.numel() != ref.numel():
+            raise ValueError("state tensors must share device and element count")
+
+
 def rk_combine(y: torch.Tensor, ks: Sequence[torch.Tensor], coefs: Sequence[float], dt: float,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = y + dt * sum_j coefs[j] * ks[j]   (one fused kernel; zero coefficients are dropped)."""
     lib = _lib.load()
     pairs = [(k, c) for k, c in zip(ks, coefs) if c != 0]
     assert 1 <= len(pairs) <= 8
+    _check_state(y, *[k for k, _ in pairs], *([] if out is None else [out]))
     if out is None:
         out = torch.empty_like(y)
     kp = (C.c_void_p * len(pairs))(*[k.data_ptr() for k, _ in pairs])
@@ -76,6 +88,9 @@ def rk_error_sumsq(y0, y1, ks, coefs, dt, rtol, atol, scratch: torch.Tensor) -> 
     """Device scalar (float64) = sum((dt*sum_j c_j k_j / (atol + rtol*max(|y0|,|y1|)))^2)."""
     lib = _lib.load()
     pairs = [(k, c) for k, c in zip(ks, coefs) if c != 0]
+    _check_state(y0, y1, *[k for k, _ in pairs])
+    if scratch.device != y0.device or scratch.dtype != torch.float64 or scratch.numel() < 1:
+        raise ValueError("scratch must be a float64 tensor on the state's device")
     kp = (C.c_void_p * len(pairs))(*[k.data_ptr() for k, _ in pairs])
     cf = (C.c_float * len(pairs))(*[float(c) for _, c in pairs])
     with torch.cuda.device(y0.device):
@@ -135,6 +150,58 @@ def sample_euler(model: UNetModel, x0: torch.Tensor, t_span: torch.Tensor, y=Non
     x, _, img = model.engine().sample_euler(x0, ts, dts, y=y, cond=cond, cond_drift=cond_drift,
                                             return_uint8=return_uint8, use_graph=use_graph, guidance_weight=guidance_weight)
     return (x, img) if return_uint8 else x
+
+
+@torch.no_grad()
+def sample_sde(drift, score, x0: torch.Tensor, ts: torch.Tensor, dt: float, sigma: float = 0.1, y=None,
+               noise: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+    """Euler-Maruyama sampling of ``dx = (drift(t,x,y) + score(t,x,y)) dt + sigma dW`` from ``ts[0]`` to ``ts[-1]`` with a
+    fixed step ``dt`` - what ``torchsde.sdeint(SDE(model, score_model, labels), x0, ts=linspace(0, 1, 2), dt=0.01)`` does
+    in conditional_mnist.ipynb cells 11-12 (scheme "euler", diagonal Ito noise, g = sigma).  Returns the final state.
+
+    Two engine-backed U-Nets (``score`` may be None) run as ONE native call (cfm_sample_sde); any other callables are
+    stepped with the native update kernel (cfm_sde_em_step).  ``noise``: [n_steps, *x0.shape] injected normals, else a
+    Philox stream per step from ``seed``."""
+    lib = _lib.load()
+    t0, t1 = float(ts[0]), float(ts[-1])
+    n_steps = max(int(math.ceil((t1 - t0) / dt - 1e-9)), 0)
+    tg = [t0 + k * dt for k in range(n_steps)]
+    dg = [min(dt, t1 - t) for t in tg]
+    x = x0.detach().to(torch.float32).contiguous().clone()
+    if x.device.type != "cuda":
+        raise RuntimeError("x0 must be on a CUDA device (no CPU fallback)")
+    B = x.shape[0]
+    nd = None
+    if noise is not None:
+        nd = noise.to(device=x.device, dtype=torch.float32).contiguous()
+        assert nd.numel() == n_steps * x.numel(), "noise must be [n_steps, *x0.shape]"
+    if B == 0 or n_steps == 0:
+        return x
+    native = isinstance(drift, UNetModel) and (score is None or isinstance(score, UNetModel))
+    if native:
+        e_d = drift.engine()
+        e_s = None if score is None else score.engine()
+        yd = e_d._labels(y, B)
+        tgc = (C.c_float * n_steps)(*tg)
+        dgc = (C.c_float * n_steps)(*dg)
+        with torch.cuda.device(x.device):
+            rc = lib.cfm_sample_sde(e_d._h, None if e_s is None else e_s._h, B, C.c_void_p(x.data_ptr()),
+                                    None if yd is None else C.c_void_p(yd.data_ptr()), tgc, dgc, n_steps, float(sigma),
+                                    None if nd is None else C.c_void_p(nd.data_ptr()), C.c_uint64(seed), _stream(x.device))
+        _lib.check(rc, e_d._h)
+        return x
+    call = (lambda f, t: f(t, x) if y is None else f(t, x, y))
+    for k, (t, h) in enumerate(zip(tg, dg)):
+        tt = torch.tensor(t, dtype=torch.float32, device=x.device)
+        v = call(drift, tt).to(torch.float32).contiguous()
+        s_ = None if score is None else call(score, tt).to(torch.float32).contiguous()
+        zk = None if nd is None else nd.view(n_steps, -1)[k]
+        with torch.cuda.device(x.device):
+            rc = lib.cfm_sde_em_step(C.c_void_p(x.data_ptr()), C.c_void_p(v.data_ptr()), None if s_ is None else C.c_void_p(s_.data_ptr()),
+                                     float(h), float(sigma), None if zk is None else C.c_void_p(zk.data_ptr()), C.c_uint64(seed), k,
+                                     x.numel(), _stream(x.device))
+        _lib.check(rc)
+    return x
 
 
 State = Union[torch.Tensor, Tuple[torch.Tensor, ...]]

@@ -316,5 +316,6 @@ class SuperResModelWrapper(InPaintModelWrapper):
     @torch.no_grad()
     def forward(self, x, t, low_res=None, *args, **kwargs):
         assert low_res is not None, "SuperResModelWrapper needs low_res="
-        up = F.interpolate(low_res.to(torch.float32), size=tuple(x.shape[-2:]), mode="bilinear")
+        from .diffusion import resize_bilinear
+        up = resize_bilinear(low_res, tuple(x.shape[-2:]))
         return self.engine().forward(x, _expand_t(t, x.shape[0]), cond=up)

@@ -30,6 +30,15 @@
  *                             cifar10/compute_fid.py:83-85, mnist/utils_mnist.py:101-108
  *                             (the accept/reject controller stays on the host)
  *   cfm_make_box_condition <- InPainting/OutPainting._sample  AD/image_diffusion/likelihoods.py:78-105
+ *   cfm_ddpm_step          <- one iteration of the reverse chains above around ANY `eps_model(xi, i)` callable
+ *                             (type Network, AD/image_diffusion/sde_diffusion.py:11; AD/experiments/main.py:140)
+ *   cfm_sample_sde, cfm_sde_em_step
+ *                          <- torchsde.sdeint(SDE(model, score_model), x0, ts, dt=0.01)  conditional_mnist.ipynb cells 11-12
+ *   cfm_ddpm_em_step       <- em_step                        AD/image_diffusion/sampling.py:100-111
+ *   cfm_resize_bilinear    <- HyperResolution._sample / downsample_images
+ *                             AD/image_diffusion/likelihoods.py:119-126, mnist/utils_mnist_hy.py:18-28
+ *   cfm_fid_accumulate     <- the mu / Sigma accumulation behind fid.compute_fid / FrechetInceptionDistance.update
+ *                             cifar10/compute_fid.py:92-100, AD/experiments/main.py:261-267, 292-293
  */
 #ifndef CFM_B200_H_
 #define CFM_B200_H_
@@ -41,7 +50,7 @@
 extern "C" {
 #endif
 
-#define CFM_ABI_VERSION 1
+#define CFM_ABI_VERSION 2
 #define CFM_MAX_LEVELS 8
 
 typedef enum cfm_status {
@@ -103,6 +112,7 @@ double  cfm_engine_flops_per_sample(const cfm_engine* e);       /* 2*MAC, conv+l
 int64_t cfm_engine_workspace_bytes(const cfm_engine* e, int32_t batch);
 int32_t cfm_engine_kernel_launches(const cfm_engine* e);        /* launches issued by the last call */
 int32_t cfm_engine_tensor_core_convs(const cfm_engine* e);      /* conv ops routed to tcgen05 per NFE */
+int32_t cfm_engine_cached_graphs(const cfm_engine* e);          /* captured step graphs held (LRU-bounded)  */
 
 /* One NFE.  x_dev: [B, Cx, H, W] fp32 NCHW.  cond_dev: [B, Cc, H, W] fp32 NCHW or NULL
  * (Cx + Cc == in_channels; cond is concatenated after x on the channel axis, as the
@@ -215,6 +225,48 @@ int cfm_make_box_condition(float* cond_dev, const float* images_dev, const int32
 
 /* clip(x*127.5+128, 0, 255) -> uint8 (compute_fid.py:87). */
 int cfm_quantize_u8(uint8_t* out_dev, const float* x_dev, int64_t n, void* stream);
+
+/* ONE launch of a DDPM reverse-chain step, for a caller that evaluates the eps network itself between the launches -
+ * the reference's Network seam is any callable `eps_model(xi, i)` (sde_diffusion.py:11; main.py:140 passes a lambda).
+ * Same tables / options / noise layout / Philox streams as cfm_sample_ddpm, so a chain driven through this entry point
+ * with the engine's own forward as the network equals cfm_sample_ddpm bit for bit.
+ *   phase 0      mask blend of step `chain_index` (Replacement, before the network call; no-op otherwise)
+ *   phase 1      posterior draw: x <- c1*clip(a x - b eps) + c2 x + sigma z           (sampling.py:59-67)
+ *   phase 2 + c  Langevin corrector c: eps is the network re-evaluated on the current x   (sampling.py:113-121, 241-250)
+ * With opt->n_corrector == 0 the phase-1 launch of step 0 applies the final clip, else the last corrector of step 0. */
+int cfm_ddpm_step(float* x_dev, const float* eps_dev, const float* condition_dev, const cfm_ddpm_tables* tables,
+                  const cfm_ddpm_options* opt, int32_t chain_index, int32_t phase, const float* noise_dev,
+                  uint64_t seed, int64_t n, void* stream);
+
+/* Euler-Maruyama steps.
+ * cfm_sde_em_step:  x <- x + (drift + score) dt + sigma sqrt(dt) z   - the "euler" scheme torchsde.sdeint applies to
+ *   SDE.f = flow + score, SDE.g = sigma (conditional_mnist.ipynb cells 11-12); score_dev may be NULL.
+ * cfm_ddpm_em_step: the reverse VP-SDE step `em_step` of the Amortized sampler (sampling.py:100-111 with
+ *   sde_diffusion.py:170-205): score = -eps / sigma_t, drift = -0.5 x x - beta_t score (the reference's DDPM.drift
+ *   swaps the arguments of unsqueeze_like and so multiplies by x instead of beta_t; reproduced as is),
+ *   x <- x - dt drift + sqrt(beta_t) z sqrt(dt).
+ * z: noise_dev (n injected normals) or Philox(seed, stream_id). */
+int cfm_sde_em_step(float* x_dev, const float* drift_dev, const float* score_dev, float dt, float sigma,
+                    const float* noise_dev, uint64_t seed, uint32_t stream_id, int64_t n, void* stream);
+int cfm_ddpm_em_step(float* x_dev, const float* eps_dev, float beta_t, float sigma_t, double dt, const float* noise_dev,
+                     uint64_t seed, uint32_t stream_id, int64_t n, void* stream);
+/* Whole fixed-step Euler-Maruyama loop over two engines (flow + score networks; `score` may be NULL): for k in
+ * [0, n_steps): x += (drift(t[k], x, y) + score(t[k], x, y)) dt[k] + sigma sqrt(dt[k]) z_k.  x_dev in place.
+ * noise_dev: [n_steps, B*C*H*W] or NULL (Philox(seed), stream = k). */
+int cfm_sample_sde(cfm_engine* drift, cfm_engine* score, int32_t batch, float* x_dev, const int64_t* y_dev,
+                   const float* t_host, const float* dt_host, int32_t n_steps, float sigma, const float* noise_dev,
+                   uint64_t seed, void* stream);
+
+/* F.interpolate(mode="bilinear", align_corners=False) on `planes` = B*C fp32 planes of h_in x w_in -> h_out x w_out:
+ * HyperResolution._sample (likelihoods.py:119-126), downsample_images (mnist/utils_mnist_hy.py:18-28) and the
+ * low-res -> full-size upsample of SuperResModelWrapper. */
+int cfm_resize_bilinear(float* out_dev, const float* in_dev, int64_t planes, int32_t h_in, int32_t w_in,
+                        int32_t h_out, int32_t w_out, void* stream);
+
+/* FID sufficient statistics (cifar10/compute_fid.py:92-100; AD/experiments/main.py:261-267, 292-293): running fp64
+ * sums over feature rows, sum_dev[dim] += sum_i f_i, outer_dev[dim][dim] += sum_i f_i f_i^T; feats_dev: [n, dim] fp32.
+ * Deterministic (one accumulating thread per output element, row order).  The sums are what ranks all-reduce. */
+int cfm_fid_accumulate(double* sum_dev, double* outer_dev, const float* feats_dev, int64_t n, int32_t dim, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,25 @@ def euler_cfg_trajectory(f_cond: Callable, f_uncond: Callable, w: float, x: torc
     return euler_trajectory(f, x, t_span)
 
 
+def sde_euler_maruyama(drift: Callable, score, x: torch.Tensor, ts: torch.Tensor, dt: float, sigma: float, noise: Callable) -> torch.Tensor:
+    """``torchsde.sdeint(sde, y0, ts, dt=dt)`` with the default scheme of a diagonal Ito SDE ("euler": Euler-Maruyama) for
+    the SF2M sampler of conditional_mnist.ipynb cells 11-12: ``f = flow(t, y) + score(t, y)``, ``g = sigma``.
+    torchsde is not under /root/reference and is not pinned: PARITY UNPINNED; the published scheme is restated -
+    fixed steps ``dt`` from ts[0] to ts[-1] (last one shortened), ``y <- y + f dt + g dW`` with ``dW = sqrt(dt) z`` and
+    z drawn by ``noise(shape)`` once per step (torchsde's BrownianInterval draws are replaced by injected normals)."""
+    import math
+    t0, t1 = float(ts[0]), float(ts[-1])
+    n_steps = max(int(math.ceil((t1 - t0) / dt - 1e-9)), 0)
+    for k in range(n_steps):
+        t = t0 + k * dt
+        h = torch.tensor(min(dt, t1 - t), dtype=torch.float32)
+        tt = torch.tensor(t, dtype=torch.float32)
+        f = drift(tt, x) if score is None else drift(tt, x) + score(tt, x)
+        dw = noise(x.shape) * torch.sqrt(h)
+        x = (x + f * h) + sigma * dw
+    return x
+
+
 def euler_time_grid(t_span: torch.Tensor) -> Tuple[List[float], List[float]]:
     """The (t_k, dt_k) pairs the loop above feeds to f / uses in the update."""
     t = t_span[0]

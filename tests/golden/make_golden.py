@@ -71,8 +71,33 @@ def chains():
     np.savez_compressed(os.path.join(HERE, "ddpm_chains.npz"), **d)
 
 
+def sde_steps():
+    """``em_step`` of the Amortized sampler (sampling.py:100-111) is a closure that the reference never calls; its body is
+    evaluated here with the reference's own DDPM methods (backward_drift / backward_diffusion / score_from_noise)."""
+    ref = load_reference()
+    m = ref.sde_diffusion.DDPM(1000)
+    rs = np.random.RandomState(7)
+    xi = torch.from_numpy(rs.standard_normal((4, 3, 8, 8)).astype(np.float32))
+    noise_hat = torch.from_numpy(rs.standard_normal((4, 3, 8, 8)).astype(np.float32))
+    z = torch.from_numpy(rs.standard_normal((4, 3, 8, 8)).astype(np.float32))
+    d = {"em.x": xi.numpy(), "em.eps": noise_hat.numpy(), "em.z": z.numpy()}
+    for i in (0, 1, 500, 999):
+        batched_times = torch.full((4,), i, dtype=torch.long)
+        score_fn = m.score_from_noise
+        drift = m.backward_drift(score_fn, xi, noise_hat, batched_times)
+        diffusion = m.backward_diffusion(batched_times)
+        dt = 1 / m.Ns
+        x = xi - dt * drift + diffusion.unsqueeze(1).unsqueeze(2).unsqueeze(3) * z * np.sqrt(dt)
+        d[f"em.out{i}"] = x.numpy()
+    np.savez_compressed(os.path.join(HERE, "sde_steps.npz"), **d)
+    print("em_step golden written")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sde":
+        return sde_steps()
     chains()
+    sde_steps()
     ref = load_reference()
     assert ref is not None, "/root/reference is required to generate golden vectors"
     torch.set_num_threads(os.cpu_count())

@@ -19,7 +19,8 @@ def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ("cfm_engine_create", "cfm_engine_destroy", "cfm_engine_forward", "cfm_sample_euler",
               "cfm_sample_ddpm", "cfm_rk_combine", "cfm_rk_error_sumsq", "cfm_make_box_condition",
-              "cfm_quantize_u8", "cfm_last_error"):
+              "cfm_quantize_u8", "cfm_last_error", "cfm_ddpm_step", "cfm_sample_sde", "cfm_sde_em_step", "cfm_ddpm_em_step",
+              "cfm_resize_bilinear", "cfm_fid_accumulate", "cfm_engine_op_info"):
         assert s in syms
 
 
@@ -27,7 +28,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/cfm_b200.h but not exported"
-    assert lib.cfm_abi_version() == 1
+    assert lib.cfm_abi_version() == 2
 
 
 def test_python_binding_covers_the_header(pkg):
@@ -60,3 +61,7 @@ def test_null_arguments_are_rejected_not_crashed(pkg):
     assert lib.cfm_engine_forward(None, 1, None, None, None, 0.0, None, None, None) != 0
     assert lib.cfm_quantize_u8(None, None, 0, None) != 0
     assert lib.cfm_last_error(None) is not None
+    assert lib.cfm_ddpm_step(None, None, None, None, None, 0, 0, None, 0, 0, None) != 0
+    assert lib.cfm_resize_bilinear(None, None, 0, 1, 1, 1, 1, None) != 0
+    assert lib.cfm_fid_accumulate(None, None, None, 0, 1, None) != 0
+    assert lib.cfm_sample_sde(None, None, 1, None, None, None, None, 0, 0.1, None, 0, None) != 0

@@ -93,8 +93,8 @@ def test_ddpm_buffers_match_oracle(pkg):
 def test_unsupported_paths_raise(pkg):
     with pytest.raises(NotImplementedError):
         pkg.ReconstructionGuidance(gamma=10.0, start_fraction=1.0, update_rule="before", n_corrector=0, delta=0.1)
-    with pytest.raises(TypeError):
-        pkg.get_conditional_sample_fn(lambda x, i: x, pkg.DDPM(10), pkg.Replacement(), pkg.InPainting(14, -2.0))
+    with pytest.raises(TypeError):      # Replacement needs a likelihood that marks the holes (pad_value)
+        pkg.get_conditional_sample_fn(lambda x, i: x, pkg.DDPM(10), pkg.Replacement(), pkg.HyperResolution(7, 7))
     with pytest.raises(NotImplementedError):
         pkg.NeuralODE(lambda t, x: x, solver="rk4")
 
@@ -166,3 +166,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+
+
+def test_vectorised_box_draw_consumes_the_generator_like_the_reference_loop(pkg):
+    """InPainting.sample_boxes draws all (h, w) pairs with one torch.randint(lo, hi, (B, 2)); the reference draws h then
+    w per sample with scalar calls (likelihoods.py:49-53, 78-87).  Same global CPU generator, same values, same order,
+    and the same generator state afterwards."""
+    lk = pkg.InPainting(patch_size=20, pad_value=-2.0)
+    for B in (1, 7, 4096):
+        torch.manual_seed(123)
+        loop = torch.tensor([[int(torch.randint(5, 64 - 20 - 5, size=())), int(torch.randint(5, 64 - 20 - 5, size=()))]
+                             for _ in range(B)], dtype=torch.int32)
+        after_loop = torch.rand(1)
+        torch.manual_seed(123)
+        vec = lk.sample_boxes(B, 64)
+        after_vec = torch.rand(1)
+        assert vec.dtype == torch.int32 and tuple(vec.shape) == (B, 2)
+        assert torch.equal(vec, loop) and torch.equal(after_loop, after_vec)
+    assert tuple(lk.sample_boxes(0, 64).shape) == (0, 2)
+    with pytest.raises(RuntimeError):      # SURVEY F9: 28 px with the default patch has an empty range
+        pkg.InPainting(patch_size=20, pad_value=-2.0).sample_boxes(2, 28)
+
+
+def test_plain_callable_eps_models_are_accepted(pkg):
+    """The sampler factories take any callable (sde_diffusion.py:11 Network); construction needs no GPU."""
+    ddpm = pkg.DDPM(10)
+    f = pkg.get_prior_sample_fn(lambda xi, i: xi, ddpm, None, None)
+    g2 = pkg.get_conditional_sample_fn(lambda xi, i: xi, ddpm, pkg.Replacement(), pkg.InPainting(4, -2.0))
+    assert callable(f) and callable(g2)
+    with pytest.raises(TypeError):
+        pkg.get_prior_sample_fn(3, ddpm, None, None)

@@ -148,3 +148,38 @@ def test_condition_builders_match_reference_likelihoods():
     torch.manual_seed(8)
     assert np.array_equal(D.outpainting_condition(imgs, 10, -2.0).numpy(), g["lik.outpaint"])
     assert np.array_equal(D.hyperresolution_condition(imgs, (7, 7)).numpy(), g["lik.hyperres"])
+
+
+def test_em_step_matches_reference_methods():
+    """oracle.ddpm.em_step against the body of sampling.py:100-111 evaluated with the reference's own DDPM methods
+    (tests/golden/sde_steps.npz, generated by make_golden.py sde): bit for bit."""
+    g = np.load(os.path.join(GOLD, "sde_steps.npz"))
+    x, eps, z = (torch.from_numpy(g[k]) for k in ("em.x", "em.eps", "em.z"))
+    for i in (0, 1, 500, 999):
+        got = D.em_step(1000, x, eps, i, z)
+        assert np.array_equal(got.numpy(), g[f"em.out{i}"]), i
+
+
+def test_fid_oracle_known_answers():
+    """Frechet distance restatement: identical statistics -> 0; a pure mean shift -> |d|^2; commuting diagonal
+    covariances -> closed form sum (sqrt(a) - sqrt(b))^2."""
+    rs = np.random.RandomState(0)
+    f = rs.standard_normal((500, 6))
+    mu, cov = D.fid_statistics(f)
+    assert abs(D.frechet_distance(mu, cov, mu, cov)) < 1e-8
+    d = rs.standard_normal(6)
+    assert abs(D.frechet_distance(mu + d, cov, mu, cov) - d.dot(d)) < 1e-8
+    a, b = rs.uniform(0.5, 2, 6), rs.uniform(0.5, 2, 6)
+    want = float(((np.sqrt(a) - np.sqrt(b)) ** 2).sum())
+    assert abs(D.frechet_distance(mu, np.diag(a), mu, np.diag(b)) - want) < 1e-8
+
+
+def test_sde_euler_maruyama_closed_form():
+    """Oracle Euler-Maruyama on dx = -x dt + sigma dW with the noise switched off reduces to Euler on dx = -x dt:
+    x_n = x_0 (1 - dt)^n; with noise on, the injected normals enter as sigma * sqrt(dt) * z."""
+    from oracle import integrators as I
+    x0 = torch.ones(3, 2)
+    out = I.sde_euler_maruyama(lambda t, x: -x, None, x0, torch.tensor([0.0, 1.0]), 0.01, 0.0, lambda s: torch.zeros(s))
+    assert torch.allclose(out, x0 * (1 - 0.01) ** 100, atol=1e-5)
+    out = I.sde_euler_maruyama(lambda t, x: 0 * x, lambda t, x: 0 * x, x0, torch.tensor([0.0, 0.02]), 0.01, 0.5, lambda s: torch.ones(s))
+    assert torch.allclose(out, x0 + 2 * 0.5 * 0.1, atol=1e-6)
