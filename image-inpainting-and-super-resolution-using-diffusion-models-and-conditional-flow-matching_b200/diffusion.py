@@ -79,16 +79,19 @@ class DDPM(nn.Module):
         reg("posterior_mean_coef1", betas * torch.sqrt(ac_prev) / (1.0 - ac))
         reg("posterior_mean_coef2", (1.0 - ac_prev) * torch.sqrt(self.alphas) / (1.0 - ac))
 
-    def model_time(self) -> torch.Tensor:
-        """t fed to the U-Net at step i: ``1.0 * i / Ns`` on an int64 tensor (main.py:140)."""
-        return (1.0 * torch.arange(self.Ns, dtype=torch.long)) / self.Ns
+    def model_time(self, device=None) -> torch.Tensor:
+        """t fed to the U-Net at step i: ``1.0 * i / Ns`` on an int64 tensor (main.py:140), evaluated on ``device`` - where
+        the reference's lambda evaluates it.  (torch's CUDA division by a Python scalar multiplies by the fp32 reciprocal,
+        its CPU division divides: the two differ in the last bit for some i, and a fused chain must feed the U-Net exactly
+        the t the caller's own ``eps_model(xi, i)`` would.)"""
+        return ((1.0 * torch.arange(self.Ns, dtype=torch.long, device=device)) / self.Ns).cpu()
 
-    def tables(self) -> dict:
+    def tables(self, device=None) -> dict:
         names = ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
                  "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
                  "posterior_log_variance_clipped")
         tb = {n: getattr(self, n).detach().cpu() for n in names}
-        tb["model_time"] = self.model_time()
+        tb["model_time"] = self.model_time(device)
         return tb
 
     # algebra kept for API compatibility (host/torch tensors; the fused kernel is used by the samplers)
@@ -441,7 +444,7 @@ def get_prior_sample_fn(eps_model, ddpm: DDPM, conditioning=None, likelihood=Non
         if net is None:
             return _stepwise_chain(eps_model, ddpm, xT, "amortized" if amortized else "prior", condition=cond,
                                    noise=_noise_tensor(noise, ddpm.Ns, xT), seed=s_)
-        return net.engine().sample_ddpm(xT, ddpm.tables(), mode="amortized" if amortized else "prior", condition=cond,
+        return net.engine().sample_ddpm(xT, ddpm.tables(xT.device), mode="amortized" if amortized else "prior", condition=cond,
                                         noise=_noise_tensor(noise, ddpm.Ns, xT), seed=s_, use_graph=use_graph)
 
     return sample
@@ -480,7 +483,7 @@ def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *
             net = backend()
             if net is None:
                 return _stepwise_chain(eps_model, ddpm, xT, none_value=none_value, **kw)
-            return net.engine().sample_ddpm(xT, ddpm.tables(), use_graph=use_graph, **kw)
+            return net.engine().sample_ddpm(xT, ddpm.tables(xT.device), use_graph=use_graph, **kw)
         return sample
 
     if isinstance(conditioning, Replacement):
@@ -498,7 +501,7 @@ def get_conditional_sample_fn(eps_model, ddpm: DDPM, conditioning, likelihood, *
             net = backend()
             if net is None:
                 return _stepwise_chain(eps_model, ddpm, xT, **kw)
-            return net.engine().sample_ddpm(xT, ddpm.tables(), use_graph=use_graph, **kw)
+            return net.engine().sample_ddpm(xT, ddpm.tables(xT.device), use_graph=use_graph, **kw)
         return sample
 
     raise NotImplementedError(f"no engine sampler for conditioning {type(conditioning).__name__}")
