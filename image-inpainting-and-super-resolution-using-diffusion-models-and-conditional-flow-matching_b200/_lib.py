@@ -14,6 +14,7 @@ MAX_LEVELS = 8
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+FLAG_SEPARATE_GROUPNORM = 1
 EULER_COND_DRIFT = 1
 EULER_USE_GRAPH = 2
 DDPM_PRIOR, DDPM_REPLACEMENT, DDPM_AMORTIZED = 0, 1, 2
@@ -28,7 +29,7 @@ class UNetConfigC(C.Structure):
         ("num_classes", C.c_int32), ("num_heads", C.c_int32), ("num_head_channels", C.c_int32),
         ("num_heads_upsample", C.c_int32), ("use_scale_shift_norm", C.c_int32),
         ("resblock_updown", C.c_int32), ("use_new_attention_order", C.c_int32),
-        ("precision", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("precision", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -416,7 +416,7 @@ static EncodeTiledFn g_flash_encode = nullptr;
 
 bool attn_flash_supported(const Engine& e, const Op& op) {
   if (!e.bf16 || op.kind != OP_ATTN) return false;
-  const char* off = getenv("CFM_DISABLE_FLASH_ATTN");
+  const char* off = tuning_env("CFM_DISABLE_FLASH_ATTN");
   if (off && off[0] == '1') return false;
   return (op.ch == 32 || op.ch == 64) && op.Cin % 8 == 0;
 }
@@ -462,7 +462,7 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.B = B;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
-  static const bool no64 = [] { const char* v = getenv("CFM_DISABLE_FLASH64"); return v && v[0] == '1'; }();
+  static const bool no64 = [] { const char* v = tuning_env("CFM_DISABLE_FLASH64"); return v && v[0] == '1'; }();
   if (T > 128 && !no64) {
     // long sequences: 64-key blocks, 3-4 CTAs per SM
     auto it64 = pl.maps64.find(B);

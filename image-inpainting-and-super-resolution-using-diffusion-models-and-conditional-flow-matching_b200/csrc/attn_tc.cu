@@ -202,7 +202,7 @@ static EncodeTiledFn g_attn_encode = nullptr;
 
 bool attn_tc_supported(const Engine& e, const Op& op) {
   if (!e.bf16 || op.kind != OP_ATTN) return false;
-  const char* off = getenv("CFM_DISABLE_TC_ATTN");
+  const char* off = tuning_env("CFM_DISABLE_TC_ATTN");
   if (off && off[0] == '1') return false;
   return op.ch == AT_D && op.Hin * op.Win == AT_T;
 }
@@ -239,7 +239,7 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.out = (bf16*)tensor_ptr(e, op.out, B);
   {
     // two CTAs per SM, two CTAs (query tiles) per (sample, head): one wave covers sm_count pairs
-    static const int pf = [] { const char* v = getenv("CFM_ATTN_PREFETCH"); return v ? atoi(v) : 1; }();
+    static const int pf = [] { const char* v = tuning_env("CFM_ATTN_PREFETCH"); return v ? atoi(v) : 1; }();
     p.pf_db = pf * e.sm_count / op.heads; p.pf_dh = pf * e.sm_count % op.heads;
   }
   if (B > 65535) { e.err = "attn_tc: batch too large for the grid"; return CFM_ERR_INVALID; }

@@ -208,7 +208,7 @@ static EncodeTiledFn g_wide_encode = nullptr;
 
 bool attn_wide_supported(const Engine& e, const Op& op) {
   if (!e.bf16 || op.kind != OP_ATTN) return false;
-  const char* off = getenv("CFM_DISABLE_WIDE_ATTN");
+  const char* off = tuning_env("CFM_DISABLE_WIDE_ATTN");
   if (off && off[0] == '1') return false;
   return op.ch > 64 && op.ch <= 512 && op.ch % 64 == 0 && op.Hin * op.Win <= AW_T;
 }

@@ -1004,7 +1004,7 @@ static int get_encode(Engine& e) {
   return 0;
 }
 
-static bool env_off(const char* name) { const char* v = getenv(name); return v && v[0] == '1'; }
+static bool env_off(const char* name) { const char* v = tuning_env(name); return v && v[0] == '1'; }
 
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -1053,7 +1053,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   const int Cout = op.out_is_output ? 32 : op.Cout;      // padded rows of W are zero
   pl->cout_pad = Cout;
   pl->block_n = pick_block_n(Cout);
-  static const int pair_min_n = [] { const char* v = getenv("CFM_TC_PAIR_MIN_N"); return v ? atoi(v) : 128; }();
+  static const int pair_min_n = [] { const char* v = tuning_env("CFM_TC_PAIR_MIN_N"); return v ? atoi(v) : 128; }();
   // N >= 128: CTA pair (half the weight tile per SM).  At N = 128 each CTA of the pair also takes two 128-row M-halves
   // per weight tile (a 512 x 128 pair tile): the K-iteration stays 512 cycles long (a 256-cycle K-iteration is
   // shorter than the issue loop) and the shared-memory bytes per MMA cycle drop from 182 to ~135 of the 128 B/clk port.
@@ -1092,7 +1092,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   // (32 sectors of 32 different lines per instruction); they stage the tile in shared memory and let TMA write it.
   // The staging boxes come out of the ring space, which these layers do not need.
   {
-    static const int max_k = [] { const char* v = getenv("CFM_TC_TMA_STORE_MAX_K"); return v ? atoi(v) : 8; }();
+    static const int max_k = [] { const char* v = tuning_env("CFM_TC_TMA_STORE_MAX_K"); return v ? atoi(v) : 8; }();
     const int tk_all = eks * eks * (Cin / kc) + op.Cskip / kc;
     const bool halves_ok = pl->mh == 1 || pl->bn % 2 == 0 || (pl->bn == 1 && pl->bh % 2 == 0);
     if (pl->pair && !op.out_is_output && !op.out_f32 && !op.ups && pl->block_n % 64 == 0 && Cout % 64 == 0 && tk_all <= max_k &&
@@ -1109,10 +1109,10 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   // lie in one sample, one N tile must span all channels and a group must be 4, 8, 16 or 32 channels.
   // the two-pass epilogue holds an accumulator stage ~2x longer: it only pays where the K loop of a tile is long enough to
   // cover it (measured: wins from 36 K-iterations, loses at 18)
-  static const int gn_min_k = [] { const char* v = getenv("CFM_TC_GN_MIN_K"); return v ? atoi(v) : 0; }();
+  static const int gn_min_k = [] { const char* v = tuning_env("CFM_TC_GN_MIN_K"); return v ? atoi(v) : 0; }();
   op.gn_fused = false;
   if (op.gn_request && pl->pair && !pl->tma_store && !op.ups && !op.out_is_output && !op.out_f32 && op.res0 < 0 && Cout == op.Cout &&
-      pl->block_n == Cout && Cout <= TC_GN_MAX_COUT && pl->valid_rows == rows && pl->bw == Wg && !env_off("CFM_DISABLE_TC_GN") &&
+      pl->block_n == Cout && Cout <= TC_GN_MAX_COUT && pl->valid_rows == rows && pl->bw == Wg && !(e.cfg.flags & CFM_FLAG_SEPARATE_GROUPNORM) &&
       eks * eks * (Cin / kc) + op.Cskip / kc >= gn_min_k) {
     const int cpg = Cout / 32, HW = Hg * Wg;
     const bool cpg_ok = cpg >= 4 && pow2(cpg) && cpg <= 32;

@@ -218,15 +218,7 @@ static int add_attention(Engine& e, const std::string& p, Cur x, int heads, Cur*
   Op op; op.kind = OP_ATTN; op.name = p + ".attention"; op.out = att;
   op.heads = heads; op.ch = C / heads; op.Cin = C; op.Hin = x.H; op.Win = x.W;
   op.flops = 2.0 * 2.0 * (double)(x.H * x.W) * (x.H * x.W) * C;
-  if (attn_qkv_shape_ok(e, C, heads, x.H * x.W)) {
-    // q, k, v are projected inside the attention kernel: no qkv conv, no [B, T, 3C] tensor
-    const float *w = nullptr, *b = nullptr;
-    if ((rc = fetch(e, p + ".qkv.weight", (int64_t)3 * C * C, &w))) return rc;
-    if ((rc = fetch(e, p + ".qkv.bias", 3 * C, &b))) return rc;
-    op.name = p + ".qkv+attention"; op.src0 = a;
-    op.flops += 2.0 * (double)(x.H * x.W) * C * 3 * C;
-    if ((rc = attn_qkv_prepare(e, op, w, b))) return rc;
-  } else {
+  {
     const int qkv = new_tensor(e, 3 * C, x.H, x.W);
     if ((rc = add_conv(e, p + ".qkv", p + ".qkv", 1, 1, 0, a, -1, false, C, x.H, x.W, 3 * C, "", -1, -1, 0, -1, -1, -1, qkv, false))) return rc;
     op.src0 = qkv;
@@ -278,7 +270,7 @@ static int add_stem_tc(Engine& e, int Cin, int S, int Cout, int out, bool* done)
 // (fp32, 32 per pixel) and (2) a gather that sums each pixel's 3x3 neighbourhood of them.  *done stays false (and
 // nothing is added) when the shapes do not fit.
 static int add_head_tc(Engine& e, int a, Cur h, int Cout, bool* done) {
-  const char* off = getenv("CFM_DISABLE_TC_HEAD_TAPS");
+  const char* off = tuning_env("CFM_DISABLE_TC_HEAD_TAPS");
   // 2 or 3 output channels fill the 32-wide row of partial products (18 / 27 of 32); with one channel (MNIST) the fp32
   // row is mostly padding and the direct 3x3 conv measured the same
   if ((off && off[0] == '1') || 9 * Cout > 32 || 9 * Cout <= 16) return 0;
@@ -487,7 +479,6 @@ static int ensure_batch(Engine& e, int B) {
     tc_conv_release(e);   // tensor maps hold arena addresses
     attn_tc_release(e);
     attn_flash_release(e);
-    attn_qkv_release(e);
     attn_wide_release(e);
     drop_graphs(e);
     const size_t bytes = (size_t)e.arena_elems_per_sample * B * esize(e);
@@ -584,12 +575,6 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_GN: {
-        if (e.bf16 && gn_stream_supported(e, op)) {       // large maps: persistent TMA-pipelined kernel
-          int rc = gn_stream_launch(e, op, B, st);
-          if (rc) return rc;
-          e.launches++;
-          break;
-        }
         if (e.bf16 && gn_bf16_supported(e, op)) {
           int rc = gn_bf16_launch(e, op, B, st);
           if (rc) return rc;
@@ -643,12 +628,6 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         break;
       }
       case OP_ATTN: {
-        if (op.fq) {
-          int rc = attn_qkv_launch(e, op, B, st);
-          if (rc) return rc;
-          e.launches++;
-          break;
-        }
         if (attn_tc_supported(e, op)) {
           int rc = attn_tc_launch(e, op, B, st);
           if (rc) return rc;
@@ -926,7 +905,7 @@ int cfm_engine_profile_get(const cfm_engine* h, int32_t i, char* name, int32_t n
   if (kind) {
     if (op.kind == OP_CONV) *kind = op.tc ? 4 : 0;
     else if (op.kind == OP_IM2COL || op.kind == OP_HEAD_GATHER) *kind = 2;
-    else if (op.kind == OP_ATTN) *kind = (op.fq || attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op) || attn_wide_supported(h->impl, op)) ? 5 : 3;
+    else if (op.kind == OP_ATTN) *kind = (attn_tc_supported(h->impl, op) || attn_flash_supported(h->impl, op) || attn_wide_supported(h->impl, op)) ? 5 : 3;
     else *kind = (int)op.kind;
   }
   if (ms) *ms = h->impl.prof_ms[i];

@@ -10,6 +10,17 @@
 
 namespace cfm {
 
+// A/B switches of the kernels (profiles/README.md) exist only in tuning builds (-DCFM_TUNING, `CFM_BUILD_TUNING=1` for
+// __graft_entry__.build): the shipped library reads no environment variable and runs one code path.
+inline const char* tuning_env(const char* name) {
+#ifdef CFM_TUNING
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 struct HostTensor { const float* data; int64_t numel; };
 
 // An activation tensor of the plan: NHWC [B, H, W, C]; `off` is a per-sample element offset
@@ -24,7 +35,6 @@ struct TensorDesc {
 enum OpKind { OP_CONV = 0, OP_GN = 1, OP_RESAMPLE = 2, OP_ATTN = 3, OP_IM2COL = 4, OP_HEAD_GATHER = 5 };
 
 struct TcConvPlan;   // tcgen05 implicit-GEMM lowering of a conv op (conv_tc.cu)
-struct AttnQkvPlan;  // attention with the qkv projection fused in (attn_qkv.cu)
 
 struct Op {
   OpKind kind;
@@ -45,7 +55,6 @@ struct Op {
   int heads = 0, ch = 0;
   // tensor-core lowering (bf16 mode), null when the generic kernel runs this op
   TcConvPlan* tc = nullptr;
-  AttnQkvPlan* fq = nullptr;   // attention op that takes the GroupNorm output and projects q, k, v itself
   double flops = 0;        // 2*MAC per sample
   // conv with the following GroupNorm (+SiLU) applied in its epilogue (ResBlock conv1 + out_layers.0; conv_tc.cu, kGN):
   // gn_request is set by the plan (gamma / beta / silu then describe that GroupNorm), gn_fused by tc_conv_prepare.
@@ -123,7 +132,7 @@ struct LaunchCfg {
   }
 };
 inline bool pdl_enabled() {
-  static const bool on = [] { const char* v = getenv("CFM_DISABLE_PDL"); return !(v && v[0] == '1'); }();
+  static const bool on = [] { const char* v = tuning_env("CFM_DISABLE_PDL"); return !(v && v[0] == '1'); }();
   return on;
 }
 
@@ -140,11 +149,6 @@ bool attn_tc_supported(const Engine& e, const Op& op);
 int  attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 void attn_tc_release(Engine& e);
 void attn_tc_forget(Engine& e);
-// attn_qkv.cu
-bool attn_qkv_shape_ok(const Engine& e, int C, int heads, int T);
-int  attn_qkv_prepare(Engine& e, Op& op, const float* w_oi, const float* bias);
-int  attn_qkv_launch(Engine& e, const Op& op, int B, cudaStream_t st);
-void attn_qkv_release(Engine& e);
 // attn_flash.cu
 bool attn_flash_supported(const Engine& e, const Op& op);
 int  attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st);
@@ -164,8 +168,6 @@ struct DeviceOnce {
 };
 
 bool gn_bf16_supported(const Engine& e, const Op& op);
-bool gn_stream_supported(const Engine& e, const Op& op);
-int  gn_stream_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 bool resample_bf16_supported(const Engine& e, const Op& op);
 int  resample_bf16_launch(Engine& e, const Op& op, int B, cudaStream_t st);
 bool head_conv_supported(const Engine& e, const Op& op);

@@ -211,10 +211,10 @@ static GnGeom gn_geometry(const Op& op) {
   g.cpg = C / 32;
   const int base = g.cpg / gcd_i(g.cpg, 8) * 8;        // lcm(cpg, 8): smallest legal slab
   if (base > GN_MAX_SLAB || C % base) return g;
-  static const int target = [] { const char* v = getenv("CFM_GN_ITEM_BYTES"); return v ? atoi(v) : 64 * 1024; }();
+  static const int target = [] { const char* v = tuning_env("CFM_GN_ITEM_BYTES"); return v ? atoi(v) : 64 * 1024; }();
   // slab: a multiple of `base` dividing C, preferably a whole number of 64-byte DRAM bursts per pixel (32 channels;
   // e.g. 96 for C = 384, where 48-channel slabs would straddle bursts) and at most 64 channels when that works
-  static const int pref_slab = [] { const char* v = getenv("CFM_GN_PREF_SLAB"); return v ? atoi(v) : 64; }();
+  static const int pref_slab = [] { const char* v = tuning_env("CFM_GN_PREF_SLAB"); return v ? atoi(v) : 64; }();
   // ... but 128 channels (256-byte rows) when such an item still fits one CTA without a cluster (16x16 maps: -4 %)
   const int pref = (long long)HW * GN_MAX_SLAB * 2 <= target ? std::max(pref_slab, GN_MAX_SLAB) : pref_slab;
   int slab = 0;
@@ -247,7 +247,7 @@ static GnGeom gn_geometry(const Op& op) {
 
 bool gn_bf16_supported(const Engine& e, const Op& op) {
   if (!e.bf16 || op.kind != OP_GN) return false;
-  const char* off = getenv("CFM_DISABLE_FAST_GN");
+  const char* off = tuning_env("CFM_DISABLE_FAST_GN");
   if (off && off[0] == '1') return false;
   const GnGeom g = gn_geometry(op);
   if (!g.ok || g.smem > 200 * 1024) return false;
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 int stem_im2col_launch(Engine& e, const Op& op, int B, const float* x, const float* cond, cudaStream_t st) {
   const int cx = cond ? e.x_channels() : e.cfg.in_channels;
   auto smem_for = [&](int r) { return sizeof(float) * ((size_t)op.Cin * (r + 2) * (op.Win + 2) + op.Cout); };
-  static const int max_rows = [] { const char* v = getenv("CFM_IM2COL_ROWS"); return v ? atoi(v) : 16; }();
+  static const int max_rows = [] { const char* v = tuning_env("CFM_IM2COL_ROWS"); return v ? atoi(v) : 16; }();
   int R = 4;
   for (int r = 32; r >= 4; r >>= 1)
     if (r <= max_rows && r <= std::max(4, op.Hin) && smem_for(r) <= 48 * 1024) { R = r; break; }

@@ -32,6 +32,7 @@ class UNetConfig:
     use_scale_shift_norm: bool = False
     resblock_updown: bool = False
     use_new_attention_order: bool = False
+    fuse_groupnorm: bool = True      # engine option (not a reference hyper-parameter): fold out_layers GroupNorm into conv1
 
     def to_c(self, precision: int) -> _lib.UNetConfigC:
         if len(self.channel_mult) > _lib.MAX_LEVELS or len(self.attention_ds) > _lib.MAX_LEVELS:
@@ -51,6 +52,7 @@ class UNetConfig:
         c.resblock_updown = int(self.resblock_updown)
         c.use_new_attention_order = int(self.use_new_attention_order)
         c.precision = precision
+        c.flags = 0 if self.fuse_groupnorm else _lib.FLAG_SEPARATE_GROUPNORM
         return c
 
 

@@ -123,7 +123,7 @@ class UNetModel(nn.Module):
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
                  use_checkpoint=False, use_fp16=False, num_heads=1, num_head_channels=-1, num_heads_upsample=-1,
                  use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
-                 precision: str = "bf16"):
+                 precision: str = "bf16", fuse_groupnorm: bool = True):
         super().__init__()
         if dims != 2:
             raise NotImplementedError("the engine implements the 2-D U-Net only")
@@ -135,7 +135,7 @@ class UNetModel(nn.Module):
                                  conv_resample=conv_resample, num_classes=num_classes, num_heads=num_heads,
                                  num_head_channels=num_head_channels, num_heads_upsample=num_heads_upsample,
                                  use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
-                                 use_new_attention_order=use_new_attention_order)
+                                 use_new_attention_order=use_new_attention_order, fuse_groupnorm=fuse_groupnorm)
         self.image_size, self.in_channels, self.model_channels = image_size, in_channels, model_channels
         self.out_channels, self.num_classes, self.dropout = out_channels, num_classes, dropout
         self.precision = precision

@@ -87,8 +87,13 @@ typedef struct cfm_unet_config {
   int32_t resblock_updown;
   int32_t use_new_attention_order;
   int32_t precision;            /* cfm_precision */
-  int32_t reserved[7];
+  int32_t flags;                /* CFM_FLAG_* (0 = defaults) */
+  int32_t reserved[6];
 } cfm_unet_config;
+
+/* keep every GroupNorm a pass of its own (by default a ResBlock's out_layers GroupNorm + SiLU is applied in the epilogue
+ * of the block's first conv whenever the tensor-core kernel can hold the statistics of whole samples) */
+#define CFM_FLAG_SEPARATE_GROUPNORM 1
 
 typedef struct cfm_engine cfm_engine;
 

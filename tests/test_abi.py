@@ -36,7 +36,7 @@ def test_python_binding_covers_the_header(pkg):
 
 
 def test_config_struct_layout_matches_header(pkg):
-    # 6 ints + 8 floats + 1 int + 8 ints + 9 ints + 7 reserved
+    # 6 ints + 8 floats + 1 int + 8 ints + 9 ints + flags + 6 reserved
     assert ctypes.sizeof(pkg._lib.UNetConfigC) == 4 * (6 + 8 + 1 + 8 + 9 + 7)
     assert ctypes.sizeof(pkg._lib.DdpmOptionsC) == 4 * 8
 

@@ -20,14 +20,14 @@ def rel_l2(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
 
 
-def build(pkg, cfg, params, precision, dev):
+def build(pkg, cfg, params, precision, dev, **extra):
     m = pkg.UNetModel(image_size=cfg.image_size, in_channels=cfg.in_channels, model_channels=cfg.model_channels,
                       out_channels=cfg.out_channels, num_res_blocks=cfg.num_res_blocks,
                       attention_resolutions=cfg.attention_ds, channel_mult=cfg.channel_mult, num_classes=cfg.num_classes,
                       num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels,
                       num_heads_upsample=cfg.num_heads_upsample, use_scale_shift_norm=cfg.use_scale_shift_norm,
                       resblock_updown=cfg.resblock_updown, use_new_attention_order=cfg.use_new_attention_order,
-                      precision=precision)
+                      precision=precision, **extra)
     m.load_state_dict(params)
     return m.to(dev).eval()
 
@@ -185,39 +185,6 @@ def test_superres_config_runs_on_tensor_core_kernels(pkg, cuda):
     assert r < TOL["bf16"], r
 
 
-def test_fused_qkv_attention_opt_in(pkg, cuda, monkeypatch):
-    # experimental kernel that projects q, k, v inside the attention kernel (CFM_ENABLE_FUSED_QKV=1): kept parity-green
-    monkeypatch.setenv("CFM_ENABLE_FUSED_QKV", "1")
-    cfg, _, _ = GOLDEN_CONFIGS["cifar"]
-    g = np.load(os.path.join(GOLD, "unet_cifar.npz"))
-    params = O.seeded_params(cfg, int(g["seed"]))
-    m = build(pkg, cfg, params, "bf16", cuda)
-    x = torch.from_numpy(g["x"]).to(cuda)
-    names = [r["name"] for r in m.engine().profile_forward(x, 0.5, repeats=1)]
-    assert any(n.endswith("qkv+attention") for n in names)
-    out = m(x, torch.from_numpy(g["t"]).to(cuda)).cpu()
-    assert rel_l2(out, torch.from_numpy(g["out"])) < TOL["bf16"]
-
-
-def test_stream_groupnorm_opt_in(pkg, cuda, monkeypatch):
-    # experimental persistent TMA-pipelined GroupNorm for the large maps (CFM_ENABLE_GN_STREAM=1; slower than the staged
-    # kernel, see gn_stream.cu): same arithmetic, kept parity-green, concat inputs and FiLM included
-    for name in ("cifar", "flowers_ddpm"):
-        cfg, _, _ = GOLDEN_CONFIGS[name]
-        g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
-        params = O.seeded_params(cfg, int(g["seed"]))
-        m = build(pkg, cfg, params, "bf16", cuda)
-        x, t = torch.from_numpy(g["x"]).to(cuda), torch.from_numpy(g["t"]).to(cuda)
-        base = m(x, t).cpu()
-        monkeypatch.setenv("CFM_ENABLE_GN_STREAM", "1")
-        out = m(x, t).cpu()
-        monkeypatch.delenv("CFM_ENABLE_GN_STREAM")
-        assert rel_l2(out, torch.from_numpy(g["out"])) < TOL["bf16"]
-        d = rel_l2(out, base)
-        print(f"stream GroupNorm vs staged GroupNorm [{name}]: rel-L2 = {d:.3e}")
-        assert d < TOL["bf16"]          # other summation order -> different bf16 roundings downstream, same tolerance
-
-
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
 def test_engines_on_two_devices_in_one_process(pkg):
     # kernel attributes (dynamic shared memory) are per device context: a second engine on another GPU of the same
@@ -268,10 +235,10 @@ def test_cifar_nfe_at_benchmarked_batch(pkg, cuda, B):
 
 
 @pytest.mark.parametrize("name,batch", [("cifar", 5), ("flowers_ddpm", 2), ("tiny_neworder", 7)])
-def test_groupnorm_folded_into_conv_epilogue(pkg, cuda, monkeypatch, name, batch):
+def test_groupnorm_folded_into_conv_epilogue(pkg, cuda, name, batch):
     # default path: a ResBlock's out_layers.0/1 (GroupNorm + SiLU) runs in the epilogue of its first conv (conv_tc2_kernel
     # <.., true>: statistics from the fp32 accumulators, samples that span several CTA tiles exchange partial sums through
-    # L2); CFM_DISABLE_TC_GN=1 keeps the separate GroupNorm pass.  Both must sit within the bf16 bar of the reference
+    # L2); fuse_groupnorm=False (CFM_FLAG_SEPARATE_GROUPNORM) keeps the separate GroupNorm pass.  Both must sit within the bf16 bar of the reference
     # golden and close to each other.  cifar covers 32x32 (4 tiles per sample), 16x16 (2), 8x8 and 4x4 maps (2 / 8 samples
     # per tile); flowers uses FiLM and must NOT fold; batch position must not matter (ragged tail tiles included).
     cfg, _, _ = GOLDEN_CONFIGS[name]
@@ -286,10 +253,8 @@ def test_groupnorm_folded_into_conv_epilogue(pkg, cuda, monkeypatch, name, batch
     names = [r["name"] for r in m.engine().profile_forward(x, 0.5, repeats=1)]
     n_folded = sum("+out_layers.0" in n for n in names)
     assert torch.equal(m(x, t).cpu(), fused)             # a second evaluation (next epoch of the exchange flags): same bits
-    monkeypatch.setenv("CFM_DISABLE_TC_GN", "1")
-    m2 = build(pkg, cfg, params, "bf16", cuda)
+    m2 = build(pkg, cfg, params, "bf16", cuda, fuse_groupnorm=False)
     plain = m2(x, t).cpu()
-    monkeypatch.delenv("CFM_DISABLE_TC_GN")
     names2 = [r["name"] for r in m2.engine().profile_forward(x, 0.5, repeats=1)]
     assert not any("+out_layers.0" in n for n in names2) and len(names2) == len(names) + n_folded
     if name == "cifar":
