@@ -105,6 +105,8 @@ struct TcParams {
   int gn_ctas;                      // CTA tiles per sample (> 1: partial sums are exchanged through L2, see the kernel)
   int gn_hw;                        // pixels per sample
   int gn_silu;
+  bf16* out2;                       // dual output: `out` receives the un-normalised tile as well (a block output that is both
+                                    // a residual / skip operand and the input of the next GroupNorm), `out2` the normalised one
   uint2* gn_exch;                   // [B][gn_ctas][32][2]: {sum | sum of squares, epoch} of every group over one CTA tile
   const unsigned* gn_epoch;         // device counter, bumped once per NFE (setup_rows_kernel): marks the words of this NFE
 };
@@ -208,7 +210,15 @@ __device__ __forceinline__ void epi_bias_emb(const TcParams& p, const EpiRow& r,
   }
 }
 // 32 fp32 -> bf16, this lane's 64 B of its output row: two full 32 B sectors per store instruction
-__device__ __forceinline__ void epi_store_bf16(const TcParams& p, const EpiRow& r, int cg, const float (&f)[32]) {
+__device__ __forceinline__ void epi_add_res(float (&f)[32], const uint4 (&res)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
+  }
+}
+__device__ __forceinline__ void epi_store_bf16(const TcParams& p, const EpiRow& r, int cg, const float (&f)[32], bf16* dst) {
   uint4 o[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -216,7 +226,7 @@ __device__ __forceinline__ void epi_store_bf16(const TcParams& p, const EpiRow& 
 #pragma unroll
     for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
   }
-  bf16* op = p.out + r.pix * p.Cout + cg;
+  bf16* op = dst + r.pix * p.Cout + cg;
   stg256(op, o[0], o[1]);
   stg256(op + 16, o[2], o[3]);
 }
@@ -244,15 +254,8 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const EpiRow& r, i
              make_uint4(__float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]), __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7])));
     return;
   }
-  if (p.res0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat162* rb = (const __nv_bfloat162*)&res[j];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(rb[q]); f[8 * j + 2 * q] += t2.x; f[8 * j + 2 * q + 1] += t2.y; }
-    }
-  }
-  epi_store_bf16(p, r, cg, f);
+  if (p.res0) epi_add_res(f, res);
+  epi_store_bf16(p, r, cg, f, p.out);
 }
 // ---- fused GroupNorm epilogue helpers ----
 // Statistics are kept per GRANULE of 4 consecutive channels (a group is a whole number of granules: cpg % 4 == 0), so each
@@ -733,24 +736,45 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
         const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
         const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
+        uint4 res_cur[4], res_nxt[4];
+        if (p.res0) {
+          if (sub == 0 && pt + n_pairs < pair_tiles) {      // next tile's residual rows -> L2
+            const TileCoord tn = decode_pair_tile(p, pt + n_pairs, (int)rank);
+            epi_prefetch_res(p, epi_decode_row(p, tn, quad * 32 + lane), tn.nt * p.block_n, p.block_n);
+            if (kMH == 2) epi_prefetch_res(p, epi_decode_row(p, tn, 128 + quad * 32 + lane), tn.nt * p.block_n, p.block_n);
+          }
+          if (n_mine > 0) epi_load_res(p, row0, lane, sub << 5, res_nxt);
+        }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols);
-        // ---------------- pass 1: statistics ----------------
+        // ---------------- pass 1: finished values (bias + embedding + residual) back into TMEM, statistics ----------------
         float run_s[8], run_q[8];
         for (int k = 0; k < n_mine; ++k) {
           const int half = kMH == 2 ? (k & 1) : 0;
           const int ci = sub + 2 * (kMH == 2 ? (k >> 1) : k);
           const EpiRow rr = epi_pick(row0, row1, half != 0);
+          const uint32_t ta = t_addr + (uint32_t)(half * p.block_n + (ci << 5));
           uint32_t v[32];
-          tmem_ld32(t_addr + (uint32_t)(half * p.block_n + (ci << 5)), v);
+          tmem_ld32(ta, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
+          if (p.res0 && k + 1 < n_mine) {   // the next item's residual row travels while this item is being reduced
+            const int nh = kMH == 2 ? ((k + 1) & 1) : 0;
+            const int nc0 = (sub + 2 * (kMH == 2 ? ((k + 1) >> 1) : (k + 1))) << 5;
+            epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nc0, res_nxt);
+          }
           tmem_ld_wait();
           float f[32];
           epi_bias_emb(p, rr, ci << 5, v, s_bias_addr, f);
+          if (p.res0) epi_add_res(f, res_cur);
           if (!rr.valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = 0.f;
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(f[j]);
+          tmem_st32(ta, v);                 // pass 2 reads the finished value back: no second bias / embedding / residual fetch
           epi_granules(f, run_s, run_q, sum_halves && half == 1);
           if (sum_halves && half == 0) continue;
           float2* sc = s_scr + ci * 64;
@@ -763,6 +787,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             if ((lane & 1) == 0) sc[(quad * 2 + (lane >> 4)) * 8 + ((lane >> 1) & 7)] = make_float2(run_s[0], run_q[0]);
           }
         }
+        tmem_st_wait();
         named_bar_sync(5, 32 * TC_EPI_WARPS);
         // ---------------- per-(sample, group) statistics of the tile ----------------
         if (et < n_units * 32) {
@@ -798,18 +823,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         }
         named_bar_sync(5, 32 * TC_EPI_WARPS);
         const float hs = p.gn_silu ? 0.5f : 1.0f;                   // silu(y) = h * tanh(h) + h with h = y / 2
+        const bool dual = p.out2 != nullptr;
         const bool table = n_units <= 2;
         if (table) {
-          // per-(sample, channel) scale / shift with everything folded in: y = acc * sc + sh,
-          //   sc = rstd * gamma * hs,  sh = ((bias + emb - mean) * rstd * gamma + beta) * hs
+          // per-(sample, channel) scale / shift: y = f * sc + sh,  sc = rstd * gamma * hs,  sh = (beta - mean * rstd * gamma) * hs
           for (int i = et; i < n_units * p.Cout; i += 32 * TC_EPI_WARPS) {
             const int u = i >= p.Cout ? 1 : 0, c = i - u * p.Cout;
             const float2 m = s_mr[u * 32 + (c >> p.gn_cpg_log2)];
-            float add = s_bias[c];
-            const int n = epi_decode_row(p, tc, u * p.gn_R).n;
-            if (p.emb && n < p.B) add += __ldg(p.emb + (long long)p.emb_row[n] * p.emb_stride + c);
             const float sc = m.y * s_gamma[c] * hs;
-            s_tab[u * TC_GN_MAX_COUT + c] = make_float2(sc, fmaf(add - m.x, sc, s_beta[c] * hs));
+            s_tab[u * TC_GN_MAX_COUT + c] = make_float2(sc, fmaf(-m.x, sc, s_beta[c] * hs));
           }
           named_bar_sync(5, 32 * TC_EPI_WARPS);
         }
@@ -828,15 +850,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           }
           const int trow = half * 128 + quad * 32 + lane;
           float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (dual && rr.valid) epi_store_bf16(p, rr, c0, f, p.out);
           if (table) {
             const float2* tb = s_tab + (trow >> p.gn_R_log2) * TC_GN_MAX_COUT + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float4 t4 = *(const float4*)(tb + j);
-              f[j] = fmaf(__uint_as_float(v[j]), t4.x, t4.y); f[j + 1] = fmaf(__uint_as_float(v[j + 1]), t4.z, t4.w);
+              f[j] = fmaf(f[j], t4.x, t4.y); f[j + 1] = fmaf(f[j + 1], t4.z, t4.w);
             }
           } else {
-            epi_bias_emb(p, rr, c0, v, s_bias_addr, f);
             const float2* mr = s_mr + (trow >> p.gn_R_log2) * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -851,7 +875,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = silu_from_half(f[j]);
           }
-          if (rr.valid) epi_store_bf16(p, rr, c0, f);
+          if (rr.valid) epi_store_bf16(p, rr, c0, f, dual ? p.out2 : p.out);
         }
         if (n_mine == 0) {
           tc_fence_before();
@@ -983,7 +1007,7 @@ struct TcConvPlan {
   int ring_bytes = TC_RING_BYTES;
   bool b_stat = false;          // weights resident in shared memory across the M tiles of a pair (n_b == total_k)
   // fused GroupNorm epilogue (conv_tc2_kernel<.., true>)
-  bool gn = false; int gn_R = 0, gn_seg = 32, gn_ctas = 1, gn_cpg = 0;
+  bool gn_ok = false, gn = false, gn_dual = false; int gn_R = 0, gn_seg = 32, gn_ctas = 1, gn_cpg = 0, gn_total_k = 0;
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
   std::map<int, TcMaps> maps;   // per batch size
@@ -1111,7 +1135,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   // cover it (measured: wins from 36 K-iterations, loses at 18)
   static const int gn_min_k = [] { const char* v = tuning_env("CFM_TC_GN_MIN_K"); return v ? atoi(v) : 0; }();
   op.gn_fused = false;
-  if (op.gn_request && pl->pair && !pl->tma_store && !op.ups && !op.out_is_output && !op.out_f32 && op.res0 < 0 && Cout == op.Cout &&
+  if (pl->pair && !pl->tma_store && !op.ups && !op.out_is_output && !op.out_f32 && Cout == op.Cout &&
       pl->block_n == Cout && Cout <= TC_GN_MAX_COUT && pl->valid_rows == rows && pl->bw == Wg && !(e.cfg.flags & CFM_FLAG_SEPARATE_GROUPNORM) &&
       eks * eks * (Cin / kc) + op.Cskip / kc >= gn_min_k) {
     const int cpg = Cout / 32, HW = Hg * Wg;
@@ -1123,9 +1147,12 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
       if (HW % 32) { if (HW == 16 && pl->mh == 1) seg = 16; else R = 0; }
     }
     if (cpg_ok && R > 0 && ctas <= 32 && (ctas == 1 || pl->bn == 1)) {
-      pl->gn = true; pl->gn_R = R; pl->gn_seg = seg; pl->gn_ctas = ctas; pl->gn_cpg = cpg;
+      // capable: the 12 KB of the epilogue's tables come out of the rings whether or not a GroupNorm ends up attached
+      // (tc_conv_attach_gn runs after the plan is complete and must not re-pack the weights)
+      pl->gn_ok = true; pl->gn_R = R; pl->gn_seg = seg; pl->gn_ctas = ctas; pl->gn_cpg = cpg;
+      pl->gn_total_k = eks * eks * (Cin / kc) + op.Cskip / kc;
       pl->ring_bytes = TC_GN_OFF;
-      op.gn_fused = true; op.gn_ctas = ctas;
+      if (op.gn_request && op.res0 < 0) { pl->gn = true; op.gn_fused = true; op.gn_ctas = ctas; }
     }
   }
   // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous), fill its rows exactly and
@@ -1311,6 +1338,7 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
       p.gn_gamma = op.gamma; p.gn_beta = op.beta; p.gn_eps = 1e-5f; p.gn_cpg = pl->gn_cpg; p.gn_cpg_log2 = ilog2(pl->gn_cpg);
       p.gn_R = pl->gn_R; p.gn_R_log2 = ilog2(pl->gn_R); p.gn_seg = pl->gn_seg; p.gn_ctas = pl->gn_ctas; p.gn_hw = pl->Hg * pl->Wg;
       p.gn_silu = op.silu;
+      if (pl->gn_dual) p.out2 = (bf16*)tensor_ptr(e, op.out2, B);
       if (pl->gn_ctas > 1) {
         if (!e.gn_exch || !e.gn_epoch || op.gn_exch_off < 0) { e.err = "internal: GroupNorm exchange buffers missing for " + op.name; return CFM_ERR_INTERNAL; }
         p.gn_exch = e.gn_exch + (size_t)op.gn_exch_off * B * 64;
@@ -1327,6 +1355,22 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   cudaError_t ce = cudaLaunchKernelEx(&lc.cfg, conv_tc_kernel, it->second.a[0], it->second.a[1], it->second.a[2], it->second.b, p);
   if (ce != cudaSuccess) { e.err = std::string("conv_tc_kernel launch failed: ") + cudaGetErrorString(ce); return CFM_ERR_CUDA; }
   return 0;
+}
+
+// Fold the GroupNorm `gn` (single source = conv.out, no FiLM) into the epilogue of the conv that produces its input: the
+// conv then writes both tensors, conv.out (un-normalised: it is still a residual / skip operand) and gn.out.
+bool tc_conv_attach_gn(Engine& e, Op& conv, const Op& gn) {
+  TcConvPlan* pl = conv.tc;
+  if (!pl || !pl->gn_ok || pl->gn || gn.kind != OP_GN || gn.src1 >= 0 || gn.film || gn.src0 != conv.out || gn.Cin != conv.Cout) return false;
+  // writing two tensors from a two-pass epilogue only pays when the K loop of a tile covers it (>= 30 K-iterations) or
+  // the map is small enough that the GroupNorm launch it replaces is pure latency (measured: profiles/r02_gn_fold_ab.txt)
+  static const int min_k = [] { const char* v = tuning_env("CFM_TC_GN_DUAL_MIN_K"); return v ? atoi(v) : 30; }();
+  if (pl->gn_total_k < min_k && pl->Hg * pl->Wg > 256) return false;
+  pl->gn = true; pl->gn_dual = true;
+  conv.gamma = gn.gamma; conv.beta = gn.beta; conv.silu = gn.silu;
+  conv.out2 = gn.out; conv.gn_fused = true; conv.gn_ctas = pl->gn_ctas;
+  if (pl->gn_ctas > 1) { conv.gn_exch_off = e.gn_tiles_per_sample; e.gn_tiles_per_sample += pl->gn_ctas; }
+  return true;
 }
 
 double tc_conv_executed_flops(const Op& op) {

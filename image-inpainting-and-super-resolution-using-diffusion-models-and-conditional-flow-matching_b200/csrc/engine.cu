@@ -421,19 +421,33 @@ static int build_plan(Engine& e) {
   e.flops_per_sample = 2.0 * ((double)mc * e.ted + (double)e.ted * e.ted + (double)e.emb_total * e.ted);
   for (auto& op : e.ops) e.flops_per_sample += op.flops;
 
+  // ---- fold single-source GroupNorms into the conv that produces their input (a block's last conv, a down-sampling
+  // conv): the conv's epilogue then writes the un-normalised block output AND the normalised tensor, and the GroupNorm
+  // pass with its extra read of the block output disappears ----
+  if (e.bf16 && !(e.cfg.flags & CFM_FLAG_SEPARATE_GROUPNORM)) {
+    for (size_t i = 1; i < e.ops.size(); ++i) {
+      if (e.ops[i].kind != OP_GN || e.ops[i - 1].kind != OP_CONV) continue;
+      if (!tc_conv_attach_gn(e, e.ops[i - 1], e.ops[i])) continue;
+      e.ops[i - 1].name += "+" + e.ops[i].name;
+      e.ops.erase(e.ops.begin() + i);
+      --i;
+    }
+  }
+
   // ---- liveness + first-fit arena assignment (per-sample element offsets, 64-element aligned) ----
   for (int i = 0; i < (int)e.ops.size(); ++i) {
     const Op& op = e.ops[i];
     for (int id : {op.src0, op.src1, op.skip0, op.skip1, op.res0, op.res1})
       if (id >= 0) e.tensors[id].last_use = i;
-    if (op.out >= 0) { if (e.tensors[op.out].first_use < 0) e.tensors[op.out].first_use = i; e.tensors[op.out].last_use = std::max(e.tensors[op.out].last_use, i); }
+    for (int o : {op.out, op.out2})
+      if (o >= 0) { if (e.tensors[o].first_use < 0) e.tensors[o].first_use = i; e.tensors[o].last_use = std::max(e.tensors[o].last_use, i); }
   }
   struct Blk { long long off, len; };
   std::vector<Blk> free_list;
   long long top = 0;
   auto align = [](long long v) { return (v + 63) / 64 * 64; };
   for (int i = 0; i < (int)e.ops.size(); ++i) {
-    const int o = e.ops[i].out;
+    for (const int o : {e.ops[i].out, e.ops[i].out2})
     if (o >= 0 && e.tensors[o].first_use == i) {
       const long long need = align(e.tensors[o].elems());
       int best = -1;
@@ -921,7 +935,7 @@ int cfm_engine_op_info(const cfm_engine* h, int32_t i, int32_t what, double* val
   auto tb = [&](int id) { return id >= 0 ? (double)e.tensors[id].elems() * es : 0.0; };
   if (what == 0) { *value = (op.kind == OP_CONV && op.tc) ? tc_conv_executed_flops(op) : op.flops; return 0; }
   if (what == 1) {
-    double b = tb(op.src0) + tb(op.src1) + tb(op.skip0) + tb(op.skip1) + tb(op.res0) + tb(op.res1) + tb(op.out);
+    double b = tb(op.src0) + tb(op.src1) + tb(op.skip0) + tb(op.skip1) + tb(op.res0) + tb(op.res1) + tb(op.out) + tb(op.out2);
     const int S = e.cfg.image_size;
     if (op.src_is_input || op.kind == OP_IM2COL) b += 4.0 * e.cfg.in_channels * S * S;           // fp32 NCHW network input
     if (op.out_is_output) b += 4.0 * e.cfg.out_channels * S * S;                                 // fp32 NCHW network output

@@ -41,6 +41,7 @@ struct Op {
   std::string name;
   // tensor ids (-1 = none). For convs: src = main operand, skip = 1x1 operand, res = identity residual.
   int src0 = -1, src1 = -1, skip0 = -1, skip1 = -1, res0 = -1, res1 = -1, out = -1;
+  int out2 = -1;           // conv with a folded GroupNorm that still writes its un-normalised result: out2 = the normalised tensor
   bool src_is_input = false, out_is_output = false;
   bool out_f32 = false;    // tcgen05 conv writing fp32 NHWC rows (the head's per-tap partial products)
   // conv
@@ -140,6 +141,7 @@ inline bool pdl_enabled() {
 bool tc_conv_supported(const Engine& e, const Op& op);
 int  tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w_main_oihw, const std::vector<float>& w_skip_oi);
 int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_nchw = nullptr);
+bool tc_conv_attach_gn(Engine& e, Op& conv, const Op& gn);
 void tc_conv_release(Engine& e);
 double tc_conv_executed_flops(const Op& op);   // 2*MAC per sample the tcgen05 kernel issues (padding and folding included)
 // bf16 fast kernels (kernels_bf16.cu)
