@@ -174,11 +174,18 @@ def _drift_report(pkg, O, model_bf16, cfg, params, dev, nfe, batch, oracle_batch
     m32.load_state_dict(params)
     m32 = m32.to(dev).eval()
     xb, ib = pkg.sample_euler(model_bf16, x0.to(dev), t_span, return_uint8=True, use_graph=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     xf, if_ = pkg.sample_euler(m32, x0.to(dev), t_span, return_uint8=True, use_graph=False)
+    torch.cuda.synchronize()
+    fp32_s = time.perf_counter() - t0
     m32.refresh()
     rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
     u8 = lambda a, b: {"mismatch_frac": float((a != b).float().mean()), "max_abs_diff": int((a.int() - b.int()).abs().max())}
-    rep = {"nfe": nfe, "batch": batch, "bf16_vs_fp32_engine": {"rel_l2": rel(xb.cpu(), xf.cpu()), "uint8": u8(ib.cpu(), if_.cpu())}}
+    rep = {"nfe": nfe, "batch": batch, "bf16_vs_fp32_engine": {"rel_l2": rel(xb.cpu(), xf.cpu()), "uint8": u8(ib.cpu(), if_.cpu())},
+           # throughput of the exact mode (fp32 storage, CUDA-core kernels, <= 1e-4 per NFE): this very run, wall clock
+           "fp32_exact_mode": {"samples_per_s": batch / fp32_s, "batch": batch, "nfe": nfe,
+                               "note": "correctness mode on CUDA cores (no tensor-core fp32 path); first call includes engine build"}}
     if oracle_batch > 0:
         t0 = time.perf_counter()
         xo = I.euler_trajectory(lambda t, x: O.wrapper_forward(cfg, params, t, x), x0[:oracle_batch], t_span)[-1]

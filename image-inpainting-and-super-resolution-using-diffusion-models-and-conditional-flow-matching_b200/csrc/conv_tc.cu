@@ -808,11 +808,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               st_relaxed_gpu_v2(ex + (my * 32 + g) * 2, __float_as_uint(ts), epoch);
               st_relaxed_gpu_v2(ex + (my * 32 + g) * 2 + 1, __float_as_uint(tq), epoch);
               ts = 0.f; tq = 0.f;
-              for (int j = 0; j < p.gn_ctas; ++j) {        // fixed order over the sample's tiles: bit-reproducible
-                uint2 a, b;
-                do { a = ld_relaxed_gpu_v2(ex + (j * 32 + g) * 2); } while (a.y != epoch);
-                do { b = ld_relaxed_gpu_v2(ex + (j * 32 + g) * 2 + 1); } while (b.y != epoch);
-                ts += __uint_as_float(a.x); tq += __uint_as_float(b.x);
+              for (int j0 = 0; j0 < p.gn_ctas; j0 += 4) {  // fixed order over the sample's tiles: bit-reproducible
+                // four tiles' words per round trip to L2 (the other tiles of the sample have usually published already)
+                uint2 a[4], b[4];
+                bool ok;
+                do {
+                  ok = true;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (j0 + j < p.gn_ctas) {
+                      a[j] = ld_relaxed_gpu_v2(ex + ((j0 + j) * 32 + g) * 2);
+                      b[j] = ld_relaxed_gpu_v2(ex + ((j0 + j) * 32 + g) * 2 + 1);
+                    }
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (j0 + j < p.gn_ctas) ok = ok && a[j].y == epoch && b[j].y == epoch;
+                } while (!ok);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j0 + j < p.gn_ctas) { ts += __uint_as_float(a[j].x); tq += __uint_as_float(b[j].x); }
               }
             }
           }
@@ -1366,6 +1380,7 @@ bool tc_conv_attach_gn(Engine& e, Op& conv, const Op& gn) {
   // the map is small enough that the GroupNorm launch it replaces is pure latency (measured: profiles/r02_gn_fold_ab.txt)
   static const int min_k = [] { const char* v = tuning_env("CFM_TC_GN_DUAL_MIN_K"); return v ? atoi(v) : 30; }();
   if (pl->gn_total_k < min_k && pl->Hg * pl->Wg > 256) return false;
+  if (pl->gn_ctas > 4) return false;      // many tiles per sample (64x64 maps and up): the exchange costs more than the pass it saves
   pl->gn = true; pl->gn_dual = true;
   conv.gamma = gn.gamma; conv.beta = gn.beta; conv.silu = gn.silu;
   conv.out2 = gn.out; conv.gn_fused = true; conv.gn_ctas = pl->gn_ctas;
