@@ -734,6 +734,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const unsigned epoch = p.gn_ctas > 1 ? *p.gn_epoch : 0u;
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
         const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
+        const int cbase = tc.nt * p.block_n;                       // first channel of this N tile (whole groups per tile)
+        const int groups_tile = p.block_n >> p.gn_cpg_log2;
         const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
         const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
         uint4 res_cur[4], res_nxt[4];
@@ -743,7 +745,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             epi_prefetch_res(p, epi_decode_row(p, tn, quad * 32 + lane), tn.nt * p.block_n, p.block_n);
             if (kMH == 2) epi_prefetch_res(p, epi_decode_row(p, tn, 128 + quad * 32 + lane), tn.nt * p.block_n, p.block_n);
           }
-          if (n_mine > 0) epi_load_res(p, row0, lane, sub << 5, res_nxt);
+          if (n_mine > 0) epi_load_res(p, row0, lane, cbase + (sub << 5), res_nxt);
         }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -762,11 +764,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           if (p.res0 && k + 1 < n_mine) {   // the next item's residual row travels while this item is being reduced
             const int nh = kMH == 2 ? ((k + 1) & 1) : 0;
             const int nc0 = (sub + 2 * (kMH == 2 ? ((k + 1) >> 1) : (k + 1))) << 5;
-            epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, nc0, res_nxt);
+            epi_load_res(p, epi_pick(row0, row1, nh != 0), lane, cbase + nc0, res_nxt);
           }
           tmem_ld_wait();
           float f[32];
-          epi_bias_emb(p, rr, ci << 5, v, s_bias_addr, f);
+          epi_bias_emb(p, rr, cbase + (ci << 5), v, s_bias_addr, f);
           if (p.res0) epi_add_res(f, res_cur);
           if (!rr.valid) {
 #pragma unroll
@@ -790,8 +792,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         tmem_st_wait();
         named_bar_sync(5, 32 * TC_EPI_WARPS);
         // ---------------- per-(sample, group) statistics of the tile ----------------
-        if (et < n_units * 32) {
-          const int u = et >> 5, g = et & 31;                   // a warp per unit, a lane per group
+        if (et < n_units * 32 && (et & 31) < groups_tile) {
+          const int u = et >> 5, g = et & 31;                   // a warp per unit, a lane per group of this N tile
           const int g0 = g * gpg;                                // first granule of the group; groups never straddle chunks
           const float2* sc = s_scr + (g0 >> 3) * 64 + (g0 & 7);
           float ts = 0.f, tq = 0.f;
@@ -805,7 +807,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             const int my = (tc.th * p.bh * p.W) / (128 * kMH);
             if (n < p.B) {
               uint2* ex = p.gn_exch + ((long long)n * p.gn_ctas) * 64;
-              st_relaxed_gpu_v2(ex + (my * 32 + g) * 2, __float_as_uint(ts), epoch);
+              st_relaxed_gpu_v2(ex + (my * 32 + g) * 2, __float_as_uint(ts), epoch);       // (tiles that exchange span all channels: g is global)
               st_relaxed_gpu_v2(ex + (my * 32 + g) * 2 + 1, __float_as_uint(tq), epoch);
               ts = 0.f; tq = 0.f;
               for (int j0 = 0; j0 < p.gn_ctas; j0 += 4) {  // fixed order over the sample's tiles: bit-reproducible
@@ -841,11 +843,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const bool table = n_units <= 2;
         if (table) {
           // per-(sample, channel) scale / shift: y = f * sc + sh,  sc = rstd * gamma * hs,  sh = (beta - mean * rstd * gamma) * hs
-          for (int i = et; i < n_units * p.Cout; i += 32 * TC_EPI_WARPS) {
-            const int u = i >= p.Cout ? 1 : 0, c = i - u * p.Cout;
+          for (int i = et; i < n_units * p.block_n; i += 32 * TC_EPI_WARPS) {
+            const int u = i >= p.block_n ? 1 : 0, c = i - u * p.block_n;       // c: channel within this N tile
             const float2 m = s_mr[u * 32 + (c >> p.gn_cpg_log2)];
-            const float sc = m.y * s_gamma[c] * hs;
-            s_tab[u * TC_GN_MAX_COUT + c] = make_float2(sc, fmaf(-m.x, sc, s_beta[c] * hs));
+            const float sc = m.y * s_gamma[cbase + c] * hs;
+            s_tab[u * TC_GN_MAX_COUT + c] = make_float2(sc, fmaf(-m.x, sc, s_beta[cbase + c] * hs));
           }
           named_bar_sync(5, 32 * TC_EPI_WARPS);
         }
@@ -866,7 +868,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (dual && rr.valid) epi_store_bf16(p, rr, c0, f, p.out);
+          if (dual && rr.valid) epi_store_bf16(p, rr, cbase + c0, f, p.out);
           if (table) {
             const float2* tb = s_tab + (trow >> p.gn_R_log2) * TC_GN_MAX_COUT + c0;
 #pragma unroll
@@ -879,7 +881,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float2 m = mr[(c0 + j) >> p.gn_cpg_log2];       // 4 | cpg: the four channels share a group
-              const float4 ga = *(const float4*)(s_gamma + c0 + j), be = *(const float4*)(s_beta + c0 + j);
+              const float4 ga = *(const float4*)(s_gamma + cbase + c0 + j), be = *(const float4*)(s_beta + cbase + c0 + j);
               const float r = m.y * hs;
               f[j] = fmaf((f[j] - m.x) * r, ga.x, be.x * hs); f[j + 1] = fmaf((f[j + 1] - m.x) * r, ga.y, be.y * hs);
               f[j + 2] = fmaf((f[j + 2] - m.x) * r, ga.z, be.z * hs); f[j + 3] = fmaf((f[j + 3] - m.x) * r, ga.w, be.w * hs);
@@ -889,7 +891,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = silu_from_half(f[j]);
           }
-          if (rr.valid) epi_store_bf16(p, rr, c0, f, dual ? p.out2 : p.out);
+          if (rr.valid) epi_store_bf16(p, rr, cbase + c0, f, dual ? p.out2 : p.out);
         }
         if (n_mine == 0) {
           tc_fence_before();
@@ -1021,6 +1023,7 @@ struct TcConvPlan {
   int ring_bytes = TC_RING_BYTES;
   bool b_stat = false;          // weights resident in shared memory across the M tiles of a pair (n_b == total_k)
   // fused GroupNorm epilogue (conv_tc2_kernel<.., true>)
+  TcConvPlan* alt = nullptr;   // narrow-N variant of the same conv for launches with few M tiles (own weights copy and maps)
   bool gn_ok = false, gn = false, gn_dual = false; int gn_R = 0, gn_seg = 32, gn_ctas = 1, gn_cpg = 0, gn_total_k = 0;
   int cout_pad = 0;            // GEMM N extent (== Cout, or 32 for the zero-padded network head)
   float* bias_pad = nullptr;
@@ -1085,19 +1088,20 @@ static bool size_rings(TcConvPlan* pl, int G) {
   return false;
 }
 
-int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::vector<float>& ws) {
+int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::vector<float>& ws, int force_block_n) {
   TcConvPlan* pl = new TcConvPlan();
   const int Cin = op.Cin, ks = op.ks;
   const int Cout = op.out_is_output ? 32 : op.Cout;      // padded rows of W are zero
   pl->cout_pad = Cout;
-  pl->block_n = pick_block_n(Cout);
+  pl->block_n = force_block_n ? force_block_n : pick_block_n(Cout);
   static const int pair_min_n = [] { const char* v = tuning_env("CFM_TC_PAIR_MIN_N"); return v ? atoi(v) : 128; }();
   // N >= 128: CTA pair (half the weight tile per SM).  At N = 128 each CTA of the pair also takes two 128-row M-halves
   // per weight tile (a 512 x 128 pair tile): the K-iteration stays 512 cycles long (a 256-cycle K-iteration is
   // shorter than the issue loop) and the shared-memory bytes per MMA cycle drop from 182 to ~135 of the 128 B/clk port.
   // N <= 96: one CTA with a 256-row tile.
-  pl->pair = !op.out_is_output && pl->block_n >= pair_min_n && !env_off("CFM_DISABLE_TC_2CTA");
-  pl->mh = (pl->block_n <= 128 && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;      // 2 x 128 rows per CTA share one B tile
+  pl->pair = !op.out_is_output && (pl->block_n >= pair_min_n || force_block_n) && !env_off("CFM_DISABLE_TC_2CTA");
+  pl->mh = (pl->block_n <= 128 && !force_block_n && !env_off("CFM_DISABLE_TC_MH2")) ? 2 : 1;      // 2 x 128 rows per CTA share one B tile
+  // force_block_n: the NARROW variant of a small-map layer (see the end of this function): smallest tiles, most of them
   const int rows = 128 * pl->mh;
   // K-iteration width: 64 channels (SWIZZLE_128B rows) when every operand allows it, else 32 (SWIZZLE_64B)
   pl->kc = 64;
@@ -1150,7 +1154,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   static const int gn_min_k = [] { const char* v = tuning_env("CFM_TC_GN_MIN_K"); return v ? atoi(v) : 0; }();
   op.gn_fused = false;
   if (pl->pair && !pl->tma_store && !op.ups && !op.out_is_output && !op.out_f32 && Cout == op.Cout &&
-      pl->block_n == Cout && Cout <= TC_GN_MAX_COUT && pl->valid_rows == rows && pl->bw == Wg && !(e.cfg.flags & CFM_FLAG_SEPARATE_GROUPNORM) &&
+      Cout <= TC_GN_MAX_COUT && pl->block_n % (Cout / 32) == 0 && pl->valid_rows == rows && pl->bw == Wg && !(e.cfg.flags & CFM_FLAG_SEPARATE_GROUPNORM) &&
       eks * eks * (Cin / kc) + op.Cskip / kc >= gn_min_k) {
     const int cpg = Cout / 32, HW = Hg * Wg;
     const bool cpg_ok = cpg >= 4 && pow2(cpg) && cpg <= 32;
@@ -1160,7 +1164,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
       R = HW;
       if (HW % 32) { if (HW == 16 && pl->mh == 1) seg = 16; else R = 0; }
     }
-    if (cpg_ok && R > 0 && ctas <= 32 && (ctas == 1 || pl->bn == 1)) {
+    if (cpg_ok && R > 0 && ctas <= 32 && (ctas == 1 || (pl->bn == 1 && pl->block_n == Cout))) {
       // capable: the 12 KB of the epilogue's tables come out of the rings whether or not a GroupNorm ends up attached
       // (tc_conv_attach_gn runs after the plan is complete and must not re-pack the weights)
       pl->gn_ok = true; pl->gn_R = R; pl->gn_seg = seg; pl->gn_ctas = ctas; pl->gn_cpg = cpg;
@@ -1249,6 +1253,18 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
     cudaMemcpy(bp, hb.data(), sizeof(float) * Cout, cudaMemcpyHostToDevice);
     pl->bias_pad = (float*)bp;
   }
+  if (force_block_n) { op.tc = pl; return 0; }
+  // NARROW variant for the small maps (8x8 and below, 256 channels): at small batches such a layer has fewer 256-row x
+  // 256-channel pair tiles than the GPU has CTA pairs (batch 128 at 4x4: 8 tiles of 72 K-iterations on 8 of 74 pairs - the
+  // same ~30 us as at batch 1024).  The same conv with 64- or 128-channel N tiles has 4x / 2x as many tiles with a K loop
+  // that is 4x / 2x shorter; tc_conv_launch picks it when the wide tiling would leave more than half of the pairs idle.
+  if (pl->pair && !pl->tma_store && !op.ups && !op.out_f32 && Cout == 256 && pl->block_n == 256 && Hg * Wg <= 64 && !env_off("CFM_DISABLE_TC_NARROW")) {
+    Op alt = op;
+    alt.tc = nullptr;
+    const int rc = tc_conv_prepare(e, alt, w, ws, Hg * Wg <= 16 ? 64 : 128);
+    if (rc) { delete pl; return rc; }
+    if (alt.tc && (alt.tc->gn == pl->gn) && (alt.tc->gn_ok == pl->gn_ok)) pl->alt = alt.tc; else delete alt.tc;
+  }
   op.tc = pl;
   static DeviceOnce attr_set;
   if (attr_set.pending(e.device)) {
@@ -1264,8 +1280,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   return get_encode(e);
 }
 
-static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
-  TcConvPlan* pl = op.tc;
+static int encode_maps(Engine& e, const Op& op, TcConvPlan* pl, int B, TcMaps* m) {
   std::memset(m, 0, sizeof(*m));
   const CUtensorMapSwizzle swz = pl->kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < pl->n_seg; ++s) {
@@ -1307,10 +1322,15 @@ static int encode_maps(Engine& e, const Op& op, int B, TcMaps* m) {
 
 int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_nchw) {
   TcConvPlan* pl = op.tc;
+  if (pl->alt) {      // fewer wide pair tiles than half of the CTA pairs: take the narrow tiling
+    const int tiles128 = ((pl->Wg + pl->bw - 1) / pl->bw) * ((pl->Hg + pl->bh - 1) / pl->bh) * ((B + pl->bn - 1) / pl->bn);
+    const int pair_tiles = ((tiles128 + 1) / 2) * (pl->cout_pad / pl->block_n) * pl->n_phase;
+    if (pair_tiles * 2 <= e.sm_count / 2) pl = pl->alt;
+  }
   auto it = pl->maps.find(B);
   if (it == pl->maps.end()) {
     TcMaps m;
-    int rc = encode_maps(e, op, B, &m);
+    int rc = encode_maps(e, op, pl, B, &m);
     if (rc) return rc;
     it = pl->maps.emplace(B, m).first;
   }
@@ -1382,6 +1402,7 @@ bool tc_conv_attach_gn(Engine& e, Op& conv, const Op& gn) {
   if (pl->gn_total_k < min_k && pl->Hg * pl->Wg > 256) return false;
   if (pl->gn_ctas > 4) return false;      // many tiles per sample (64x64 maps and up): the exchange costs more than the pass it saves
   pl->gn = true; pl->gn_dual = true;
+  if (pl->alt) { pl->alt->gn = true; pl->alt->gn_dual = true; }
   conv.gamma = gn.gamma; conv.beta = gn.beta; conv.silu = gn.silu;
   conv.out2 = gn.out; conv.gn_fused = true; conv.gn_ctas = pl->gn_ctas;
   if (pl->gn_ctas > 1) { conv.gn_exch_off = e.gn_tiles_per_sample; e.gn_tiles_per_sample += pl->gn_ctas; }
@@ -1396,7 +1417,7 @@ double tc_conv_executed_flops(const Op& op) {
 
 void tc_conv_release(Engine& e) {
   for (Op& op : e.ops)
-    if (op.tc) op.tc->maps.clear();
+    if (op.tc) { op.tc->maps.clear(); if (op.tc->alt) op.tc->alt->maps.clear(); }
 }
 
 }  // namespace cfm

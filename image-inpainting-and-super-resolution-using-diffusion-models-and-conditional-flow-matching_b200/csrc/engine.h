@@ -139,7 +139,7 @@ inline bool pdl_enabled() {
 
 // conv_tc.cu
 bool tc_conv_supported(const Engine& e, const Op& op);
-int  tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w_main_oihw, const std::vector<float>& w_skip_oi);
+int  tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w_main_oihw, const std::vector<float>& w_skip_oi, int force_block_n = 0);
 int  tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_nchw = nullptr);
 bool tc_conv_attach_gn(Engine& e, Op& conv, const Op& gn);
 void tc_conv_release(Engine& e);
