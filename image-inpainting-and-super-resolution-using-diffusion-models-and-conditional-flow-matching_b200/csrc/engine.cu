@@ -539,6 +539,17 @@ __global__ void setup_rows_kernel(int B, int rows, int uniform, float t_scalar, 
   if (i < B) row_of_sample[i] = uniform ? (y ? (int)y[i] : 0) : i;
 }
 
+// fp32 convs whose channel counts are multiples of 16 (all but the stem and the head) take the register-blocked kernel
+static bool launch_conv_fast(const ConvArgs<float>& a, long long M, cudaStream_t st) {
+  if (a.src_nchw0 || a.out_nchw || !a.out) return false;
+  if (a.C0 % 16 || a.C1 % 16 || a.S0 % 16 || a.S1 % 16 || a.Cout % 64 || a.R0 % 4 || a.R1 % 4 || (a.res0 && a.R0 + a.R1 != a.Cout)) return false;
+  const unsigned gm = (unsigned)((M + CF_BM - 1) / CF_BM);
+  if (a.Cout % 128 == 0 && (long long)gm * (a.Cout / 128) >= 148) conv_fp32_fast_kernel<128><<<dim3(gm, a.Cout / 128), 256, 0, st>>>(a);
+  else conv_fp32_fast_kernel<64><<<dim3(gm, a.Cout / 64), 256, 0, st>>>(a);
+  return true;
+}
+static bool launch_conv_fast(const ConvArgs<bf16>&, long long, cudaStream_t) { return false; }
+
 template <typename T>
 static int run_ops(Engine& e, int B, const float* x, const float* cond, float* out, cudaStream_t st) {
   int op_index = 0;
@@ -583,6 +594,7 @@ static int run_ops(Engine& e, int B, const float* x, const float* cond, float* o
         if (op.out_is_output) a.out_nchw = out; else a.out = (T*)tensor_ptr(e, op.out, B);
         a.B = B; a.Hout = op.Hout; a.Wout = op.Wout; a.Cout = op.Cout;
         const long long M = (long long)B * op.Hout * op.Wout;
+        if (launch_conv_fast(a, M, st)) { e.launches++; break; }     // exact mode: register-blocked fp32 kernel
         dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (unsigned)((op.Cout + CG_BN - 1) / CG_BN));
         conv_generic_kernel<T><<<grid, 256, 0, st>>>(a);
         e.launches++;

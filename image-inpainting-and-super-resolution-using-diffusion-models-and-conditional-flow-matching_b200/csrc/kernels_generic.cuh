@@ -151,6 +151,143 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Exact-mode (fp32) convolution, register-blocked: 128 pixels x 128 (or 64) output channels per CTA, 8 x 8 (8 x 4)
+// outputs per thread, K in slices of 16 through double-buffered shared memory.  Every K slice lies inside ONE tap and
+// ONE source tensor (all segment widths are multiples of 16 channels - every layer except the 3-channel stem and head,
+// which stay on conv_generic_kernel), so a thread gathers its pixel's 8 consecutive channels with two 16-byte loads
+// and the tap / bounds arithmetic is per slice, not per element.  Each output's products are accumulated in K order by
+// one thread: bit-identical for any batch split.  fp32 FMA peak of a B200 is ~72 TFLOP/s; this is the correctness mode
+// (<= 1e-4 per NFE), the tensor-core path is the product's fast path.
+// ---------------------------------------------------------------------------------------
+constexpr int CF_BM = 128, CF_BK = 16;
+
+template <int BN>
+__global__ void __launch_bounds__(256) conv_fp32_fast_kernel(ConvArgs<float> a) {
+  constexpr int TN = BN / 16;                          // outputs per thread along N: 8 (BN = 128) or 4 (BN = 64)
+  __shared__ __align__(16) float As[2][CF_BK][CF_BM];
+  __shared__ __align__(16) float Bs[2][CF_BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;              // thread's outputs: pixels ty*8 .. +8, channels tx*TN .. +TN
+  const int Cin = a.C0 + a.C1;
+  const int Kmain = a.ks * a.ks * Cin;
+  const int Ktot = Kmain + a.S0 + a.S1;
+  const long long M = (long long)a.B * a.Hout * a.Wout;
+  const long long m0 = (long long)blockIdx.x * CF_BM;
+  const int n0 = blockIdx.y * BN;
+  const int pad = a.ks >> 1;
+  const int Hv = a.ups ? a.Hin * 2 : a.Hin, Wv = a.ups ? a.Win * 2 : a.Win;
+
+  // loader role: pixel lp of the tile, channels lc .. lc + 8 of every K slice
+  const int lp = tid >> 1, lc = (tid & 1) * 8;
+  const long long pm = m0 + lp;
+  const bool pvalid = pm < M;
+  int pb = 0, poy = 0, pox = 0;
+  if (pvalid) {
+    pb = (int)(pm / (a.Hout * a.Wout));
+    const int r = (int)(pm - (long long)pb * a.Hout * a.Wout);
+    poy = r / a.Wout; pox = r - poy * a.Wout;
+  }
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[BN / 64];                            // prefetched slice (registers) while the previous one is consumed
+  auto fetch = [&](int k0) {
+    // A: this thread's 8 channels of slice k0 for its pixel
+    const float* sp = nullptr;
+    if (pvalid) {
+      if (k0 < Kmain) {
+        const int tap = k0 / Cin, c = k0 - tap * Cin + lc;
+        const int ky = tap / a.ks, kx = tap - ky * a.ks;
+        int iy = poy * a.stride + ky - pad, ix = pox * a.stride + kx - pad;
+        if (iy >= 0 && iy < Hv && ix >= 0 && ix < Wv) {
+          if (a.ups) { iy >>= 1; ix >>= 1; }
+          const long long pix = ((long long)pb * a.Hin + iy) * a.Win + ix;
+          sp = (c < a.C0) ? a.src0 + pix * a.C0 + c : a.src1 + pix * a.C1 + (c - a.C0);
+        }
+      } else {
+        const int c = k0 - Kmain + lc;
+        const long long pix = ((long long)pb * a.Hout + poy) * a.Wout + pox;
+        sp = (c < a.S0) ? a.skip0 + pix * a.S0 + c : a.skip1 + pix * a.S1 + (c - a.S0);
+      }
+    }
+    ra[0] = sp ? __ldg((const float4*)sp) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ra[1] = sp ? __ldg((const float4*)sp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // B: 16 x BN weights of the slice, float4 per thread (x BN / 64)
+#pragma unroll
+    for (int i = 0; i < BN / 64; ++i) {
+      const int idx = tid + i * 256;
+      const int kl = idx / (BN / 4), n4 = idx - kl * (BN / 4);
+      const int k = k0 + kl;
+      const float* wp = (k < Kmain) ? a.w_main + (long long)k * a.Cout : a.w_skip + (long long)(k - Kmain) * a.Cout;
+      rb[i] = __ldg((const float4*)(wp + n0) + n4);
+    }
+  };
+  auto stash = [&](int buf) {
+    const float v[8] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[buf][lc + j][lp] = v[j];
+#pragma unroll
+    for (int i = 0; i < BN / 64; ++i) {
+      const int idx = tid + i * 256;
+      const int kl = idx / (BN / 4), n4 = idx - kl * (BN / 4);
+      *(float4*)&Bs[buf][kl][n4 * 4] = rb[i];
+    }
+  };
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < Ktot; k0 += CF_BK) {
+    const bool more = k0 + CF_BK < Ktot;
+    if (more) fetch(k0 + CF_BK);
+#pragma unroll
+    for (int kk = 0; kk < CF_BK; ++kk) {
+      float av[8], bv[TN];
+      const float4 a0 = *(const float4*)&As[buf][kk][ty * 8], a1 = *(const float4*)&As[buf][kk][ty * 8 + 4];
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 b4 = *(const float4*)&Bs[buf][kk][tx * TN + j];
+        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  // epilogue: bias + embedding vector + identity residual, NHWC fp32 rows
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+    const int b = (int)(m / (a.Hout * a.Wout));
+    const float* embp = a.emb ? a.emb + (long long)a.emb_row[b] * a.emb_stride : nullptr;
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      const int n = n0 + tx * TN + j;
+      float4 v = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+      const float4 bi = *(const float4*)(a.bias + n);
+      v.x += bi.x; v.y += bi.y; v.z += bi.z; v.w += bi.w;
+      if (embp) { const float4 e4 = *(const float4*)(embp + n); v.x += e4.x; v.y += e4.y; v.z += e4.z; v.w += e4.w; }
+      if (a.res0) {
+        const float4 r4 = (n < a.R0) ? *(const float4*)(a.res0 + m * a.R0 + n) : *(const float4*)(a.res1 + m * a.R1 + (n - a.R0));
+        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+      }
+      *(float4*)(a.out + m * a.Cout + n) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // GroupNorm(32 groups, eps) [+ FiLM] [+ SiLU] over an NHWC tensor (optionally a concat of two).
 // One CTA per (sample, group).  Group data is staged in shared memory when it fits so
 // the mean / centred variance / normalise passes read global memory once.
