@@ -9,6 +9,7 @@
 // as an MN-major B operand straight from its NHWC rows) into the same TMEM columns; the epilogue
 // normalises by the row sum and stores bf16.  96 KB smem + 256 TMEM columns -> 2 CTAs per SM, so
 // one CTA's softmax overlaps the other's MMAs and loads.
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include "engine.h"
@@ -192,6 +193,218 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent, pipelined variant (round 2): one CTA per SM walks (sample, head) items; both 128-query tiles of an item
+// are in flight together, so K and V are loaded once per head instead of once per query tile, and the next item's
+// operands stream in while the current one is in its softmax.
+//   warp 0      TMA producer: Q0 | Q1 | K (64 KB) of item j+1 and V (32 KB) of item j into buffers that the PV MMAs of
+//               items j-1 / j-2 have released (pv_done barriers) -> ~96 KB in flight per SM throughout
+//   warp 1      MMA issuer: S0 = Q0 K^T, S1 = Q1 K^T (128 x 256 x 64 each) into TMEM columns [0, 256) / [256, 512);
+//               then O_g = P_g V as the two softmax groups deliver their P
+//   warps 2-5   softmax group 0 (query tile 0), one thread per query row: exact two-pass fp32 softmax from TMEM,
+//   warps 6-9   softmax group 1 (query tile 1)     bf16 P into swizzled smem, O / rowsum -> bf16 -> global
+// Shared memory: three 64 KB buffers rotate through the roles {Q|K of item j, later overlaid by P0 of item j},
+// {P1 of item j}, {Q|K of item j+1}: q_j = 2j mod 3 holds Q|K and P0, p_j = q_{j-1} holds P1; V has its own 32 KB.
+// 268 M exponentials per block at batch 1024 put the MUFU floor at ~0.06 ms, the DRAM floor (qkv read once, output
+// written once) at 0.083 ms; the one-CTA-per-tile kernel above takes 0.197 ms.
+// ------------------------------------------------------------------------------------------------
+constexpr int AP_THREADS = 320;
+constexpr int AP_BUF = 65536;
+constexpr int AP_V_OFF = 3 * AP_BUF;
+constexpr int AP_BAR_OFF = AP_V_OFF + 32768;
+constexpr int AP_SMEM = AP_BAR_OFF + 256 + 1024;
+
+__global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __grid_constant__ CUtensorMap map, const AttnTcParams p,
+                                                                        int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_qk = (uint64_t*)(smem + AP_BAR_OFF);   // [2]
+  uint64_t* full_v = full_qk + 2;
+  uint64_t* bar_s = full_qk + 3;                         // S0 and S1 of the item complete
+  uint64_t* bar_p = full_qk + 4;                         // [2] 128 arrivals: P_g written, S_g no longer needed
+  uint64_t* bar_o = full_qk + 6;                         // [2] O_g complete
+  uint64_t* bar_e = full_qk + 8;                         // 256 arrivals: O read out of TMEM
+  uint64_t* pv_done = full_qk + 9;                       // [2] by item parity: every MMA of the item has retired
+  uint32_t* tmem_slot = (uint32_t*)(full_qk + 11);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  pdl_launch_dependents();
+  if (tid == 0) {
+    prefetch_tmap(&map);
+    mbar_init(&full_qk[0], 1); mbar_init(&full_qk[1], 1); mbar_init(full_v, 1); mbar_init(bar_s, 1);
+    mbar_init(&bar_p[0], 128); mbar_init(&bar_p[1], 128); mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
+    mbar_init(bar_e, 256); mbar_init(&pv_done[0], 1); mbar_init(&pv_done[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int j = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+        const int b = it / p.heads, h = it - b * p.heads;
+        const int qcol = p.new_order ? h * AT_D : h * 3 * AT_D;
+        const int kcol = p.new_order ? p.C + h * AT_D : h * 3 * AT_D + AT_D;
+        const int vcol = p.new_order ? 2 * p.C + h * AT_D : h * 3 * AT_D + 2 * AT_D;
+        const int row0 = b * AT_T;
+        uint8_t* qk = smem + ((2 * j) % 3) * AP_BUF;
+        if (j >= 2) mbar_wait(&pv_done[j & 1], (uint32_t)(((j - 2) >> 1) & 1));      // this buffer was P1 of item j - 2
+        mbar_expect_tx(&full_qk[j & 1], 65536);
+        tma_load_2d(qk, &map, &full_qk[j & 1], qcol, row0);
+        tma_load_2d(qk + 16384, &map, &full_qk[j & 1], qcol, row0 + 128);
+        tma_load_2d(qk + 32768, &map, &full_qk[j & 1], kcol, row0);
+        tma_load_2d(qk + 49152, &map, &full_qk[j & 1], kcol, row0 + 128);
+        if (j >= 1) mbar_wait(&pv_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));  // V of item j - 1 consumed
+        mbar_expect_tx(full_v, 32768);
+        tma_load_2d(smem + AP_V_OFF, &map, full_v, vcol, row0);
+        tma_load_2d(smem + AP_V_OFF + 16384, &map, full_v, vcol, row0 + 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = make_idesc(AT_M, AT_T);
+    const uint32_t idesc_o = make_idesc_major(AT_M, AT_D, 0, 1);
+    const uint32_t vbase = smem_u32(smem + AP_V_OFF);
+    int j = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      const uint32_t qk = smem_u32(smem + ((2 * j) % 3) * AP_BUF);
+      const uint32_t p1 = smem_u32(smem + ((2 * j + 1) % 3) * AP_BUF);
+      mbar_wait(&full_qk[j & 1], (uint32_t)((j >> 1) & 1));
+      if (j > 0) mbar_wait(bar_e, par ^ 1);              // O of the previous item has left TMEM
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t kd = make_desc_sw128(qk + 32768);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const uint64_t qd = make_desc_sw128(qk + m * 16384);
+#pragma unroll
+          for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem + (uint32_t)(m * 256), qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k > 0);
+        }
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(&bar_p[g], par);
+        if (g == 0) mbar_wait(full_v, par);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t pbase = g == 0 ? qk : p1;
+#pragma unroll
+          for (int k = 0; k < AT_T / 16; ++k) {
+            const uint64_t ad = make_desc_sw128(pbase + (k >> 2) * 16384 + (k & 3) * 32);
+            const uint64_t bd = make_desc_sw128_mn(vbase + k * 2048, 1024);
+            umma_bf16(tmem + (uint32_t)(g * 256), ad, bd, idesc_o, k > 0);
+          }
+          umma_commit(&bar_o[g]);
+          if (g == 1) umma_commit(&pv_done[j & 1]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue: group g = query tile g, one thread per query row =====================
+    const int g = (warp - 2) >> 2;
+    const int r = (warp & 3) * 32 + lane;                 // row of the tile = TMEM lane
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 256);
+    int j = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      const int b = it / p.heads, h = it - b * p.heads;
+      uint8_t* prow = smem + ((g == 0 ? 2 * j : 2 * j + 1) % 3) * AP_BUF + r * 128;
+      mbar_wait(bar_s, par);
+      tc_fence_after();
+      // both passes keep the NEXT 32 scores in flight (tcgen05.ld) while the current 32 are consumed: with one thread per
+      // row and two warps per scheduler the TMEM read latency is otherwise the whole cost of the max pass
+      float mx = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_row, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_T; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld32(t_row + (uint32_t)(c0 + 32), vb);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+          tmem_ld_wait();
+          if (c0 + 64 < AT_T) tmem_ld32(t_row + (uint32_t)(c0 + 64), va);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
+        }
+      }
+      const float mxs = mx * p.scale_log2;
+      float sum = 0.f;
+      auto emit = [&](const uint32_t (&v)[32], int c0) {
+        uint8_t* pchunk = prow + (c0 >> 6) * 16384;
+        const int c16 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o4;
+          __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[i * 8 + 2 * q]), p.scale_log2, -mxs));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[i * 8 + 2 * q + 1]), p.scale_log2, -mxs));
+            sum += e0 + e1;
+            o2[q] = __floats2bfloat162_rn(e0, e1);
+          }
+          *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+        }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_row, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_T; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld32(t_row + (uint32_t)(c0 + 32), vb);
+          emit(va, c0);
+          tmem_ld_wait();
+          if (c0 + 64 < AT_T) tmem_ld32(t_row + (uint32_t)(c0 + 64), va);
+          emit(vb, c0 + 32);
+        }
+      }
+      fence_proxy_async();          // P went through the generic proxy; the MMA reads it through the async proxy
+      tc_fence_before();
+      mbar_arrive(&bar_p[g]);
+      mbar_wait(&bar_o[g], par);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      bf16* op = p.out + ((long long)(b * AT_T + g * AT_M + r)) * p.C + h * AT_D;
+      uint32_t v0[32], v1[32];
+      tmem_ld32(t_row, v0);
+      tmem_ld32(t_row + 32u, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_e);           // the next item's S may overwrite these TMEM columns
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t* v = hh ? v1 : v0;
+        uint4 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162* o2 = (__nv_bfloat162*)&o[i];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o2[q] = __floats2bfloat162_rn(__uint_as_float(v[i * 8 + 2 * q]) * inv, __uint_as_float(v[i * 8 + 2 * q + 1]) * inv);
+        }
+        stg256(op + hh * 32, o[0], o[1]);
+        stg256(op + hh * 32 + 16, o[2], o[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct AttnTcPlan { std::map<int, CUtensorMap> maps; };
 static std::map<const Op*, AttnTcPlan> g_attn_plans;   // keyed by op address (ops vector is stable after build)
 
@@ -241,6 +454,18 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     // two CTAs per SM, two CTAs (query tiles) per (sample, head): one wave covers sm_count pairs
     static const int pf = [] { const char* v = tuning_env("CFM_ATTN_PREFETCH"); return v ? atoi(v) : 1; }();
     p.pf_db = pf * e.sm_count / op.heads; p.pf_dh = pf * e.sm_count % op.heads;
+  }
+  static const bool persist = [] { const char* v = tuning_env("CFM_DISABLE_ATTN_PERSIST"); return !(v && v[0] == '1'); }();
+  if (persist) {
+    static DeviceOnce attr2;
+    if (attr2.pending(e.device)) {
+      if (cudaFuncSetAttribute(attn_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_tc_persist_kernel) failed"; return CFM_ERR_CUDA; }
+      attr2.done(e.device);
+    }
+    const int n_items = B * op.heads;
+    LaunchCfg lp(dim3((unsigned)std::min(n_items, e.sm_count)), dim3(AP_THREADS), AP_SMEM, st, 1, pdl_enabled());
+    if (cudaLaunchKernelEx(&lp.cfg, attn_tc_persist_kernel, it->second, p, n_items) != cudaSuccess) { e.err = "attn_tc_persist_kernel launch failed"; return CFM_ERR_CUDA; }
+    return 0;
   }
   if (B > 65535) { e.err = "attn_tc: batch too large for the grid"; return CFM_ERR_INVALID; }
   LaunchCfg lc(dim3(AT_T / AT_M, op.heads, B), dim3(256), AT_SMEM, st, 1, pdl_enabled());
