@@ -9,7 +9,8 @@ from ._lib import EngineError, LIB_PATH
 from .engine import Engine, UNetConfig
 from .models import (UNetModel, UNetModelWrapper, InPaintModelWrapper, SuperResModelWrapper, create_model,
                      load_checkpoint, parameter_layout, default_channel_mult)
-from .integrators import NeuralODE, odeint, sample_euler, sample_sde, euler_time_grid, rk_combine, rk_error_sumsq
+from .integrators import (NeuralODE, odeint, sample_euler, sample_sde, euler_time_grid, rk_combine, rk_error_sumsq,
+                          rk_scaled_sumsq, rk_dense_output)
 from .diffusion import (DDPM, EpsModel, Amortized, Replacement, ReconstructionGuidance, InPainting, OutPainting,
                         HyperResolution, get_conditioning, get_likelihood, get_prior_sample_fn,
                         get_conditional_sample_fn, downsample_images, resize_bilinear, extract)

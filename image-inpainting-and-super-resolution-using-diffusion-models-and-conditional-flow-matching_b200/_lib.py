@@ -81,6 +81,10 @@ SIGNATURES = {
     "cfm_rk_error_sumsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_float), C.c_int32, C.c_float, C.c_float, C.c_float,
                                      C.c_int64, C.c_void_p]),
+    "cfm_rk_scaled_sumsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64,
+                                      C.c_void_p]),
+    "cfm_rk_dense_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                      C.c_float, C.c_int64, C.c_void_p]),
     "cfm_make_box_condition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "cfm_quantize_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -1190,6 +1190,27 @@ int cfm_rk_error_sumsq(double* sumsq_dev, const float* y0_dev, const float* y1_d
   return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
 }
 
+int cfm_rk_scaled_sumsq(double* sumsq_dev, const float* a_dev, const float* b_dev, const float* y_dev, float rtol, float atol,
+                        int64_t n, void* stream) {
+  if (!sumsq_dev || !a_dev || !y_dev || n < 0) return CFM_ERR_INVALID;
+  if (cudaMemsetAsync(sumsq_dev, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return CFM_ERR_CUDA;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  double* partial = nullptr; unsigned* ticket = nullptr;
+  if (int rc = rk_scratch(blocks, &partial, &ticket)) return rc;
+  rk_scaled_sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sumsq_dev, partial, ticket, a_dev, b_dev, y_dev, rtol, atol, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
+int cfm_rk_dense_output(float* out_dev, const float* y0_dev, const float* y1_dev, const float* ymid_dev, const float* f0_dev,
+                        const float* f1_dev, float dt, float x, int64_t n, void* stream) {
+  if (!out_dev || !y0_dev || !y1_dev || !ymid_dev || !f0_dev || !f1_dev || n < 0) return CFM_ERR_INVALID;
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  rk_dense_output_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, y0_dev, y1_dev, ymid_dev, f0_dev, f1_dev, dt, x, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : CFM_ERR_CUDA;
+}
+
 // One launch of a DDPM reverse-chain step for a caller that evaluates the eps network itself (a plain Python callable:
 // AD/experiments/main.py:140 passes `lambda xi, i: ema_network(xi, 1.0 * i / ddpm.Ns)`).
 //   phase 0: mask blend of step i (Replacement; before the network call)   phase 1: posterior draw from eps

@@ -314,27 +314,13 @@ __global__ void rk_combine_kernel(float* __restrict__ out, const float* __restri
   }
 }
 
-// Squared error norm of dopri5, deterministic: every block leaves its partial sum (fp64, fixed intra-block order) in
-// partial[blockIdx.x]; the block that finishes LAST (a ticket counter decides who that is - the counter orders nothing
-// arithmetic) adds the partials in block order and writes the result.  The same inputs give the same bits on every run,
-// so an accept / reject decision at ratio ~ 1 cannot flip between runs.
-__global__ void rk_error_sumsq_kernel(double* __restrict__ sumsq, double* __restrict__ partial, unsigned* __restrict__ ticket,
-                                      const float* __restrict__ y0, const float* __restrict__ y1,
-                                      RkPtrs p, float dt, float rtol, float atol, long long n) {
+// Deterministic grid total of one fp64 value per thread (shared by the dopri5 norms below): every block leaves its
+// partial sum (fixed intra-block order) in partial[blockIdx.x]; the block that finishes LAST (a ticket counter decides who
+// that is - the counter orders nothing arithmetic) adds the partials in block order and writes the result.
+__device__ __forceinline__ void rk_block_total(double acc, double* __restrict__ sumsq, double* __restrict__ partial,
+                                               unsigned* __restrict__ ticket) {
   __shared__ double red[32];
   __shared__ bool is_last;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  double acc = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < p.n_k) s = (j == 0) ? __fmul_rn(p.coef[0], p.k[0][i]) : __fadd_rn(s, __fmul_rn(p.coef[j], p.k[j][i]));
-    const float err = __fmul_rn(dt, s);
-    const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(y0[i]), fabsf(y1[i]))));
-    const float r = err / tol;
-    acc += (double)r * (double)r;
-  }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) red[w] = acc;
@@ -355,6 +341,65 @@ __global__ void rk_error_sumsq_kernel(double* __restrict__ sumsq, double* __rest
     for (unsigned b = 0; b < gridDim.x; ++b) tot += ((volatile double*)partial)[b];
     *sumsq = tot;
     *ticket = 0u;
+  }
+}
+
+// Squared error norm of dopri5, deterministic: every block leaves its partial sum (fp64, fixed intra-block order) in
+// partial[blockIdx.x]; the block that finishes LAST (a ticket counter decides who that is - the counter orders nothing
+// arithmetic) adds the partials in block order and writes the result.  The same inputs give the same bits on every run,
+// so an accept / reject decision at ratio ~ 1 cannot flip between runs.
+__global__ void rk_error_sumsq_kernel(double* __restrict__ sumsq, double* __restrict__ partial, unsigned* __restrict__ ticket,
+                                      const float* __restrict__ y0, const float* __restrict__ y1,
+                                      RkPtrs p, float dt, float rtol, float atol, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < p.n_k) s = (j == 0) ? __fmul_rn(p.coef[0], p.k[0][i]) : __fadd_rn(s, __fmul_rn(p.coef[j], p.k[j][i]));
+    const float err = __fmul_rn(dt, s);
+    const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(y0[i]), fabsf(y1[i]))));
+    const float r = err / tol;
+    acc += (double)r * (double)r;
+  }
+  rk_block_total(acc, sumsq, partial, ticket);
+}
+
+// Initial-step heuristic of dopri5 (torchdiffeq `_select_initial_step`): sum_i ((a_i - b_i) / (atol + rtol * |y_i|))^2
+// (b may be NULL), reduced like the error norm above.
+__global__ void rk_scaled_sumsq_kernel(double* __restrict__ sumsq, double* __restrict__ partial, unsigned* __restrict__ ticket,
+                                       const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ y,
+                                       float rtol, float atol, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float num = b ? __fsub_rn(a[i], b[i]) : a[i];
+    const float r = num / __fadd_rn(atol, __fmul_rn(fabsf(y[i]), rtol));
+    acc += (double)r * (double)r;
+  }
+  rk_block_total(acc, sumsq, partial, ticket);
+}
+
+// Dense output of an accepted dopri5 step at fraction x of the step (torchdiffeq `_interp_fit` + `_interp_evaluate`):
+// the quartic through y0, y_mid, y1 with end slopes f0, f1, evaluated by Horner in the reference's operation order.
+__global__ void rk_dense_output_kernel(float* __restrict__ out, const float* __restrict__ y0, const float* __restrict__ y1,
+                                       const float* __restrict__ ym, const float* __restrict__ f0, const float* __restrict__ f1,
+                                       float dt, float x, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float a0 = y0[i], a1 = y1[i], am = ym[i], fa = f0[i], fb = f1[i];
+    // a = 2 dt (fb - fa) - 8 (y1 + y0) + 16 ym
+    const float ca = __fadd_rn(__fsub_rn(__fmul_rn(__fmul_rn(2.f, dt), __fsub_rn(fb, fa)), __fmul_rn(8.f, __fadd_rn(a1, a0))), __fmul_rn(16.f, am));
+    // b = dt (5 fa - 3 fb) + 18 y0 + 14 y1 - 32 ym
+    const float cb = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(dt, __fsub_rn(__fmul_rn(5.f, fa), __fmul_rn(3.f, fb))), __fmul_rn(18.f, a0)), __fmul_rn(14.f, a1)), __fmul_rn(32.f, am));
+    // c = dt (fb - 4 fa) - 11 y0 - 5 y1 + 16 ym
+    const float cc = __fadd_rn(__fsub_rn(__fsub_rn(__fmul_rn(dt, __fsub_rn(fb, __fmul_rn(4.f, fa))), __fmul_rn(11.f, a0)), __fmul_rn(5.f, a1)), __fmul_rn(16.f, am));
+    const float cd = __fmul_rn(dt, fa);
+    float r = __fadd_rn(__fmul_rn(ca, x), cb);
+    r = __fadd_rn(__fmul_rn(r, x), cc);
+    r = __fadd_rn(__fmul_rn(r, x), cd);
+    out[i] = __fadd_rn(__fmul_rn(r, x), a0);
   }
 }
 

@@ -100,6 +100,34 @@ def rk_error_sumsq(y0, y1, ks, coefs, dt, rtol, atol, scratch: torch.Tensor) -> 
     return scratch
 
 
+def rk_scaled_sumsq(a, b, y, rtol, atol, scratch: torch.Tensor) -> torch.Tensor:
+    """Device scalar (float64) = sum(((a - b) / (atol + rtol*|y|))^2); ``b`` may be None (initial-step heuristic)."""
+    lib = _lib.load()
+    _check_state(a, y, *([] if b is None else [b]))
+    if scratch.device != y.device or scratch.dtype != torch.float64 or scratch.numel() < 1:
+        raise ValueError("scratch must be a float64 tensor on the state's device")
+    with torch.cuda.device(y.device):
+        rc = lib.cfm_rk_scaled_sumsq(C.c_void_p(scratch.data_ptr()), C.c_void_p(a.data_ptr()),
+                                     None if b is None else C.c_void_p(b.data_ptr()), C.c_void_p(y.data_ptr()),
+                                     float(rtol), float(atol), y.numel(), _stream(y.device))
+    _lib.check(rc)
+    return scratch
+
+
+def rk_dense_output(y0, y1, y_mid, f0, f1, dt: float, x: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Quartic dense output of an accepted dopri5 step at fraction ``x`` of the step (one fused kernel)."""
+    lib = _lib.load()
+    _check_state(y0, y1, y_mid, f0, f1, *([] if out is None else [out]))
+    if out is None:
+        out = torch.empty_like(y0)
+    with torch.cuda.device(y0.device):
+        rc = lib.cfm_rk_dense_output(C.c_void_p(out.data_ptr()), C.c_void_p(y0.data_ptr()), C.c_void_p(y1.data_ptr()),
+                                     C.c_void_p(y_mid.data_ptr()), C.c_void_p(f0.data_ptr()), C.c_void_p(f1.data_ptr()),
+                                     float(dt), float(x), y0.numel(), _stream(y0.device))
+    _lib.check(rc)
+    return out
+
+
 class NeuralODE(torch.nn.Module):
     """``NeuralODE(vector_field, solver="euler"|"dopri5", atol=, rtol=).trajectory(x, t_span)``."""
 
@@ -273,21 +301,26 @@ def odeint(func: Callable, y0: State, t: torch.Tensor, rtol: float = 1e-7, atol:
             sums = _allreduce_sum(sums, norm_group)
         return max((s / n) ** 0.5 for s, n in zip(sums, gsizes))
 
-    def norm(v: torch.Tensor) -> float:
-        if norm_group is None:
-            return max(float(v[offs[i]:offs[i + 1]].abs().pow(2).mean().sqrt()) for i in range(len(sizes)))
-        sums = _allreduce_sum([float(v[offs[i]:offs[i + 1]].double().pow(2).sum()) for i in range(len(sizes))], norm_group)
+    def scaled_norm(a: torch.Tensor, b: Optional[torch.Tensor], yy: torch.Tensor) -> float:
+        """max over components of RMS((a - b) / (atol + rtol*|y|)) - the initial-step heuristic's norms, one fused
+        deterministic kernel + one host read per component."""
+        sums = []
+        for i in range(len(sizes)):
+            sl = slice(offs[i], offs[i + 1])
+            s = rk_scaled_sumsq(a[sl], None if b is None else b[sl], yy[sl], rtol, atol, scratch)
+            sums.append(float(s.item()))
+        if norm_group is not None:
+            sums = _allreduce_sum(sums, norm_group)
         return max((s / n) ** 0.5 for s, n in zip(sums, gsizes))
 
     y = torch.cat([c.reshape(-1) for c in comps])
     t_list = [float(v) for v in t]
     t0 = t_list[0]
     f0 = f(t0, y)
-    scale = atol + y.abs() * rtol
-    d0, d1 = norm(y / scale), norm(f0 / scale)
+    d0, d1 = scaled_norm(y, None, y), scaled_norm(f0, None, y)
     h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
-    f1 = f(t0 + h0, y + h0 * f0)
-    d2 = norm((f1 - f0) / scale) / h0
+    f1 = f(t0 + h0, rk_combine(y, [f0], [1.0], h0))
+    d2 = scaled_norm(f1, f0, y) / h0
     h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
     dt = min(100 * h0, h1)
 
@@ -309,12 +342,8 @@ def odeint(func: Callable, y0: State, t: torch.Tensor, rtol: float = 1e-7, atol:
             ratio = mixed_norm_of_ratio(y, y1, k, _C_ERR, dt)
             if ratio <= 1:
                 n_accept += 1
-                y_mid = rk_combine(y, k, _C_MID, dt)
-                fa, fb = k[0], k[-1]
-                coeffs = (2 * dt * (fb - fa) - 8 * (y1 + y) + 16 * y_mid,
-                          dt * (5 * fa - 3 * fb) + 18 * y + 14 * y1 - 32 * y_mid,
-                          dt * (fb - 4 * fa) - 11 * y - 5 * y1 + 16 * y_mid,
-                          dt * fa, y)
+                # dense output of this step: (y0, y1, y_mid, f0, f1, dt) - evaluated by one kernel per output time
+                coeffs = (y, y1, rk_combine(y, k, _C_MID, dt), k[0], k[-1], dt)
                 t_lo, t_hi = t_hi, t_hi + dt
                 y, f0 = y1, k[-1]
             if ratio == 0:
@@ -323,8 +352,7 @@ def odeint(func: Callable, y0: State, t: torch.Tensor, rtol: float = 1e-7, atol:
                 factor = min(10.0, max(0.9 / ratio ** 0.2, 1.0 if ratio < 1 else 0.2))
             dt = dt * factor
         xx = (t_out - t_lo) / (t_hi - t_lo)
-        a_, b_, c_, d_, e_ = coeffs
-        outputs.append((((a_ * xx + b_) * xx + c_) * xx + d_) * xx + e_)
+        outputs.append(rk_dense_output(*coeffs, xx))
     if stats is not None:
         stats.update(nfe=nfe, steps=n_steps, accepted=n_accept)
     stacked = torch.stack(outputs)

@@ -25,7 +25,7 @@
  *   cfm_sample_ddpm        <- get_prior_sample_fn / get_conditional_sample_fn(...)(xT[, condition])
  *                             AD/image_diffusion/sampling.py:50-75, 80-133, 209-260
  *                             with DDPM tables AD/image_diffusion/sde_diffusion.py:127-167
- *   cfm_rk_combine, cfm_rk_error_sumsq
+ *   cfm_rk_combine, cfm_rk_error_sumsq, cfm_rk_scaled_sumsq, cfm_rk_dense_output
  *                          <- the state algebra of torchdiffeq.odeint(method="dopri5")
  *                             cifar10/compute_fid.py:83-85, mnist/utils_mnist.py:101-108
  *                             (the accept/reject controller stays on the host)
@@ -220,6 +220,15 @@ int cfm_rk_combine(float* out_dev, const float* y_dev, const float* const* k_dev
 int cfm_rk_error_sumsq(double* sumsq_dev, const float* y0_dev, const float* y1_dev,
                        const float* const* k_dev, const float* coef_host, int32_t n_k, float dt,
                        float rtol, float atol, int64_t n, void* stream);
+
+/* dopri5 initial-step heuristic (torchdiffeq `_select_initial_step`, called from odeint: compute_fid.py:83-85,
+ * utils_mnist.py:101-108): sumsq_dev[0] (double, device) = sum_i ((a_i - b_i) / (atol + rtol*|y_i|))^2; b_dev may be NULL. */
+int cfm_rk_scaled_sumsq(double* sumsq_dev, const float* a_dev, const float* b_dev, const float* y_dev,
+                        float rtol, float atol, int64_t n, void* stream);
+/* dopri5 dense output (torchdiffeq `_interp_fit` / `_interp_evaluate`): the quartic through y0, y_mid, y1 with end
+ * slopes f0, f1 of an accepted step of length dt, evaluated at fraction x in [0, 1] of the step. */
+int cfm_rk_dense_output(float* out_dev, const float* y0_dev, const float* y1_dev, const float* ymid_dev,
+                        const float* f0_dev, const float* f1_dev, float dt, float x, int64_t n, void* stream);
 
 /* Box-mask condition on the device: boxes_dev[b] = {h, w} (int32 pairs, drawn on the host
  * with the reference's RNG order).  inpaint: cond = images with box := pad_value;

@@ -359,6 +359,34 @@ def test_error_norm_is_deterministic(pkg, cuda):
         pkg.rk_combine(y0.cpu(), [ks[0].cpu()], [1.0], 0.1)          # raw-pointer kernels: CPU tensors are rejected
 
 
+def test_dopri5_dense_output_and_initial_step_kernels(pkg, cuda):
+    """The interpolant and the initial-step norms of dopri5 as native kernels: the dense output is bit-identical to the
+    oracle's expression (oracle/integrators.py, torchdiffeq `_interp_fit` / `_interp_evaluate`) evaluated by torch on the
+    CPU in fp32; the scaled norm equals the fp64 sum of the fp32 ratios squared and is run-to-run deterministic."""
+    n = 4 * 3 * 16 * 16 + 3
+    g = torch.Generator().manual_seed(3)
+    y, y1, ym, fa, fb = (torch.randn(n, generator=g) for _ in range(5))
+    dt, xx = 0.0375, 0.6180339887
+    coeffs = (2 * dt * (fb - fa) - 8 * (y1 + y) + 16 * ym,
+              dt * (5 * fa - 3 * fb) + 18 * y + 14 * y1 - 32 * ym,
+              dt * (fb - 4 * fa) - 11 * y - 5 * y1 + 16 * ym,
+              dt * fa, y)
+    a_, b_, c_, d_, e_ = coeffs
+    want = (((a_ * xx + b_) * xx + c_) * xx + d_) * xx + e_
+    got = pkg.rk_dense_output(y.to(cuda), y1.to(cuda), ym.to(cuda), fa.to(cuda), fb.to(cuda), dt, xx).cpu()
+    assert torch.equal(got, want), float((got - want).abs().max())
+    scratch = torch.zeros(1, dtype=torch.float64, device=cuda)
+    for b in (None, fb):
+        vals = [float(pkg.rk_scaled_sumsq(fa.to(cuda), None if b is None else b.to(cuda), y.to(cuda), 1e-4, 1e-5, scratch).item())
+                for _ in range(3)]
+        assert len(set(vals)) == 1
+        num = fa if b is None else fa - b
+        ref = float((num / (1e-5 + y.abs() * 1e-4)).double().pow(2).sum())
+        assert abs(vals[0] - ref) <= 1e-12 * ref
+    with pytest.raises(ValueError):
+        pkg.rk_dense_output(y, y1, ym, fa, fb, dt, xx)               # CPU tensors are rejected
+
+
 def test_input_validation(pkg, cuda):
     """shapes, devices and labels are checked before raw pointers reach the kernels."""
     cfg, params, net = chain_net(pkg, cuda, 1)
