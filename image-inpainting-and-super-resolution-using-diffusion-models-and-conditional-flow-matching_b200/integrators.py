@@ -151,6 +151,7 @@ class NeuralODE(torch.nn.Module):
     @torch.no_grad()
     def trajectory(self, x: torch.Tensor, t_span: torch.Tensor) -> torch.Tensor:
         if self.solver == "dopri5":
+            _warn_bf16_tolerance(self.vf, self.rtol, self.atol)
             return odeint(self._call, x, t_span, rtol=self.rtol, atol=self.atol, method="dopri5")
         ts, dts = euler_time_grid(t_span)
         if type(self.vf) is UNetModelWrapper and self.vf.num_classes is None:
@@ -235,6 +236,18 @@ def sample_sde(drift, score, x0: torch.Tensor, ts: torch.Tensor, dt: float, sigm
 State = Union[torch.Tensor, Tuple[torch.Tensor, ...]]
 
 
+def _warn_bf16_tolerance(func, rtol: float, atol: float) -> None:
+    """The reference integrates an fp32 network at atol = rtol = 1e-4 (compute_fid.py:83-85).  A bf16 vector field carries
+    ~4e-3 of relative rounding noise per evaluation: at tolerances tighter than that the step controller ends up
+    resolving the noise (more rejected steps) - say so instead of silently spending NFEs."""
+    model = getattr(func, "vf", func)
+    if getattr(model, "precision", None) == "bf16" and min(rtol, atol) < 1e-3:
+        import warnings
+        warnings.warn(f"dopri5 with rtol={rtol:g}, atol={atol:g} on a precision='bf16' model: the vector field's rounding "
+                      "noise (~4e-3 relative) exceeds the tolerance; build the model with precision='fp32' for adaptive "
+                      "integration at this tolerance", RuntimeWarning, stacklevel=3)
+
+
 def _allreduce_sum(values: Sequence[float], group) -> List[float]:
     """Sum a few host scalars over the ranks of ``group`` (NCCL: on the device; gloo: on the host)."""
     import torch.distributed as dist
@@ -258,6 +271,7 @@ def odeint(func: Callable, y0: State, t: torch.Tensor, rtol: float = 1e-7, atol:
         return NeuralODE(func, "euler").trajectory(y0, t)
     if method != "dopri5":
         raise NotImplementedError(method)
+    _warn_bf16_tolerance(func, rtol, atol)
     is_tuple = isinstance(y0, (tuple, list))
     comps = [c.to(torch.float32).contiguous() for c in (y0 if is_tuple else [y0])]
     dev = comps[0].device

@@ -124,6 +124,28 @@ def test_dopri5_matches_oracle_controller(pkg, cuda):
     assert ca.shape == (2, 4, 3, 16, 16) and abs(float(cb[-1, 0, 0]) - np.e) < 1e-3
 
 
+def test_dopri5_bf16_is_flagged_and_bounded(pkg, cuda):
+    """the reference runs dopri5 at atol = rtol = 1e-4 on an fp32 net.  A bf16 model at that tolerance raises a
+    RuntimeWarning (its rounding noise is above the tolerance); at a tolerance the precision supports it stays quiet, and
+    its NFE count and result stay close to the fp32 run."""
+    import warnings
+    cfg, params, m32 = small_cfm(pkg, cuda, "fp32")
+    _, _, m16 = small_cfm(pkg, cuda, "bf16")
+    x0 = torch.randn(4, 3, 16, 16, device=cuda)
+    t = torch.linspace(0, 1, 2)
+    s32, s16 = {}, {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        ref = pkg.odeint(m32, x0, t, rtol=1e-4, atol=1e-4, method="dopri5", stats=s32)
+        got = pkg.odeint(m16, x0, t, rtol=5e-3, atol=5e-3, method="dopri5", stats=s16)
+    with pytest.warns(RuntimeWarning, match="bf16"):
+        pkg.odeint(m16, x0, t, rtol=1e-4, atol=1e-4, method="dopri5")
+    with pytest.warns(RuntimeWarning, match="bf16"):
+        pkg.NeuralODE(m16, solver="dopri5", atol=1e-4, rtol=1e-4).trajectory(x0, t)
+    assert s16["nfe"] <= s32["nfe"]
+    assert rel_l2(got[-1].cpu(), ref[-1].cpu()) < 5e-2
+
+
 def ddpm_setup(pkg, cuda, precision, in_ch, Ns):
     cfg = O.config_from_create_model(image_size=16, in_channels=in_ch, out_channels=1, num_channels=32, num_res_blocks=1,
                                      channel_mult="1,2", attention_resolutions="8", resblock_updown=True)
