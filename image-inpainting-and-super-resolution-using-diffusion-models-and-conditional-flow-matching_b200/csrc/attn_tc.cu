@@ -213,26 +213,41 @@ constexpr int AP_V_OFF = 3 * AP_BUF;
 constexpr int AP_BAR_OFF = AP_V_OFF + 32768;
 constexpr int AP_SMEM = AP_BAR_OFF + 256 + 1024;
 
+// 2^x for x <= 0 on the FMA pipe: round-to-nearest split x = n + f (magic-number add), cubic minimax of 2^f on
+// [-0.5, 0.5] (relative error 7.5e-5 - the result is rounded to bf16, eps 3.9e-3), n added to the exponent field.  One
+// exponential in four goes this way: the softmax pass is bound by the 16-lane MUFU pipe, the FMA pipe has slots to spare.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                   // 1.5 * 2^23: n sits in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float pl = fmaf(0.05517165f, f, 0.24261112f);
+  pl = fmaf(pl, f, 0.69326099f);
+  pl = fmaf(pl, f, 0.99992807f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
 __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __grid_constant__ CUtensorMap map, const AttnTcParams p,
                                                                         int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_qk = (uint64_t*)(smem + AP_BAR_OFF);   // [2]
   uint64_t* full_v = full_qk + 2;
-  uint64_t* bar_s = full_qk + 3;                         // S0 and S1 of the item complete
-  uint64_t* bar_p = full_qk + 4;                         // [2] 128 arrivals: P_g written, S_g no longer needed
-  uint64_t* bar_o = full_qk + 6;                         // [2] O_g complete
-  uint64_t* bar_e = full_qk + 8;                         // 256 arrivals: O read out of TMEM
-  uint64_t* pv_done = full_qk + 9;                       // [2] by item parity: every MMA of the item has retired
-  uint32_t* tmem_slot = (uint32_t*)(full_qk + 11);
+  uint64_t* bar_s = full_qk + 3;                         // [group][key half]: S_g columns of that half complete
+  uint64_t* bar_p = full_qk + 7;                         // [group][key half] 128 arrivals: P_g of that half written
+  uint64_t* bar_o = full_qk + 11;                        // [2] O_g complete
+  uint64_t* bar_e = full_qk + 13;                        // [2] 128 arrivals: O_g read out of TMEM
+  uint64_t* pv_done = full_qk + 15;                      // [2] by item parity: every MMA of the item has retired
+  uint32_t* tmem_slot = (uint32_t*)(full_qk + 17);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   pdl_launch_dependents();
   if (tid == 0) {
     prefetch_tmap(&map);
-    mbar_init(&full_qk[0], 1); mbar_init(&full_qk[1], 1); mbar_init(full_v, 1); mbar_init(bar_s, 1);
-    mbar_init(&bar_p[0], 128); mbar_init(&bar_p[1], 128); mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
-    mbar_init(bar_e, 256); mbar_init(&pv_done[0], 1); mbar_init(&pv_done[1], 1);
+    mbar_init(&full_qk[0], 1); mbar_init(&full_qk[1], 1); mbar_init(full_v, 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 128); }
+    mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1); mbar_init(&bar_e[0], 128); mbar_init(&bar_e[1], 128);
+    mbar_init(&pv_done[0], 1); mbar_init(&pv_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -267,7 +282,9 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc_s = make_idesc(AT_M, AT_T);
+    // S_g is issued as two 128-key halves with a barrier each, so the max pass starts a quarter of the way into the S
+    // MMAs; O_g = P_g V runs over the first 128 keys while the softmax is still writing the second 128.
+    const uint32_t idesc_s = make_idesc(AT_M, AT_T / 2);
     const uint32_t idesc_o = make_idesc_major(AT_M, AT_D, 0, 1);
     const uint32_t vbase = smem_u32(smem + AP_V_OFF);
     int j = 0;
@@ -276,34 +293,40 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
       const uint32_t qk = smem_u32(smem + ((2 * j) % 3) * AP_BUF);
       const uint32_t p1 = smem_u32(smem + ((2 * j + 1) % 3) * AP_BUF);
       mbar_wait(&full_qk[j & 1], (uint32_t)((j >> 1) & 1));
-      if (j > 0) mbar_wait(bar_e, par ^ 1);              // O of the previous item has left TMEM
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t kd = make_desc_sw128(qk + 32768);
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < 2; ++m) {
+        if (j > 0) mbar_wait(&bar_e[m], par ^ 1);        // O_m of the previous item has left TMEM
+        tc_fence_after();
+        if (elect_one()) {
           const uint64_t qd = make_desc_sw128(qk + m * 16384);
 #pragma unroll
-          for (int k = 0; k < AT_D / 16; ++k) umma_bf16(tmem + (uint32_t)(m * 256), qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k > 0);
-        }
-        umma_commit(bar_s);
-      }
-      __syncwarp();
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint64_t kd = make_desc_sw128(qk + 32768 + hf * 16384);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        mbar_wait(&bar_p[g], par);
-        if (g == 0) mbar_wait(full_v, par);
+            for (int k = 0; k < AT_D / 16; ++k)
+              umma_bf16(tmem + (uint32_t)(m * 256 + hf * 128), qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k > 0);
+            umma_commit(&bar_s[m * 2 + hf]);
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int step = 0; step < 4; ++step) {
+        const int g = step & 1, hf = step >> 1;          // P0 first half, P1 first half, P0 second half, P1 second half
+        mbar_wait(&bar_p[g * 2 + hf], par);
+        if (step == 0) mbar_wait(full_v, par);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t pbase = g == 0 ? qk : p1;
 #pragma unroll
-          for (int k = 0; k < AT_T / 16; ++k) {
+          for (int kk = 0; kk < AT_T / 32; ++kk) {
+            const int k = hf * (AT_T / 32) + kk;
             const uint64_t ad = make_desc_sw128(pbase + (k >> 2) * 16384 + (k & 3) * 32);
             const uint64_t bd = make_desc_sw128_mn(vbase + k * 2048, 1024);
             umma_bf16(tmem + (uint32_t)(g * 256), ad, bd, idesc_o, k > 0);
           }
-          umma_commit(&bar_o[g]);
-          if (g == 1) umma_commit(&pv_done[j & 1]);
+          if (hf == 1) umma_commit(&bar_o[g]);
+          if (step == 3) umma_commit(&pv_done[j & 1]);
         }
         __syncwarp();
       }
@@ -318,26 +341,29 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
       const uint32_t par = (uint32_t)(j & 1);
       const int b = it / p.heads, h = it - b * p.heads;
       uint8_t* prow = smem + ((g == 0 ? 2 * j : 2 * j + 1) % 3) * AP_BUF + r * 128;
-      mbar_wait(bar_s, par);
-      tc_fence_after();
       // both passes keep the NEXT 32 scores in flight (tcgen05.ld) while the current 32 are consumed: with one thread per
       // row and two warps per scheduler the TMEM read latency is otherwise the whole cost of the max pass
       float mx = -INFINITY;
       {
         uint32_t va[32], vb[32];
-        tmem_ld32(t_row, va);
 #pragma unroll 1
         for (int c0 = 0; c0 < AT_T; c0 += 64) {
+          if ((c0 & 127) == 0) {                          // first touch of a 128-key half: its S MMAs have retired
+            mbar_wait(&bar_s[g * 2 + (c0 >> 7)], par);
+            tc_fence_after();
+            tmem_ld32(t_row + (uint32_t)c0, va);
+          }
           tmem_ld_wait();
           tmem_ld32(t_row + (uint32_t)(c0 + 32), vb);
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
           tmem_ld_wait();
-          if (c0 + 64 < AT_T) tmem_ld32(t_row + (uint32_t)(c0 + 64), va);
+          if ((c0 & 127) == 0) tmem_ld32(t_row + (uint32_t)(c0 + 64), va);
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
         }
       }
+      if (g == 0) { mbar_wait(&bar_s[3], par); tc_fence_after(); }   // P0 overlays Q1 | K: S1 must have read them
       const float mxs = mx * p.scale_log2;
       float sum = 0.f;
       auto emit = [&](const uint32_t (&v)[32], int c0) {
@@ -349,8 +375,10 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
           __nv_bfloat162* o2 = (__nv_bfloat162*)&o4;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(v[i * 8 + 2 * q]), p.scale_log2, -mxs));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(v[i * 8 + 2 * q + 1]), p.scale_log2, -mxs));
+            const float x0 = fmaf(__uint_as_float(v[i * 8 + 2 * q]), p.scale_log2, -mxs);
+            const float x1 = fmaf(__uint_as_float(v[i * 8 + 2 * q + 1]), p.scale_log2, -mxs);
+            const float e0 = q == 3 ? ex2_poly(x0) : ex2_approx(x0);
+            const float e1 = q == 3 ? ex2_poly(x1) : ex2_approx(x1);
             sum += e0 + e1;
             o2[q] = __floats2bfloat162_rn(e0, e1);
           }
@@ -368,11 +396,16 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
           tmem_ld_wait();
           if (c0 + 64 < AT_T) tmem_ld32(t_row + (uint32_t)(c0 + 64), va);
           emit(vb, c0 + 32);
+          if (c0 == 64) {           // P of the first 128 keys is complete: the PV MMAs over them may start
+            fence_proxy_async();    // P went through the generic proxy; the MMA reads it through the async proxy
+            tc_fence_before();
+            mbar_arrive(&bar_p[g * 2]);
+          }
         }
       }
-      fence_proxy_async();          // P went through the generic proxy; the MMA reads it through the async proxy
+      fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_p[g]);
+      mbar_arrive(&bar_p[g * 2 + 1]);
       mbar_wait(&bar_o[g], par);
       tc_fence_after();
       const float inv = 1.0f / sum;
@@ -382,7 +415,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
       tmem_ld32(t_row + 32u, v1);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar_e);           // the next item's S may overwrite these TMEM columns
+      mbar_arrive(&bar_e[g]);       // the next item's S_g may overwrite these TMEM columns
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const uint32_t* v = hh ? v1 : v0;
