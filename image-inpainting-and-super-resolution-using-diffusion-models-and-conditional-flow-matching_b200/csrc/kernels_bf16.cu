@@ -211,7 +211,7 @@ static GnGeom gn_geometry(const Op& op) {
   g.cpg = C / 32;
   const int base = g.cpg / gcd_i(g.cpg, 8) * 8;        // lcm(cpg, 8): smallest legal slab
   if (base > GN_MAX_SLAB || C % base) return g;
-  static const int target = [] { const char* v = tuning_env("CFM_GN_ITEM_BYTES"); return v ? atoi(v) : 64 * 1024; }();
+  static const int target = [] { const char* v = tuning_env("CFM_GN_ITEM_BYTES"); return v ? atoi(v) : 96 * 1024; }();
   // slab: a multiple of `base` dividing C, preferably a whole number of 64-byte DRAM bursts per pixel (32 channels;
   // e.g. 96 for C = 384, where 48-channel slabs would straddle bursts) and at most 64 channels when that works
   static const int pref_slab = [] { const char* v = tuning_env("CFM_GN_PREF_SLAB"); return v ? atoi(v) : 64; }();

@@ -1,20 +1,34 @@
-"""End-to-end sampling throughput of every BASELINE.json config through the public Python API (one GPU, bf16,
-CUDA graphs, synthetic data, seeded weights).  Prints one line per config and writes gpurun_out/sampler_sweep.json.
-usage: python profiles/sampler_sweep.py [config-prefix ...]"""
+"""End-to-end sampling throughput of every BASELINE.json config through the public Python API (bf16, CUDA graphs,
+synthetic data, seeded weights).  One GPU, or N GPUs under torchrun (one rank per GPU, the per-GPU batch of the config
+on every rank = weak scaling, no collective in the loop; time = CUDA events, max over ranks; samples/s = whole job).
+Prints one line per config and writes gpurun_out/sampler_sweep[_nN].json.
+usage: python profiles/sampler_sweep.py [config-prefix ...]
+       python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P profiles/sampler_sweep.py"""
 import json, os, sys, time
 import torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import __graft_entry__ as g
-g.build(); pkg = g.load_package()
+RANK, WORLD, LOCAL = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(LOCAL)
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+if RANK == 0: g.build()
+if WORLD > 1: dist.barrier()
+pkg = g.load_package()
 from oracle import unet as O
 
 
 def timed(fn, reps=2):
     fn(); torch.cuda.synchronize()          # warm-up (graph capture, tensor maps)
-    t0 = time.time()
+    if WORLD > 1: dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(reps): fn()
-    torch.cuda.synchronize()
-    return (time.time() - t0) / reps
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device='cuda')
+    if WORLD > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / 1e3
 
 
 def wrapper(cls, cfg_kw, oracle_cfg, precision="bf16", **kw):
@@ -29,6 +43,7 @@ def rel(a, b):
 
 def drift(run_bf16, run_fp32):
     """Final-sample drift of the bf16 sampler against the fp32 (exact-mode) engine on the same inputs / noise seed."""
+    if RANK: return float('nan')
     a, b = run_bf16(), run_fp32()
     return rel(a, b)
 
@@ -46,7 +61,7 @@ if want("0"):
     dt = timed(lambda: pkg.sample_euler(m, x0, ts, cond=con, cond_drift=True, use_graph=True))
     m32 = wrapper(pkg.InPaintModelWrapper, dict(dim=(1, 28, 28), num_channels=32, num_res_blocks=1), cfg, precision="fp32", num_classes=None, class_cond=True)
     d = drift(lambda: pkg.sample_euler(m, x0[:4], ts, cond=con[:4], cond_drift=True), lambda: pkg.sample_euler(m32, x0[:4], ts, cond=con[:4], cond_drift=True))
-    out["0 mnist_cfm_inpaint b64 100-step Euler"] = {"s": dt, "samples_per_s": B / dt, "evals": 100, "drift_bf16_vs_fp32": d}
+    out["0 mnist_cfm_inpaint b64 100-step Euler"] = {"s": dt, "samples_per_s": WORLD * B / dt, "n_gpus": WORLD, "evals": 100, "drift_bf16_vs_fp32": d}
 if want("2"):
     B = 4096
     cfg = O.config_from_wrapper((1, 28, 28), 32, 1, class_cond=True, num_classes=10)
@@ -56,7 +71,7 @@ if want("2"):
     dt = timed(lambda: pkg.sample_euler(m, x0, ts, y=y, guidance_weight=2.0, use_graph=True), reps=1)
     m32 = wrapper(pkg.UNetModelWrapper, dict(dim=(1, 28, 28), num_channels=32, num_res_blocks=1), cfg, precision="fp32", num_classes=10, class_cond=True)
     d = drift(lambda: pkg.sample_euler(m, x0[:8], ts, y=y[:8], guidance_weight=2.0), lambda: pkg.sample_euler(m32, x0[:8], ts, y=y[:8], guidance_weight=2.0))
-    out["2 mnist_classcond CFG b4096 100-step Euler x2 evals"] = {"s": dt, "samples_per_s": B / dt, "evals": 200, "drift_bf16_vs_fp32": d}
+    out["2 mnist_classcond CFG b4096 100-step Euler x2 evals"] = {"s": dt, "samples_per_s": WORLD * B / dt, "n_gpus": WORLD, "evals": 200, "drift_bf16_vs_fp32": d}
 if want("3a"):
     B = 256
     cfg = O.config_from_create_model(image_size=28, in_channels=2, out_channels=1, num_channels=32, num_res_blocks=1, channel_mult="1, 2, 2", resblock_updown=True)
@@ -72,7 +87,7 @@ if want("3a"):
     f16 = pkg.get_conditional_sample_fn(pkg.EpsModel(net, ddpm), ddpm, pkg.Amortized(), lik, seed=5)
     f32 = pkg.get_conditional_sample_fn(pkg.EpsModel(net32, ddpm), ddpm, pkg.Amortized(), lik, seed=5)
     d = drift(lambda: f16(xT[:4], cond[:4]), lambda: f32(xT[:4], cond[:4]))
-    out["3a ddpm_mnist amortized inpainting b256 1000 steps"] = {"s": dt, "samples_per_s": B / dt, "evals": 1000, "drift_bf16_vs_fp32": d}
+    out["3a ddpm_mnist amortized inpainting b256 1000 steps"] = {"s": dt, "samples_per_s": WORLD * B / dt, "n_gpus": WORLD, "evals": 1000, "drift_bf16_vs_fp32": d}
 if want("3b"):
     B = 128
     kw = dict(image_size=64, in_channels=3, out_channels=3, num_channels=128, num_res_blocks=1, resblock_updown=True, num_head_channels=64, use_scale_shift_norm=True, num_heads=4)
@@ -90,7 +105,7 @@ if want("3b"):
     f16 = pkg.get_conditional_sample_fn(pkg.EpsModel(net, d40), d40, pkg.Replacement(), lik, seed=5)
     f32 = pkg.get_conditional_sample_fn(pkg.EpsModel(net32, d40), d40, pkg.Replacement(), lik, seed=5)
     d = drift(lambda: f16(xT[:2], cond[:2]), lambda: f32(xT[:2], cond[:2]))
-    out["3b ddpm_flowers64 RePaint-style replacement b128 1000 steps"] = {"s": dt, "samples_per_s": B / dt, "evals": 1000, "drift_bf16_vs_fp32": d, "drift_chain_steps": 40}
+    out["3b ddpm_flowers64 RePaint-style replacement b128 1000 steps"] = {"s": dt, "samples_per_s": WORLD * B / dt, "n_gpus": WORLD, "evals": 1000, "drift_bf16_vs_fp32": d, "drift_chain_steps": 40}
 if want("4"):
     B = 32
     cfg = O.config_from_wrapper((3, 128, 128), 128, 1, extra_in_channels=3)
@@ -102,10 +117,14 @@ if want("4"):
     m32 = wrapper(pkg.SuperResModelWrapper, dict(dim=(3, 128, 128), num_channels=128, num_res_blocks=1), cfg, precision="fp32", num_classes=None, class_cond=True)
     t10 = torch.linspace(0, 1, 11)
     d = drift(lambda: pkg.sample_euler(m, x0[:1], t10, cond=up[:1]), lambda: pkg.sample_euler(m32, x0[:1], t10, cond=up[:1]))
-    out["4 superres 32->128 CFM b32 50-step Euler"] = {"s": dt, "samples_per_s": B / dt, "evals": 50, "drift_bf16_vs_fp32": d, "drift_steps": 10}
+    out["4 superres 32->128 CFM b32 50-step Euler"] = {"s": dt, "samples_per_s": WORLD * B / dt, "n_gpus": WORLD, "evals": 50, "drift_bf16_vs_fp32": d, "drift_steps": 10}
 
 for k, v in out.items():
-    print(f"{k:62s} {v['s']:8.3f} s  {v['samples_per_s']:10.1f} samples/s  {v['s'] / v['evals'] * 1e3:8.3f} ms per U-Net eval batch  "
+    if RANK: break
+    print(f"[{WORLD} GPU] " + f"{k:62s} {v['s']:8.3f} s  {v['samples_per_s']:10.1f} samples/s  {v['s'] / v['evals'] * 1e3:8.3f} ms per U-Net eval batch  "
           f"final-sample drift bf16 vs fp32 engine {v.get('drift_bf16_vs_fp32', float('nan')):.2e}", flush=True)
-os.makedirs('gpurun_out', exist_ok=True)
-json.dump(out, open('gpurun_out/sampler_sweep.json', 'w'), indent=1)
+if RANK == 0:
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(out, open('gpurun_out/sampler_sweep' + (f'_n{WORLD}' if WORLD > 1 else '') + '.json', 'w'), indent=1)
+if WORLD > 1:
+    dist.barrier(); dist.destroy_process_group()
