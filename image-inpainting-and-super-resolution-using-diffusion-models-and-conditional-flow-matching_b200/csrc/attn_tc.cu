@@ -213,19 +213,6 @@ constexpr int AP_V_OFF = 3 * AP_BUF;
 constexpr int AP_BAR_OFF = AP_V_OFF + 32768;
 constexpr int AP_SMEM = AP_BAR_OFF + 256 + 1024;
 
-// 2^x for x <= 0 on the FMA pipe: round-to-nearest split x = n + f (magic-number add), cubic minimax of 2^f on
-// [-0.5, 0.5] (relative error 7.5e-5 - the result is rounded to bf16, eps 3.9e-3), n added to the exponent field.  One
-// exponential in four goes this way: the softmax pass is bound by the 16-lane MUFU pipe, the FMA pipe has slots to spare.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;                   // 1.5 * 2^23: n sits in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float pl = fmaf(0.05517165f, f, 0.24261112f);
-  pl = fmaf(pl, f, 0.69326099f);
-  pl = fmaf(pl, f, 0.99992807f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
-}
-
 __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __grid_constant__ CUtensorMap map, const AttnTcParams p,
                                                                         int n_items) {
   extern __shared__ uint8_t smem_raw[];
@@ -377,8 +364,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
           for (int q = 0; q < 4; ++q) {
             const float x0 = fmaf(__uint_as_float(v[i * 8 + 2 * q]), p.scale_log2, -mxs);
             const float x1 = fmaf(__uint_as_float(v[i * 8 + 2 * q + 1]), p.scale_log2, -mxs);
-            const float e0 = q == 3 ? ex2_poly(x0) : ex2_approx(x0);
-            const float e1 = q == 3 ? ex2_poly(x1) : ex2_approx(x1);
+            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
             sum += e0 + e1;
             o2[q] = __floats2bfloat162_rn(e0, e1);
           }

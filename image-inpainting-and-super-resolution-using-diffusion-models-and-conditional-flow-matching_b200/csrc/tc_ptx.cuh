@@ -261,4 +261,5 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
                ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+
 }  // namespace cfm
