@@ -1,14 +1,13 @@
 // Fused attention core on tcgen05/TMEM for the U-Net's AttentionBlock (unet.py:424-483):
 //   a = softmax((q s)^T (k s)) v,  s = ch^-1/4, per (sample, head); T = 256 tokens, ch = 64.
 //
-// One CTA per (sample, head, 128-query tile).  TMA brings the head's Q tile, K and V (128-byte
-// channel rows of the NHWC qkv tensor) into SWIZZLE_128B shared memory.  S = Q K^T is one
-// 128x256x64 UMMA chain into TMEM; each of the 128 threads owns one query row, reads it back with
-// tcgen05.ld, does an exact two-pass softmax in fp32 and writes bf16 P into shared memory in the
-// K-major swizzled layout (re-using the Q/K buffers); O = P V is a second UMMA chain (V consumed
-// as an MN-major B operand straight from its NHWC rows) into the same TMEM columns; the epilogue
-// normalises by the row sum and stores bf16.  96 KB smem + 256 TMEM columns -> 2 CTAs per SM, so
-// one CTA's softmax overlaps the other's MMAs and loads.
+// TMA brings a head's Q tiles, K and V (128-byte channel rows of the NHWC qkv tensor) into SWIZZLE_128B shared memory.
+// S = Q K^T runs as UMMA chains into TMEM; each softmax thread owns one query row, reads it back with tcgen05.ld, does
+// an exact two-pass softmax in fp32 and writes bf16 P into shared memory in the K-major swizzled layout; O = P V is a
+// second UMMA chain (V consumed as an MN-major B operand straight from its NHWC rows) into the TMEM columns S has
+// vacated; the epilogue normalises by the row sum and stores bf16.
+// The shipped kernel is attn_tc_persist_kernel (one persistent CTA per SM, both query tiles of a head in flight); the
+// round-1 kernel (one CTA per query tile, two CTAs per SM) is compiled only into -DCFM_TUNING builds for A/B runs.
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -21,9 +20,11 @@ namespace cfm {
 void* tensor_ptr(const Engine& e, int id, int B);
 
 constexpr int AT_T = 256, AT_D = 64, AT_M = 128;
+#ifdef CFM_TUNING
 constexpr int AT_V_OFF = 0, AT_Q_OFF = 32768, AT_K_OFF = 49152, AT_P_OFF = 32768;
 constexpr int AT_BAR_OFF = 98304, AT_XCH_OFF = 98304 + 64;
 constexpr int AT_SMEM = AT_XCH_OFF + 2 * 256 * 4 + 1024;
+#endif
 
 struct AttnTcParams { int heads, C, new_order; float scale_log2; bf16* out; int pf_db, pf_dh; };
 
@@ -33,6 +34,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+#ifdef CFM_TUNING
 // 256 threads per CTA: thread t and thread t + 128 share query row (t & 127) - warps w and w + 4 may both read TMEM
 // lanes 32 (w & 3) .. +31 - and split the 256 keys (softmax) / the 64 output channels (epilogue) between them, so the
 // serial load -> max -> exp -> store chain of a row is half as long and 16 warps per SM hide its latency.
@@ -191,6 +193,8 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
+
+#endif  // CFM_TUNING
 
 // ------------------------------------------------------------------------------------------------
 // Persistent, pipelined variant (round 2): one CTA per SM walks (sample, head) items; both 128-query tiles of an item
@@ -445,11 +449,6 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_attn_encode = (EncodeTiledFn)fn;
   }
-  static DeviceOnce attr;
-  if (attr.pending(e.device)) {
-    if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_tc_kernel) failed"; return CFM_ERR_CUDA; }
-    attr.done(e.device);
-  }
   AttnTcPlan& pl = g_attn_plans[&op];
   const void* qkv = tensor_ptr(e, op.src0, B);
   auto it = pl.maps.find(B);
@@ -469,26 +468,30 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
   p.heads = op.heads; p.C = op.Cin; p.new_order = e.cfg.use_new_attention_order;
   p.scale_log2 = (1.0f / sqrtf((float)op.ch)) * 1.4426950408889634f;
   p.out = (bf16*)tensor_ptr(e, op.out, B);
-  {
-    // two CTAs per SM, two CTAs (query tiles) per (sample, head): one wave covers sm_count pairs
-    static const int pf = [] { const char* v = tuning_env("CFM_ATTN_PREFETCH"); return v ? atoi(v) : 1; }();
-    p.pf_db = pf * e.sm_count / op.heads; p.pf_dh = pf * e.sm_count % op.heads;
-  }
-  static const bool persist = [] { const char* v = tuning_env("CFM_DISABLE_ATTN_PERSIST"); return !(v && v[0] == '1'); }();
-  if (persist) {
-    static DeviceOnce attr2;
-    if (attr2.pending(e.device)) {
-      if (cudaFuncSetAttribute(attn_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_tc_persist_kernel) failed"; return CFM_ERR_CUDA; }
-      attr2.done(e.device);
+#ifdef CFM_TUNING
+  if (const char* v = tuning_env("CFM_DISABLE_ATTN_PERSIST"); v && v[0] == '1') {      // round-1 kernel, A/B only
+    static DeviceOnce attr;
+    if (attr.pending(e.device)) {
+      if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_tc_kernel) failed"; return CFM_ERR_CUDA; }
+      attr.done(e.device);
     }
-    const int n_items = B * op.heads;
-    LaunchCfg lp(dim3((unsigned)std::min(n_items, e.sm_count)), dim3(AP_THREADS), AP_SMEM, st, 1, pdl_enabled());
-    if (cudaLaunchKernelEx(&lp.cfg, attn_tc_persist_kernel, it->second, p, n_items) != cudaSuccess) { e.err = "attn_tc_persist_kernel launch failed"; return CFM_ERR_CUDA; }
+    // two CTAs per SM, two CTAs (query tiles) per (sample, head): one wave covers sm_count pairs
+    static const int pf = [] { const char* v2 = tuning_env("CFM_ATTN_PREFETCH"); return v2 ? atoi(v2) : 1; }();
+    p.pf_db = pf * e.sm_count / op.heads; p.pf_dh = pf * e.sm_count % op.heads;
+    if (B > 65535) { e.err = "attn_tc: batch too large for the grid"; return CFM_ERR_INVALID; }
+    LaunchCfg lc(dim3(AT_T / AT_M, op.heads, B), dim3(256), AT_SMEM, st, 1, pdl_enabled());
+    if (cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel, it->second, p) != cudaSuccess) { e.err = "attn_tc_kernel launch failed"; return CFM_ERR_CUDA; }
     return 0;
   }
-  if (B > 65535) { e.err = "attn_tc: batch too large for the grid"; return CFM_ERR_INVALID; }
-  LaunchCfg lc(dim3(AT_T / AT_M, op.heads, B), dim3(256), AT_SMEM, st, 1, pdl_enabled());
-  if (cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel, it->second, p) != cudaSuccess) { e.err = "attn_tc_kernel launch failed"; return CFM_ERR_CUDA; }
+#endif
+  static DeviceOnce attr2;
+  if (attr2.pending(e.device)) {
+    if (cudaFuncSetAttribute(attn_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM) != cudaSuccess) { e.err = "cudaFuncSetAttribute(attn_tc_persist_kernel) failed"; return CFM_ERR_CUDA; }
+    attr2.done(e.device);
+  }
+  const int n_items = B * op.heads;
+  LaunchCfg lp(dim3((unsigned)std::min(n_items, e.sm_count)), dim3(AP_THREADS), AP_SMEM, st, 1, pdl_enabled());
+  if (cudaLaunchKernelEx(&lp.cfg, attn_tc_persist_kernel, it->second, p, n_items) != cudaSuccess) { e.err = "attn_tc_persist_kernel launch failed"; return CFM_ERR_CUDA; }
   return 0;
 }
 

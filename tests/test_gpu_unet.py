@@ -234,6 +234,34 @@ def test_cifar_nfe_at_benchmarked_batch(pkg, cuda, B):
     assert m.engine().workspace_bytes(B) == m.engine().workspace_bytes(1) * B
 
 
+@pytest.mark.parametrize("name,B", [("mnist_inpaint", 64), ("mnist_cfm", 4096), ("mnist_ddpm", 256), ("flowers_ddpm", 128)])
+def test_other_configs_at_their_benchmarked_batch(pkg, cuda, name, B):
+    # BASELINE configs 0, 2, 3a, 3b at the batch their throughput is quoted on (profiles/sampler_sweep.py): the golden
+    # rows of the reference's own evaluation are planted at the start, the middle and the end of a random batch; every
+    # copy must equal the small-batch result bit for bit (size-independent property: a sample's result does not depend on
+    # the batch it sits in) and stay within the bf16 bar of the reference output.
+    cfg, _, _ = GOLDEN_CONFIGS[name]
+    g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
+    params = O.seeded_params(cfg, int(g["seed"]))
+    m = build(pkg, cfg, params, "bf16", cuda)
+    gx, gt = torch.from_numpy(g["x"]).to(cuda), torch.from_numpy(g["t"]).to(cuda)
+    n = gx.shape[0]
+    small = m(gx, gt)
+    gen = torch.Generator(device=cuda).manual_seed(B)
+    x = torch.randn(B, *gx.shape[1:], device=cuda, generator=gen)
+    t = torch.rand(B, device=cuda, generator=gen)
+    spots = [0, B // 2 - 1, B - n]
+    for s in spots:
+        x[s:s + n] = gx; t[s:s + n] = gt
+    out = m(x, t)
+    assert torch.isfinite(out).all()
+    for s in spots:
+        assert torch.equal(out[s:s + n], small), f"{name}: rows {s}..{s + n - 1} of a batch of {B} differ from the batch-{n} result"
+    r = rel_l2(out[:n].cpu(), torch.from_numpy(g["out"]))
+    print(f"{name}[bf16, B={B}] rel-L2 vs reference golden = {r:.3e}")
+    assert r < TOL["bf16"], r
+
+
 @pytest.mark.parametrize("name,batch", [("cifar", 5), ("flowers_ddpm", 2), ("tiny_neworder", 7)])
 def test_groupnorm_folded_into_conv_epilogue(pkg, cuda, name, batch):
     # default path: a ResBlock's out_layers.0/1 (GroupNorm + SiLU) runs in the epilogue of its first conv (conv_tc2_kernel
