@@ -62,3 +62,38 @@ CHAIN_CASES = {
     "amortized": _case("amortized", 2, 106),
     "amortized_corrector1": _case("amortized", 2, 107, n_corrector=1, delta=0.2),
 }
+
+
+# --- seeded sweep over the constructor's keyword space (tests/test_oracle.py pins the oracle on it against the live
+# reference, tests/test_gpu_unet.py the engine against the oracle) ---------------------------------------------------
+N_RANDOM_CONFIGS = 16
+
+
+def random_config(seed):
+    """A seeded draw from the reference's create_model keyword space (unet.py:43-105) inside the GroupNorm32 domain
+    (every channel count a multiple of 32), small enough for the CPU oracle."""
+    import numpy as np
+    rs = np.random.RandomState(7000 + seed)
+    size = int(rs.choice([8, 12, 16, 20, 32]))
+    levels = int(rs.randint(1, 4 if size % 8 == 0 else 3))
+    while size % (1 << (levels - 1)):
+        levels -= 1
+    mult = tuple(int(rs.choice([1, 2, 3])) for _ in range(levels))
+    nc = int(rs.choice([32, 64, 96]))
+    attn_levels = [lv for lv in range(levels) if rs.rand() < 0.6 and (size >> lv) <= 16]
+    kw = dict(image_size=size, in_channels=int(rs.choice([1, 2, 3, 6])), out_channels=int(rs.choice([1, 3])), num_channels=nc,
+              num_res_blocks=int(rs.randint(1, 3)), channel_mult=",".join(map(str, mult)),
+              attention_resolutions=",".join(str(size >> lv) for lv in attn_levels) if attn_levels else str(4 * size),
+              use_scale_shift_norm=bool(rs.rand() < 0.35), resblock_updown=bool(rs.rand() < 0.4),
+              use_new_attention_order=bool(rs.rand() < 0.4))
+    widths = {nc * mult[lv] for lv in attn_levels} | {nc * mult[-1]}        # channels of every attention block (middle included)
+    hcs = [h for h in (32, 64) if all(w % h == 0 for w in widths)]
+    if rs.rand() < 0.5 and hcs:
+        kw["num_head_channels"] = int(rs.choice(hcs))
+    else:
+        kw["num_heads"] = int(rs.choice([h for h in (1, 2, 4) if all(w % h == 0 for w in widths)]))
+        if rs.rand() < 0.3:
+            kw["num_heads_upsample"] = int(rs.choice([1, 2]))
+    if rs.rand() < 0.3:
+        kw["num_classes"] = int(rs.randint(2, 12))
+    return kw, int(rs.randint(1, 8))

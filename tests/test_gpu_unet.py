@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_configs import GOLDEN_CONFIGS
+from golden_configs import GOLDEN_CONFIGS, random_config
 from oracle import unet as O
 
 pytestmark = pytest.mark.gpu
@@ -166,6 +166,27 @@ def test_odd_maps_and_head_widths_match_oracle(pkg, cuda, precision, size, mult,
     r = rel_l2(got, want)
     print(f"odd[{size},{mult},{precision}] rel-L2 = {r:.3e}")
     assert r < TOL[precision], r
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_configs_match_oracle(pkg, cuda, seed):
+    # seeded sweep over the constructor's keyword space: channel multipliers 1-3 on 32 / 64 / 96 base channels (K-iterations
+    # of 32 and 64 channels, N tiles of every width), 1-3 levels, FiLM, up/down ResBlocks, both attention orders, head
+    # counts / widths, class labels, ragged batches - both precisions against the CPU oracle
+    kw, B = random_config(seed)
+    cfg = O.config_from_create_model(**kw)
+    params = O.seeded_params(cfg, 900 + seed)
+    rs = np.random.RandomState(seed)
+    x = torch.from_numpy(rs.standard_normal((B, kw["in_channels"], kw["image_size"], kw["image_size"])).astype(np.float32))
+    t = torch.from_numpy(rs.uniform(0, 1, size=(B,)).astype(np.float32))
+    y = torch.from_numpy(rs.randint(0, kw["num_classes"], size=(B,))) if "num_classes" in kw else None
+    want = O.unet_forward(cfg, params, x, t, y)
+    for precision in ("fp32", "bf16"):
+        m = build(pkg, cfg, params, precision, cuda)
+        got = (m(x.to(cuda), t.to(cuda)) if y is None else m(x.to(cuda), t.to(cuda), y.to(cuda))).cpu()
+        r = rel_l2(got, want)
+        print(f"random[{seed}] {kw} B={B} [{precision}] rel-L2 = {r:.3e}")
+        assert r < TOL[precision], (kw, B, precision, r)
 
 
 def test_superres_config_runs_on_tensor_core_kernels(pkg, cuda):

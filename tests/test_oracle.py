@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from _refload import load_reference, reference_available
-from golden_configs import CHAIN_CASES, CHAIN_NS, GOLDEN_CONFIGS, chain_inputs, chain_net_cfg
+from golden_configs import CHAIN_CASES, CHAIN_NS, GOLDEN_CONFIGS, N_RANDOM_CONFIGS, chain_inputs, chain_net_cfg, random_config
 from oracle import ddpm as D
 from oracle import unet as O
 
@@ -70,6 +70,32 @@ def test_oracle_matches_live_reference_unet():
     with torch.no_grad():
         want = m(x, t)
     assert torch.equal(want, O.unet_forward(cfg, p, x, t))
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("seed", range(N_RANDOM_CONFIGS))
+def test_oracle_matches_live_reference_on_random_configs(seed):
+    """The oracle pinned across the constructor's keyword space: for every config of the seeded sweep the GPU tests use
+    (golden_configs.random_config), the vendored UNetModel and the oracle agree bit for bit - parameter names included."""
+    ref = load_reference()
+    kw, B = random_config(seed)
+    kw.pop("num_classes", None)     # the vendored forward(x, timesteps) takes no labels (unet.py:708); the label path is torchcfm's
+    cfg = O.config_from_create_model(**kw)
+    m = ref.unet.UNetModel(image_size=cfg.image_size, in_channels=cfg.in_channels, model_channels=cfg.model_channels,
+                           out_channels=cfg.out_channels, num_res_blocks=cfg.num_res_blocks,
+                           attention_resolutions=cfg.attention_ds, channel_mult=cfg.channel_mult,
+                           num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels,
+                           num_heads_upsample=cfg.num_heads_upsample, use_scale_shift_norm=cfg.use_scale_shift_norm,
+                           resblock_updown=cfg.resblock_updown, use_new_attention_order=cfg.use_new_attention_order).eval()
+    assert list(m.state_dict().keys()) == list(O.param_shapes(cfg).keys())
+    p = O.seeded_params(cfg, 900 + seed)
+    m.load_state_dict(p)
+    rs = np.random.RandomState(seed)
+    x = torch.from_numpy(rs.standard_normal((B, kw["in_channels"], kw["image_size"], kw["image_size"])).astype(np.float32))
+    t = torch.from_numpy(rs.uniform(0, 1, size=(B,)).astype(np.float32))
+    with torch.no_grad():
+        want = m(x, t)
+    assert torch.equal(want, O.unet_forward(cfg, p, x, t)), kw
 
 
 def test_mask_sampler_rng_order_and_bounds():
