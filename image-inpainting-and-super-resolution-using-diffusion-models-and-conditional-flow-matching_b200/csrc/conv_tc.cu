@@ -91,6 +91,8 @@ struct TcParams {
   int tma_store;               // pair kernel: epilogue stages bf16 rows in swizzled shared memory, TMA writes them out
   int st_dh, st_dn;            // ... box origin of a CTA's second 128-row half (kMH = 2): rows / samples to skip
   int b_stat;                  // pair kernel, short-K 1x1 convs: the weight tile of this pair's N block stays in shared memory
+  int nswap;                   // halo boxes of a tile that holds TWO whole samples (8x8 maps): image rows of the two samples interleave
+                               // (tensor-map dims ordered C, W, N, H), tile row = (h * 2 + n) * bw + w, so the y taps stay row-shifted views
   const float* bias;
   const float* emb; int emb_stride; const int* emb_row;
   const bf16* res0; const bf16* res1; int R0, R1;
@@ -148,7 +150,8 @@ __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCo
   EpiRow r;
   int wi, hi, ni, t;
   p.d_bw.divmod(row, &t, &wi);
-  p.d_bh.divmod(t, &ni, &hi);
+  if (p.nswap) { ni = t & 1; hi = t >> 1; }
+  else p.d_bh.divmod(t, &ni, &hi);
   r.n = c.tb * p.bn + ni; r.h = c.th * p.bh + hi; r.w = c.tw * p.bw + wi;
   r.valid = row < p.valid_rows && r.n < p.B && r.h < p.H && r.w < p.W;
   if (p.n_phase == 4) {   // rows index the source grid; this phase's outputs interleave into the 2H x 2W map
@@ -270,15 +273,19 @@ __device__ __forceinline__ void epi_granules(const float (&f)[32], float (&gs)[8
     gq[g] = accumulate ? gq[g] + q : q;
   }
 }
-// Sum the 8 granule pairs over the rows of a warp: reduce-scatter butterfly (4 + 2 + 1 exchanges per quantity), then
-// plain butterflies over the lanes that hold the same granule.  kSeg32: the 32 rows are one sample; lane l ends with
-// granule l >> 2 in gs[0], gq[0] (4 copies).  Otherwise each half-warp is a sample (16 pixels per sample, 4x4 maps):
-// lane l ends with granule (l >> 1) & 7 of its half-warp's rows (2 copies).
-template <bool kSeg32>
+// Sum the 8 granule pairs over the rows of a warp that belong to one sample: reduce-scatter butterfly (4 + 2 + 1
+// exchanges per quantity), then plain butterflies over the remaining lanes of the sample.
+//   kMode 0: the 32 rows are one sample; lane l ends with granule l >> 2 in gs[0], gq[0] (4 copies).
+//   kMode 1: each half-warp is a sample (16 pixels per sample, 4x4 maps): lane l ends with granule (l >> 1) & 7 of its
+//            half-warp's rows (2 copies).
+//   kMode 2: the rows of two samples interleave in runs of 8 (nswap tiles of 8x8 maps: lane bit 3 is the sample): lane l
+//            ends with granule 4 * bit4(l) + 2 * bit2(l) + bit1(l) of sample bit3(l) (2 copies).
+template <int kMode>
 __device__ __forceinline__ void epi_granule_reduce(float (&gs)[8], float (&gq)[8], int lane) {
-  constexpr int H0 = kSeg32 ? 16 : 8;
+  constexpr int HS[3][3] = {{16, 8, 4}, {8, 4, 2}, {16, 4, 2}};
 #pragma unroll
-  for (int st = 0, H = H0, n = 4; st < 3; ++st, H >>= 1, n >>= 1) {
+  for (int st = 0, n = 4; st < 3; ++st, n >>= 1) {
+    const int H = HS[kMode][st];
     const bool up = (lane & H) != 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -291,7 +298,7 @@ __device__ __forceinline__ void epi_granule_reduce(float (&gs)[8], float (&gq)[8
     }
   }
 #pragma unroll
-  for (int H = kSeg32 ? 2 : 1; H >= 1; H >>= 1) {
+  for (int H = kMode == 0 ? 2 : 1; H >= 1; H >>= 1) {
     gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], H);
     gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], H);
   }
@@ -618,7 +625,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const int dx = xi - 1 + (sg.ks == 2 ? (tc.ph & 1) : 0);
                 mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
                 if (leader) mbar_expect_tx(&fullA[ra.slot], 2 * p.a_halo_bytes);      // bytes of BOTH CTAs
-                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * p.kc, w0 + dx, yorg, n0);
+                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * p.kc, w0 + dx,
+                                p.nswap ? n0 : yorg, p.nswap ? yorg : n0);
                 ra.next();
                 for (int yi = 0; yi < sg.ks; ++yi, brow += p.Cout) {
                   mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
@@ -634,7 +642,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               for (int ch = 0; ch < sg.n_chunks; ++ch, brow += p.Cout) {
                 mbar_wait(&emptyA[ra.slot], ra.phase ^ 1);
                 if (leader) mbar_expect_tx(&fullA[ra.slot], 2 * p.a_tile_bytes);
-                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * p.kc, w0 * sg.stride + dx, h0 * sg.stride + dy, n0);
+                tma_load_4d_2sm(ring_a + ra.slot * p.a_slot_bytes, map, mapa_u32(smem_u32(&fullA[ra.slot]), 0), ch * p.kc, w0 * sg.stride + dx,
+                                p.nswap ? n0 : h0 * sg.stride + dy, p.nswap ? h0 * sg.stride + dy : n0);
                 ra.next();
                 if (load_b) {
                   mbar_wait(&emptyB[rb.slot], rb.phase ^ 1);
@@ -652,7 +661,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       const uint32_t idesc = make_idesc(256, p.block_n);
-      const uint32_t row_step = (uint32_t)(p.bw * p.kc * 2) >> 4;
+      const uint32_t row_step = (uint32_t)(p.bw * (p.nswap ? 2 : 1) * p.kc * 2) >> 4;   // one image row (of both samples: nswap)
       const uint32_t half_step = (uint32_t)(TC_BLOCK_M * p.kc * 2) >> 4;   // second M-half of each CTA's A slot
       const int n_kk = p.kc >> 4;
       const int acc_cols = p.block_n * kMH;
@@ -725,7 +734,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       float2* s_tab = (float2*)(smem + TC_GN_OFF + 8192);           // [unit <= 2][channel]: (scale, shift) of pass 2
       const int n_mine = chunks_per_half > sub ? ((chunks_per_half - sub + 1) >> 1) * kMH : 0;
       const bool sum_halves = kMH == 2 && p.gn_R == 256;            // both 128-row halves belong to the same sample
-      const int rows_blk = sum_halves ? 64 : p.gn_seg;              // tile rows one scratch block stands for
+      const bool il = kMH == 1 && p.nswap;                          // two samples, rows interleaved in runs of 8 (gn_seg == 8)
+      const int rows_blk = sum_halves ? 64 : (il ? 16 : p.gn_seg);  // tile rows one scratch block stands for
       const int n_blk = sum_halves ? 4 : (128 * kMH) / rows_blk;    // scratch blocks per chunk (<= 8)
       const int bpu = sum_halves ? 4 : p.gn_R / rows_blk;           // blocks per sample ("unit") of the tile
       const int n_units = n_blk / bpu;
@@ -780,12 +790,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           epi_granules(f, run_s, run_q, sum_halves && half == 1);
           if (sum_halves && half == 0) continue;
           float2* sc = s_scr + ci * 64;
-          if (p.gn_seg == 32) {
-            epi_granule_reduce<true>(run_s, run_q, lane);
+          if (il) {                      // block = sample * 4 + warp quarter: a sample's four blocks are contiguous
+            epi_granule_reduce<2>(run_s, run_q, lane);
+            if ((lane & 1) == 0)
+              sc[(((lane >> 3) & 1) * 4 + quad) * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = make_float2(run_s[0], run_q[0]);
+          } else if (p.gn_seg == 32) {
+            epi_granule_reduce<0>(run_s, run_q, lane);
             const int blk = sum_halves ? quad : half * 4 + quad;
             if ((lane & 3) == 0) sc[blk * 8 + (lane >> 2)] = make_float2(run_s[0], run_q[0]);
           } else {
-            epi_granule_reduce<false>(run_s, run_q, lane);
+            epi_granule_reduce<1>(run_s, run_q, lane);
             if ((lane & 1) == 0) sc[(quad * 2 + (lane >> 4)) * 8 + ((lane >> 1) & 7)] = make_float2(run_s[0], run_q[0]);
           }
         }
@@ -870,14 +884,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (dual && rr.valid) epi_store_bf16(p, rr, cbase + c0, f, p.out);
           if (table) {
-            const float2* tb = s_tab + (trow >> p.gn_R_log2) * TC_GN_MAX_COUT + c0;
+            const float2* tb = s_tab + (il ? ((trow >> 3) & 1) : (trow >> p.gn_R_log2)) * TC_GN_MAX_COUT + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float4 t4 = *(const float4*)(tb + j);
               f[j] = fmaf(f[j], t4.x, t4.y); f[j + 1] = fmaf(f[j + 1], t4.z, t4.w);
             }
           } else {
-            const float2* mr = s_mr + (trow >> p.gn_R_log2) * 32;
+            const float2* mr = s_mr + (il ? ((trow >> 3) & 1) : (trow >> p.gn_R_log2)) * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float2 m = mr[(c0 + j) >> p.gn_cpg_log2];       // 4 | cpg: the four channels share a group
@@ -1022,6 +1036,7 @@ struct TcConvPlan {
   int st_bh = 0, st_bn = 0, st_dh = 0, st_dn = 0;   // store box (128 rows) and the origin shift of the second half
   int ring_bytes = TC_RING_BYTES;
   bool b_stat = false;          // weights resident in shared memory across the M tiles of a pair (n_b == total_k)
+  bool nswap = false;           // halo boxes over two whole samples per CTA tile, image rows interleaved (TcParams::nswap)
   // fused GroupNorm epilogue (conv_tc2_kernel<.., true>)
   TcConvPlan* alt = nullptr;   // narrow-N variant of the same conv for launches with few M tiles (own weights copy and maps)
   bool gn_ok = false, gn = false, gn_dual = false; int gn_R = 0, gn_seg = 32, gn_ctas = 1, gn_cpg = 0, gn_total_k = 0;
@@ -1088,6 +1103,26 @@ static bool size_rings(TcConvPlan* pl, int G) {
   return false;
 }
 
+// nswap tensor maps list the sample dimension BEFORE the image-row dimension, i.e. with a larger stride on the lower
+// dimension.  Check once that the driver encodes such a map (nothing is dereferenced); otherwise those layers keep the
+// per-tap loads.
+static bool nswap_encodable(Engine& e) {
+  static int state = -1;
+  if (state < 0) {
+    state = 0;
+    if (get_encode(e) == 0) {
+      CUtensorMap m;
+      cuuint64_t dims[4] = {64, 8, 4, 8};
+      cuuint64_t strides[3] = {64 * 2, 8 * 8 * 64 * 2, 8 * 64 * 2};
+      cuuint32_t box[4] = {64, 8, 2, 10};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      state = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(uintptr_t)0x10000, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 1 : 0;
+    }
+  }
+  return state == 1;
+}
+
 int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::vector<float>& ws, int force_block_n) {
   TcConvPlan* pl = new TcConvPlan();
   const int Cin = op.Cin, ks = op.ks;
@@ -1146,6 +1181,13 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
       else { pl->st_bh = pl->bh / 2; pl->st_bn = 1; pl->st_dh = pl->bh / 2; }
     }
   }
+  // Maps half the size of a CTA tile (8x8 with 128-row tiles: two whole samples per CTA).  A halo box per sample would
+  // leave a gap between the samples' rows, so the row-shifted views could not be one UMMA operand; with the tensor map's
+  // dimensions ordered (C, W, N, H) the box lands as [image row][sample][pixel]: a y tap is again a shift by a whole
+  // number of swizzle atoms, and these layers pull their activations 3x instead of 9x (they ran at 68 % tensor activity).
+  pl->nswap = pl->pair && pl->mh == 1 && eks > 1 && op.stride == 1 && pl->bn == 2 && pl->bh == Hg && pl->bw == Wg && Wg % 8 == 0 &&
+              pl->valid_rows == rows && !pl->tma_store && !env_off("CFM_DISABLE_TC_HALO") && !env_off("CFM_DISABLE_TC_NSWAP") &&
+              nswap_encodable(e);
   // GroupNorm of the output applied in the epilogue (requested by the plan for a ResBlock's first conv): the CTA tile must
   // hold whole samples or a whole number of tiles must make up a sample, every warp's rows (or half-warp's: 4x4 maps) must
   // lie in one sample, one N tile must span all channels and a group must be 4, 8, 16 or 32 channels.
@@ -1167,6 +1209,7 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
     if (cpg_ok && R > 0 && ctas <= 32 && (ctas == 1 || (pl->bn == 1 && pl->block_n == Cout))) {
       // capable: the 12 KB of the epilogue's tables come out of the rings whether or not a GroupNorm ends up attached
       // (tc_conv_attach_gn runs after the plan is complete and must not re-pack the weights)
+      if (pl->nswap) seg = 8;     // rows of the two samples interleave in runs of 8 (kernel: il)
       pl->gn_ok = true; pl->gn_R = R; pl->gn_seg = seg; pl->gn_ctas = ctas; pl->gn_cpg = cpg;
       pl->gn_total_k = eks * eks * (Cin / kc) + op.Cskip / kc;
       pl->ring_bytes = TC_GN_OFF;
@@ -1175,12 +1218,13 @@ int tc_conv_prepare(Engine& e, Op& op, const std::vector<float>& w, const std::v
   }
   // halo mode: the tile must lie inside one sample (row-shifted views stay contiguous), fill its rows exactly and
   // an image row must be a whole number of 8-row swizzle atoms
-  bool halo = eks > 1 && op.stride == 1 && pl->bn == 1 && pl->bw % 8 == 0 && pl->valid_rows == rows && !env_off("CFM_DISABLE_TC_HALO");
+  bool halo = eks > 1 && op.stride == 1 && (pl->bn == 1 || pl->nswap) && pl->bw % 8 == 0 && pl->valid_rows == rows && !env_off("CFM_DISABLE_TC_HALO");
   pl->a_tile_bytes = pl->valid_rows * row_bytes;
-  pl->a_halo_bytes = (rows + 2 * pl->bw) * row_bytes;
+  pl->a_halo_bytes = (rows + 2 * pl->bw * pl->bn) * row_bytes;
   pl->b_slot_bytes = (pl->pair ? pl->block_n / 2 : pl->block_n) * row_bytes;
   pl->a_slot_bytes = halo ? pl->a_halo_bytes : rows * row_bytes;
   if (halo && !size_rings(pl, eks)) { halo = false; pl->a_slot_bytes = rows * row_bytes; }
+  if (!halo && pl->nswap) { pl->nswap = false; if (pl->gn_seg == 8) pl->gn_seg = 32; }
   if (!halo && !size_rings(pl, 1)) { e.err = "conv tile does not fit the shared-memory rings: " + op.name; delete pl; return CFM_ERR_INVALID; }
   // Short-K 1x1 convs (qkv, proj_out) on the pair kernel: every M tile of a pair uses the same N block (the launch makes
   // the number of pairs a multiple of tiles_n), so its whole K extent of weights is loaded once and stays in shared
@@ -1291,6 +1335,9 @@ static int encode_maps(Engine& e, const Op& op, TcConvPlan* pl, int B, TcMaps* m
     cuuint64_t strides[3] = {(cuuint64_t)t.C * 2, (cuuint64_t)t.W * t.C * 2, (cuuint64_t)t.H * t.W * t.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)pl->kc, (cuuint32_t)(pl->bw * st), (cuuint32_t)box_h, (cuuint32_t)pl->bn};
     cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
+    if (pl->nswap) {      // (C, W, N, H): the sample index runs inside the image row - every K segment, so all of them see the same tile rows
+      std::swap(dims[2], dims[3]); std::swap(strides[1], strides[2]); std::swap(box[2], box[3]);
+    }
     CUresult r = g_encode(&m->a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, tensor_ptr(e, pl->seg_tensor[s], B), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1341,7 +1388,7 @@ int tc_conv_launch(Engine& e, const Op& op, int B, cudaStream_t st, float* out_n
   p.B = B; p.H = pl->Hg; p.W = pl->Wg; p.n_phase = pl->n_phase;
   p.bw = pl->bw; p.bh = pl->bh; p.bn = pl->bn; p.mh = pl->mh;
   p.tiles_w = (pl->Wg + pl->bw - 1) / pl->bw; p.tiles_h = (pl->Hg + pl->bh - 1) / pl->bh; p.tiles_b = (B + pl->bn - 1) / pl->bn;
-  p.kc = pl->kc; p.valid_rows = pl->valid_rows;
+  p.kc = pl->kc; p.valid_rows = pl->valid_rows; p.nswap = pl->nswap ? 1 : 0;
   p.tiles_n = pl->cout_pad / pl->block_n;
   p.d_tiles_n.init(p.tiles_n); p.d_phase.init(p.n_phase); p.d_tiles_w.init(p.tiles_w); p.d_tiles_h.init(p.tiles_h);
   p.d_bw.init(p.bw); p.d_bh.init(p.bh);
