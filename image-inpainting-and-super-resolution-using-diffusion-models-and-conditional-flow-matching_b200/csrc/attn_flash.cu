@@ -14,6 +14,7 @@
 // result does not depend on its batch.
 #include <cstring>
 #include <map>
+#include <mutex>
 #include "engine.h"
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -408,6 +409,7 @@ attn_flash64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 // ------------------------------------------------------------------------------------------------
 struct AttnFlashPlan { std::map<int, CUtensorMap> maps; std::map<int, CUtensorMap> maps64; };   // maps64: 64-row K / V boxes
 static std::map<const Op*, AttnFlashPlan> g_flash_plans;   // keyed by op address (ops vector is stable after build)
+static std::mutex g_flash_mu;   // engines on different host threads share the map (each touches only its own ops' entries)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -438,7 +440,9 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     attr.done(e.device);
   }
   const int T = op.Hin * op.Win;
-  AttnFlashPlan& pl = g_flash_plans[&op];
+  AttnFlashPlan* plp;
+  { std::lock_guard<std::mutex> lk(g_flash_mu); plp = &g_flash_plans[&op]; }
+  AttnFlashPlan& pl = *plp;
   const void* qkv = tensor_ptr(e, op.src0, B);
   auto it = pl.maps.find(B);
   if (it == pl.maps.end()) {
@@ -497,6 +501,7 @@ int attn_flash_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
 }
 
 void attn_flash_release(Engine& e) {
+  std::lock_guard<std::mutex> lk(g_flash_mu);
   for (const Op& op : e.ops) {
     auto it = g_flash_plans.find(&op);
     if (it != g_flash_plans.end()) { it->second.maps.clear(); it->second.maps64.clear(); }
@@ -504,6 +509,7 @@ void attn_flash_release(Engine& e) {
 }
 
 void attn_flash_forget(Engine& e) {
+  std::lock_guard<std::mutex> lk(g_flash_mu);
   for (const Op& op : e.ops) g_flash_plans.erase(&op);
 }
 

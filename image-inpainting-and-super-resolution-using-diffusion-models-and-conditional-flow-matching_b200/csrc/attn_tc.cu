@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include "engine.h"
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
 // ------------------------------------------------------------------------------------------------
 struct AttnTcPlan { std::map<int, CUtensorMap> maps; };
 static std::map<const Op*, AttnTcPlan> g_attn_plans;   // keyed by op address (ops vector is stable after build)
+static std::mutex g_attn_mu;   // engines on different host threads share the map (each touches only its own ops' entries)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -449,7 +451,9 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { e.err = "cuTensorMapEncodeTiled unavailable"; return CFM_ERR_CUDA; }
     g_attn_encode = (EncodeTiledFn)fn;
   }
-  AttnTcPlan& pl = g_attn_plans[&op];
+  AttnTcPlan* plp;
+  { std::lock_guard<std::mutex> lk(g_attn_mu); plp = &g_attn_plans[&op]; }
+  AttnTcPlan& pl = *plp;
   const void* qkv = tensor_ptr(e, op.src0, B);
   auto it = pl.maps.find(B);
   if (it == pl.maps.end()) {
@@ -496,6 +500,7 @@ int attn_tc_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
 }
 
 void attn_tc_release(Engine& e) {
+  std::lock_guard<std::mutex> lk(g_attn_mu);
   for (const Op& op : e.ops) {
     auto it = g_attn_plans.find(&op);
     if (it != g_attn_plans.end()) it->second.maps.clear();
@@ -503,6 +508,7 @@ void attn_tc_release(Engine& e) {
 }
 
 void attn_tc_forget(Engine& e) {
+  std::lock_guard<std::mutex> lk(g_attn_mu);
   for (const Op& op : e.ops) g_attn_plans.erase(&op);
 }
 

@@ -12,6 +12,7 @@
 // TMEM: 512 columns (D = 512 needs them all), so one CTA per SM; the ring keeps the tensor pipe fed.
 #include <cstring>
 #include <map>
+#include <mutex>
 #include "engine.h"
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1) attn_wide_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 struct AttnWidePlan { std::map<int, CUtensorMap> maps; };
 static std::map<const Op*, AttnWidePlan> g_wide_plans;   // keyed by op address (ops vector is stable after build)
+static std::mutex g_wide_mu;   // engines on different host threads share the map (each touches only its own ops' entries)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -225,7 +227,9 @@ int attn_wide_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
     attr.done(e.device);
   }
   const int T = op.Hin * op.Win;
-  AttnWidePlan& pl = g_wide_plans[&op];
+  AttnWidePlan* plp;
+  { std::lock_guard<std::mutex> lk(g_wide_mu); plp = &g_wide_plans[&op]; }
+  AttnWidePlan& pl = *plp;
   const void* qkv = tensor_ptr(e, op.src0, B);
   auto it = pl.maps.find(B);
   if (it == pl.maps.end()) {
@@ -252,6 +256,7 @@ int attn_wide_launch(Engine& e, const Op& op, int B, cudaStream_t st) {
 }
 
 void attn_wide_release(Engine& e) {
+  std::lock_guard<std::mutex> lk(g_wide_mu);
   for (const Op& op : e.ops) {
     auto it = g_wide_plans.find(&op);
     if (it != g_wide_plans.end()) it->second.maps.clear();
@@ -259,6 +264,7 @@ void attn_wide_release(Engine& e) {
 }
 
 void attn_wide_forget(Engine& e) {
+  std::lock_guard<std::mutex> lk(g_wide_mu);
   for (const Op& op : e.ops) g_wide_plans.erase(&op);
 }
 

@@ -224,6 +224,39 @@ def test_engines_on_two_devices_in_one_process(pkg):
             assert rel_l2(per_dev[1], torch.from_numpy(g["out"])) < TOL[precision]
 
 
+def test_engines_on_two_host_threads(pkg, cuda):
+    # the tensor-map caches of the attention kernels are process-wide; two engines driven from two host
+    # threads (own CUDA streams) must not corrupt them and must give the bits a single thread gives
+    import threading
+    jobs = []
+    for name in ("cifar", "tiny_neworder", "mnist_ddpm"):
+        cfg, _, _ = GOLDEN_CONFIGS[name]
+        g = np.load(os.path.join(GOLD, f"unet_{name}.npz"))
+        params = O.seeded_params(cfg, int(g["seed"]))
+        x, t = torch.from_numpy(g["x"]).to(cuda), torch.from_numpy(g["t"]).to(cuda)
+        want = build(pkg, cfg, params, "bf16", cuda)(x, t).cpu()
+        jobs.append((cfg, params, x, t, want))
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            cfg, params, x, t, _ = jobs[i % len(jobs)]
+            with torch.cuda.stream(torch.cuda.Stream(device=cuda)):
+                m = build(pkg, cfg, params, "bf16", cuda)        # a fresh engine per thread: first launches fill the caches
+                outs = [m(x.repeat(b, 1, 1, 1), t.repeat(b))[:x.shape[0]].cpu() for b in (1, 2, 3)]
+            results[i] = outs
+        except Exception as ex:                                   # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for th in threads: th.start()
+    for th in threads: th.join()
+    assert not errors, errors
+    for i, outs in results.items():
+        for o in outs:
+            assert torch.equal(o, jobs[i % len(jobs)][4]), i
+
+
 @pytest.mark.parametrize("B", [128, 1000, 1024])
 def test_cifar_nfe_at_benchmarked_batch(pkg, cuda, B):
     # the shape bench.py times (CIFAR bf16, 1024 samples per NFE): multi-wave persistent tiling, stationary-weight pair
