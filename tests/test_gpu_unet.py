@@ -257,12 +257,13 @@ def test_engines_on_two_host_threads(pkg, cuda):
             assert torch.equal(o, jobs[i % len(jobs)][4]), i
 
 
-@pytest.mark.parametrize("B", [128, 1000, 1024])
+@pytest.mark.parametrize("B", [128, 1000, 1024, 2048])
 def test_cifar_nfe_at_benchmarked_batch(pkg, cuda, B):
     # the shape bench.py times (CIFAR bf16, 1024 samples per NFE): multi-wave persistent tiling, stationary-weight pair
     # counts, cluster GroupNorm and arena offsets beyond 2^31 bytes are only reached here.  The golden rows are planted
     # at the start, in the middle and at the end of the batch (1000 is not a multiple of any tile count); every copy
-    # must equal the B = 2 result bit for bit and sit within the bf16 bar of the reference's own output.
+    # must equal the B = 2 result bit for bit and sit within the bf16 bar of the reference's own output.  2048: a 4.8 GiB
+    # arena - byte offsets beyond 2^32.
     cfg, _, _ = GOLDEN_CONFIGS["cifar"]
     g = np.load(os.path.join(GOLD, "unet_cifar.npz"))
     params = O.seeded_params(cfg, int(g["seed"]))
