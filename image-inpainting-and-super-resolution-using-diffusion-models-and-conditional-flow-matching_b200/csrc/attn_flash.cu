@@ -70,7 +70,7 @@ __device__ __forceinline__ float af_exp_block(const uint32_t (&sv)[2][32], int k
         s4[q] += e0 + e1;
         o2[q] = __floats2bfloat162_rn(e0, e1);
       }
-      *(uint4*)(prow64 + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+      sts_u4(smem_u32(prow64) + (uint32_t)(((c16 + i) ^ (r & 7)) << 4), o4);     // explicit st.shared (a generic store resolves the space at run time)
     }
   }
   return (s4[0] + s4[1]) + (s4[2] + s4[3]);

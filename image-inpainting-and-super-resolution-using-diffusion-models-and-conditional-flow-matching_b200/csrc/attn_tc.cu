@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
         sum += e0 + e1;
         o2[q] = __floats2bfloat162_rn(e0, e1);
       }
-      *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+      sts_u4(smem_u32(pchunk) + (uint32_t)(((c16 + i) ^ (r & 7)) << 4), o4);     // explicit st.shared (a generic store resolves the space at run time)
     }
   }
   xch[256 + tid] = sum;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_tc_persist_kernel(const __
             sum += e0 + e1;
             o2[q] = __floats2bfloat162_rn(e0, e1);
           }
-          *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+          sts_u4(smem_u32(pchunk) + (uint32_t)(((c16 + i) ^ (r & 7)) << 4), o4);     // explicit st.shared (a generic store resolves the space at run time)
         }
       };
       {

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1) attn_wide_kernel(const __grid_c
           sum += e0 + e1;
           o2[q] = __floats2bfloat162_rn(e0, e1);
         }
-        *(uint4*)(pchunk + (((c16 + i) ^ (r & 7)) << 4)) = o4;
+        sts_u4(smem_u32(pchunk) + (uint32_t)(((c16 + i) ^ (r & 7)) << 4), o4);     // explicit st.shared (a generic store resolves the space at run time)
       }
     }
     fence_proxy_async();          // P was written through the generic proxy; the MMA reads it through the async proxy

@@ -117,7 +117,7 @@ struct TcParams {
 // epilogue helpers (shared by the single-CTA and the CTA-pair kernel)
 // ------------------------------------------------------------------------------------------------
 // One accumulator row (= output pixel) as the epilogue sees it.
-struct EpiRow { bool valid; int n, h, w; long long pix; };
+struct EpiRow { bool valid; int n, h, w; long long pix; const float* embp; };   // embp: this row's embedding vector (or null)
 
 struct TileCoord { int nt, ph, tw, th, tb; };
 // tile index -> (N tile, sub-pixel phase, spatial tile).  N tile and phase vary fastest, so the CTAs that share an
@@ -160,13 +160,19 @@ __device__ __forceinline__ EpiRow epi_decode_row(const TcParams& p, const TileCo
   } else {
     r.pix = ((long long)r.n * p.H + r.h) * p.W + r.w;
   }
+  r.embp = nullptr;
   return r;
+}
+// The row's time / class embedding vector: resolved ONCE per tile, before the accumulator is awaited - the index load
+// (row_of_sample[n]) and the vector loads were two dependent global round trips in front of every 32-column chunk.
+__device__ __forceinline__ void epi_attach_emb(const TcParams& p, EpiRow& r) {
+  if (p.emb && r.valid) r.embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
 }
 // rows[half] without dynamic indexing (which would put the two EpiRows in local memory): field-wise selects
 __device__ __forceinline__ EpiRow epi_pick(const EpiRow& a, const EpiRow& b, bool second) {
   EpiRow r;
   r.valid = second ? b.valid : a.valid; r.n = second ? b.n : a.n; r.h = second ? b.h : a.h; r.w = second ? b.w : a.w;
-  r.pix = second ? b.pix : a.pix;
+  r.pix = second ? b.pix : a.pix; r.embp = second ? b.embp : a.embp;
   return r;
 }
 // issue the residual loads of one 32-channel chunk early (they are the only DRAM-latency operand of the epilogue):
@@ -194,6 +200,22 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+// Explicit shared-space accesses for the epilogue's tables: through a generic pointer the compiler emits LD.E / ST.E,
+// which resolve the address space at run time and sit on the long scoreboard (8 % of a K = 18 layer's stall samples were
+// FFMAs waiting for such loads of the scale / shift table).
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t saddr, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(x), "f"(y) : "memory");
+}
 // accumulator chunk (32 fp32 from TMEM) + bias + embedding vector, in fp32
 __device__ __forceinline__ void epi_bias_emb(const TcParams& p, const EpiRow& r, int cg, const uint32_t (&v)[32], uint32_t s_bias_addr,
                                              float (&f)[32]) {
@@ -203,8 +225,8 @@ __device__ __forceinline__ void epi_bias_emb(const TcParams& p, const EpiRow& r,
     f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
     f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
   }
-  if (p.emb && r.valid) {
-    const float* embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
+  if (r.embp) {
+    const float* embp = r.embp;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 e4 = __ldg((const float4*)(embp + cg + j));
@@ -321,8 +343,8 @@ __device__ __forceinline__ void epi_finish_smem(const TcParams& p, const EpiRow&
     f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
     f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
   }
-  if (p.emb && r.valid) {
-    const float* embp = p.emb + (long long)p.emb_row[r.n] * p.emb_stride;
+  if (r.embp) {
+    const float* embp = r.embp;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 e4 = __ldg((const float4*)(embp + cg + j));
@@ -505,8 +527,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int nt = tc.nt;
-      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
-      const EpiRow row1 = p.mh == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
+      EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+      epi_attach_emb(p, row0);
+      EpiRow row1 = row0;
+      if (p.mh == 2) { row1 = epi_decode_row(p, tc, 128 + quad * 32 + lane); epi_attach_emb(p, row1); }
       // (no L2 prefetch of the next tile's residual rows here: on the narrow MNIST layers this kernel serves, the extra
       //  tile decode in a K = 32..96 tile's epilogue cost more than the latency it hid: proj_out 0.171 -> 0.187 ms)
       uint4 res_cur[4], res_nxt[4];
@@ -727,11 +751,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       //   order: bit-reproducible, no atomics.
       // Pass 2: the accumulators are read again, normalised, SiLU-activated and stored as bf16.  The second TMEM stage
       //   keeps the MMAs of the next tile running underneath.
-      float2* s_mr = (float2*)(smem + TC_GN_OFF);                   // [unit][group]
-      const float* s_gamma = (const float*)(smem + TC_GN_OFF + 2048);
-      const float* s_beta = s_gamma + TC_GN_MAX_COUT;
-      float2* s_scr = (float2*)(smem + TC_GN_OFF + 4096);           // [chunk][block][granule]
-      float2* s_tab = (float2*)(smem + TC_GN_OFF + 8192);           // [unit <= 2][channel]: (scale, shift) of pass 2
+      // shared-space byte addresses of the epilogue's tables (explicit ld.shared / st.shared, see lds_f2)
+      const uint32_t s_mr = smem_u32(smem + TC_GN_OFF);             // float2 [unit][group]: mean, rstd
+      const uint32_t s_gamma = s_mr + 2048;                         // float [256]
+      const uint32_t s_beta = s_gamma + TC_GN_MAX_COUT * 4;         // float [256]
+      const uint32_t s_scr = s_mr + 4096;                           // float2 [chunk][block][granule]
+      const uint32_t s_tab = s_mr + 8192;                           // float2 [unit <= 2][channel]: (scale, shift) of pass 2
       const int n_mine = chunks_per_half > sub ? ((chunks_per_half - sub + 1) >> 1) * kMH : 0;
       const bool sum_halves = kMH == 2 && p.gn_R == 256;            // both 128-row halves belong to the same sample
       const bool il = kMH == 1 && p.nswap;                          // two samples, rows interleaved in runs of 8 (gn_seg == 8)
@@ -746,8 +771,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
         const int cbase = tc.nt * p.block_n;                       // first channel of this N tile (whole groups per tile)
         const int groups_tile = p.block_n >> p.gn_cpg_log2;
-        const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
-        const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;
+        EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+        epi_attach_emb(p, row0);
+        EpiRow row1 = row0;
+        if (kMH == 2) { row1 = epi_decode_row(p, tc, 128 + quad * 32 + lane); epi_attach_emb(p, row1); }
         uint4 res_cur[4], res_nxt[4];
         if (p.res0) {
           if (sub == 0 && pt + n_pairs < pair_tiles) {      // next tile's residual rows -> L2
@@ -789,18 +816,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           tmem_st32(ta, v);                 // pass 2 reads the finished value back: no second bias / embedding / residual fetch
           epi_granules(f, run_s, run_q, sum_halves && half == 1);
           if (sum_halves && half == 0) continue;
-          float2* sc = s_scr + ci * 64;
+          const uint32_t sc = s_scr + (uint32_t)ci * 512u;      // 64 float2 per chunk
           if (il) {                      // block = sample * 4 + warp quarter: a sample's four blocks are contiguous
             epi_granule_reduce<2>(run_s, run_q, lane);
             if ((lane & 1) == 0)
-              sc[(((lane >> 3) & 1) * 4 + quad) * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = make_float2(run_s[0], run_q[0]);
+              sts_f2(sc + (uint32_t)((((lane >> 3) & 1) * 4 + quad) * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)) * 8u, run_s[0], run_q[0]);
           } else if (p.gn_seg == 32) {
             epi_granule_reduce<0>(run_s, run_q, lane);
             const int blk = sum_halves ? quad : half * 4 + quad;
-            if ((lane & 3) == 0) sc[blk * 8 + (lane >> 2)] = make_float2(run_s[0], run_q[0]);
+            if ((lane & 3) == 0) sts_f2(sc + (uint32_t)(blk * 8 + (lane >> 2)) * 8u, run_s[0], run_q[0]);
           } else {
             epi_granule_reduce<1>(run_s, run_q, lane);
-            if ((lane & 1) == 0) sc[(quad * 2 + (lane >> 4)) * 8 + ((lane >> 1) & 7)] = make_float2(run_s[0], run_q[0]);
+            if ((lane & 1) == 0) sts_f2(sc + (uint32_t)((quad * 2 + (lane >> 4)) * 8 + ((lane >> 1) & 7)) * 8u, run_s[0], run_q[0]);
           }
         }
         tmem_st_wait();
@@ -809,10 +836,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (et < n_units * 32 && (et & 31) < groups_tile) {
           const int u = et >> 5, g = et & 31;                   // a warp per unit, a lane per group of this N tile
           const int g0 = g * gpg;                                // first granule of the group; groups never straddle chunks
-          const float2* sc = s_scr + (g0 >> 3) * 64 + (g0 & 7);
+          const uint32_t sc = s_scr + (uint32_t)((g0 >> 3) * 64 + (g0 & 7)) * 8u;
           float ts = 0.f, tq = 0.f;
           for (int b = 0; b < bpu; ++b)
-            for (int j = 0; j < gpg; ++j) { const float2 t2 = sc[(u * bpu + b) * 8 + j]; ts += t2.x; tq += t2.y; }
+            for (int j = 0; j < gpg; ++j) { const float2 t2 = lds_f2(sc + (uint32_t)((u * bpu + b) * 8 + j) * 8u); ts += t2.x; tq += t2.y; }
           if (p.gn_ctas > 1) {
             // u == 0: the whole CTA tile lies inside sample n; `my` = its index among the sample's tiles.  Every partial
             // travels as two 8-byte words {value, epoch}: an aligned 8-byte store is single-copy atomic, so the word itself
@@ -849,7 +876,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           const float inv_n = 1.0f / (float)(p.gn_cpg * p.gn_hw);
           const float mean = ts * inv_n;
           const float var = fmaxf(tq * inv_n - mean * mean, 0.f);
-          s_mr[u * 32 + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
+          sts_f2(s_mr + (uint32_t)(u * 32 + g) * 8u, mean, rsqrtf(var + p.gn_eps));
         }
         named_bar_sync(5, 32 * TC_EPI_WARPS);
         const float hs = p.gn_silu ? 0.5f : 1.0f;                   // silu(y) = h * tanh(h) + h with h = y / 2
@@ -859,9 +886,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           // per-(sample, channel) scale / shift: y = f * sc + sh,  sc = rstd * gamma * hs,  sh = (beta - mean * rstd * gamma) * hs
           for (int i = et; i < n_units * p.block_n; i += 32 * TC_EPI_WARPS) {
             const int u = i >= p.block_n ? 1 : 0, c = i - u * p.block_n;       // c: channel within this N tile
-            const float2 m = s_mr[u * 32 + (c >> p.gn_cpg_log2)];
-            const float sc = m.y * s_gamma[cbase + c] * hs;
-            s_tab[u * TC_GN_MAX_COUT + c] = make_float2(sc, fmaf(-m.x, sc, s_beta[cbase + c] * hs));
+            const float2 m = lds_f2(s_mr + (uint32_t)(u * 32 + (c >> p.gn_cpg_log2)) * 8u);
+            const float sc = m.y * lds_f1(s_gamma + (uint32_t)(cbase + c) * 4u) * hs;
+            sts_f2(s_tab + (uint32_t)(u * TC_GN_MAX_COUT + c) * 8u, sc, fmaf(-m.x, sc, lds_f1(s_beta + (uint32_t)(cbase + c) * 4u) * hs));
           }
           named_bar_sync(5, 32 * TC_EPI_WARPS);
         }
@@ -884,18 +911,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (dual && rr.valid) epi_store_bf16(p, rr, cbase + c0, f, p.out);
           if (table) {
-            const float2* tb = s_tab + (il ? ((trow >> 3) & 1) : (trow >> p.gn_R_log2)) * TC_GN_MAX_COUT + c0;
+            const uint32_t tb = s_tab + (uint32_t)((il ? ((trow >> 3) & 1) : (trow >> p.gn_R_log2)) * TC_GN_MAX_COUT + c0) * 8u;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float4 t4 = *(const float4*)(tb + j);
+              const float4 t4 = lds_f4(tb + (uint32_t)j * 8u);
               f[j] = fmaf(f[j], t4.x, t4.y); f[j + 1] = fmaf(f[j + 1], t4.z, t4.w);
             }
           } else {
-            const float2* mr = s_mr + (il ? ((trow >> 3) & 1) : (trow >> p.gn_R_log2)) * 32;
+            const uint32_t mr = s_mr + (uint32_t)((il ? ((trow >> 3) & 1) : (trow >> p.gn_R_log2)) * 32) * 8u;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float2 m = mr[(c0 + j) >> p.gn_cpg_log2];       // 4 | cpg: the four channels share a group
-              const float4 ga = *(const float4*)(s_gamma + cbase + c0 + j), be = *(const float4*)(s_beta + cbase + c0 + j);
+              const float2 m = lds_f2(mr + (uint32_t)((c0 + j) >> p.gn_cpg_log2) * 8u);       // 4 | cpg: the four channels share a group
+              const float4 ga = lds_f4(s_gamma + (uint32_t)(cbase + c0 + j) * 4u), be = lds_f4(s_beta + (uint32_t)(cbase + c0 + j) * 4u);
               const float r = m.y * hs;
               f[j] = fmaf((f[j] - m.x) * r, ga.x, be.x * hs); f[j + 1] = fmaf((f[j + 1] - m.x) * r, ga.y, be.y * hs);
               f[j + 2] = fmaf((f[j + 2] - m.x) * r, ga.z, be.z * hs); f[j + 3] = fmaf((f[j + 3] - m.x) * r, ga.w, be.w * hs);
@@ -928,8 +955,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
         const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
         const int nt = tc.nt;
-        const EpiRow row0 = epi_decode_row(p, tc, row);
-        const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + row) : row0;
+        EpiRow row0 = epi_decode_row(p, tc, row);
+        epi_attach_emb(p, row0);
+        EpiRow row1 = row0;
+        if (kMH == 2) { row1 = epi_decode_row(p, tc, 128 + row); epi_attach_emb(p, row1); }
         if (p.res0 && sub == 0 && pt + n_pairs < pair_tiles) {
           const TileCoord tn = decode_pair_tile(p, pt + n_pairs, (int)rank);
           epi_prefetch_res(p, epi_decode_row(p, tn, row), tn.nt * p.block_n, p.block_n);
@@ -974,8 +1003,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
       const TileCoord tc = decode_pair_tile(p, pt, (int)rank);
       const int nt = tc.nt;
-      const EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
-      const EpiRow row1 = kMH == 2 ? epi_decode_row(p, tc, 128 + quad * 32 + lane) : row0;   // kMH = 1: never selected
+      EpiRow row0 = epi_decode_row(p, tc, quad * 32 + lane);
+      epi_attach_emb(p, row0);
+      EpiRow row1 = row0;                                                                  // kMH = 1: never selected
+      if (kMH == 2) { row1 = epi_decode_row(p, tc, 128 + quad * 32 + lane); epi_attach_emb(p, row1); }
       if (p.res0 && sub == 0 && pt + n_pairs < pair_tiles) {
         const TileCoord tn = decode_pair_tile(p, pt + n_pairs, (int)rank);
         epi_prefetch_res(p, epi_decode_row(p, tn, quad * 32 + lane), tn.nt * p.block_n, p.block_n);
