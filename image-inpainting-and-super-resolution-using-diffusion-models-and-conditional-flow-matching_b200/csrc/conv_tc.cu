@@ -618,11 +618,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
-  if (kGN) {
-    float* s_gb = (float*)(smem + TC_GN_OFF + 2048);
-    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) { s_gb[i] = p.gn_gamma[i]; s_gb[TC_GN_MAX_COUT + i] = p.gn_beta[i]; }
-  }
+  // (bias / gamma / beta are staged by the epilogue warps themselves, below: their global-load latency used to sit in
+  //  front of this block-wide barrier and so in front of the producer's first TMA load)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                 // peer barriers initialised before any remote arrive / multicast commit
@@ -740,6 +737,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int acc_cols = p.block_n * kMH;
     const uint32_t s_bias_addr = smem_u32(s_bias);
     int acc = 0; uint32_t acc_phase = 0;
+    {
+      // stage the per-channel constants (weights of the layer: not produced by a predecessor) while the first tile's
+      // operands are in flight; only the eight epilogue warps read them
+      const int et0 = (warp - 2) * 32 + lane;
+      for (int i = et0; i < p.Cout; i += 32 * TC_EPI_WARPS) s_bias[i] = p.bias[i];
+      if (kGN) {
+        float* s_gb = (float*)(smem + TC_GN_OFF + 2048);
+        for (int i = et0; i < p.Cout; i += 32 * TC_EPI_WARPS) { s_gb[i] = p.gn_gamma[i]; s_gb[TC_GN_MAX_COUT + i] = p.gn_beta[i]; }
+      }
+      named_bar_sync(6, 32 * TC_EPI_WARPS);
+    }
     if (kGN) {
       // ---- fused GroupNorm epilogue (ResBlock conv1 + out_layers.0/1): two passes over the accumulator stage.
       // Pass 1: every warp folds its rows to per-granule (sum, sum of squares), the eight warps combine them in a fixed
