@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(256, 2) attn_tc_kernel(const __grid_constant__
 // Shared memory: three 64 KB buffers rotate through the roles {Q|K of item j, later overlaid by P0 of item j},
 // {P1 of item j}, {Q|K of item j+1}: q_j = 2j mod 3 holds Q|K and P0, p_j = q_{j-1} holds P1; V has its own 32 KB.
 // 268 M exponentials per block at batch 1024 put the MUFU floor at ~0.06 ms, the DRAM floor (qkv read once, output
-// written once) at 0.083 ms; the one-CTA-per-tile kernel above takes 0.197 ms.
+// written once) at 0.083 ms; the one-CTA-per-tile kernel above takes 0.197 ms, this one 0.172-0.178 ms (where the rest
+// goes: profiles/r02_attn_persist_ncu.txt - waits for S / O, output-store back-pressure, 34 % issue utilisation of the
+// one-thread-per-row softmax; a polynomial exp on the FMA pipe and packed f32x2 math measured neutral).
 // ------------------------------------------------------------------------------------------------
 constexpr int AP_THREADS = 320;
 constexpr int AP_BUF = 65536;
